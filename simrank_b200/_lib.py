@@ -1,0 +1,99 @@
+"""ctypes binding of libsimrank_b200.so (the C ABI in include/simrank_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails this module
+raises.  PyTorch is used by the callers only to own device memory and streams; nothing
+here takes a torch type.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
+ABI_VERSION = 1
+
+SRK_I8_MID, SRK_I8_FINAL, SRK_I8_COUNTS = 0, 1, 2
+
+
+class EngineError(RuntimeError):
+    """A libsimrank_b200 call returned a non-zero status."""
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("coef", C.c_double),
+                ("evidence", C.c_void_p), ("ld_evidence", C.c_int64),
+                ("prior", C.c_void_p), ("ld_prior", C.c_int64),
+                ("lambda_", C.c_double),
+                ("s_old", C.c_void_p), ("ld_s_old", C.c_int64),
+                ("maxdiff", C.c_void_p), ("maxoff", C.c_void_p)]
+
+
+class RowBound(C.Structure):
+    """bound(r) = vec[r]*mul + add   (vec == NULL: add)."""
+    _fields_ = [("vec", C.c_void_p), ("mul", C.c_double), ("add", C.c_double)]
+
+    @classmethod
+    def of(cls, vec_ptr, mul, add):
+        rb = cls()
+        rb.vec, rb.mul, rb.add = vec_ptr, float(mul), float(add)
+        return rb
+
+
+class I8Args(C.Structure):
+    _fields_ = [("mode", C.c_int), ("ns", C.c_int),
+                ("R", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("in_planes", C.c_void_p), ("ld_in", C.c_int64), ("in_plane_stride", C.c_int64),
+                ("in_rowbound", RowBound),
+                ("A8", C.c_void_p), ("lda", C.c_int64),
+                ("diag_offset", C.c_int64), ("unit_diag", C.c_int),
+                ("g_row", C.c_void_p), ("g_col", C.c_void_p),
+                ("out_f64", C.c_void_p), ("ld_out", C.c_int64),
+                ("out_planes", C.c_void_p), ("ld_outp", C.c_int64), ("out_plane_stride", C.c_int64),
+                ("out_rowbound", RowBound),
+                ("epi", Epilogue)]
+
+
+_P, _I64, _INT, _DBL = C.c_void_p, C.c_int64, C.c_int, C.c_double
+# name -> (restype, argtypes); must list every symbol include/simrank_b200.h declares
+SYMBOLS = {
+    "srk_abi_version": (_INT, []),
+    "srk_last_error": (C.c_char_p, []),
+    "srk_device_cc": (_INT, []),
+    "srk_csr_half_f64": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, C.POINTER(Epilogue), _P]),
+    "srk_csr_evidence_counts": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P]),
+    "srk_csr_row_spread": (_INT, [_P, _P, _P, _I64, _P, _P]),
+    "srk_csr_to_dense_u8": (_INT, [_P, _P, _I64, _I64, _I64, _P, _I64, _P]),
+    "srk_slice_rows_f64": (_INT, [_P, _I64, _I64, _I64, C.POINTER(RowBound), _I64, _INT, _P, _I64, _I64, _P]),
+    "srk_i8_half": (_INT, [C.POINTER(I8Args), _P]),
+    "srk_i8_supported": (_INT, []),
+    "srk_topk_rows": (_INT, [_P, _I64, _I64, _I64, _INT, _P, _P, _P]),
+    "srk_set_identity_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m simrank_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.srk_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.srk_abi_version()} != {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().srk_last_error().decode("utf-8", "replace")
+        raise EngineError(f"{what or 'libsimrank_b200'} failed ({rc}): {msg}")

@@ -1,0 +1,407 @@
+// CSR (float64) half-products and the small preprocessing / retrieval kernels.
+//
+// The CSR half-product is the exact-arithmetic path of the engine and the one used when the
+// graph is too sparse/large for a dense operand (BASELINE cfg5).  It is bound by HBM for the
+// streamed operands (S read once per column panel, result written once) and by L2 for the row
+// gather; see DESIGN.md "K3".
+#include "common.cuh"
+
+namespace srk {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+// ------------------------------------------------------------------------------------------
+// OUT[c, i] = g[i] * sum_{m in N(i)} X[m, c]           (then the optional fused epilogue)
+//
+// CTA tile: TI output columns (graph rows i) x TC output rows (columns c of X).
+//   phase 1  each warp owns graph rows i0+w, i0+w+8, ...; it walks the neighbour list (indices
+//            fetched 32 at a time, broadcast with shuffles) and gathers X[m, c0 + lane + 32q],
+//            q<4: every load instruction is one fully used 256 B segment of a row of X.  All
+//            CTAs of a grid column share the same column panel of X (TC*8 B per row), which is
+//            what keeps the gather in L2.
+//   phase 2  the TI x TC tile is transposed through shared memory and written as 256 B rows of
+//            OUT, where the SimRank epilogue (C, evidence, prior, diagonal, max|dS|) is fused.
+constexpr int TI = 32;
+constexpr int TC = 128;
+constexpr int CSR_THREADS = 256;
+
+template <bool kFinal>
+__global__ void __launch_bounds__(CSR_THREADS)
+csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const double* __restrict__ g, int64_t row_begin, int64_t row_end,
+                const double* __restrict__ X, int64_t ldx, int64_t L,
+                double* __restrict__ OUT, int64_t ldo, EpilogueDev epi,
+                double* maxdiff, double* maxoff) {
+  __shared__ double tile[TC][TI + 1];
+  __shared__ double red[2][CSR_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i0 = row_begin + (int64_t)blockIdx.x * TI;
+  const int64_t c0 = (int64_t)blockIdx.y * TC;
+
+  for (int il = warp; il < TI; il += CSR_THREADS / 32) {
+    const int64_t i = i0 + il;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < row_end) {
+      const int64_t beg = indptr[i], end = indptr[i + 1];
+      for (int64_t e = beg; e < end; e += 32) {
+        const int cnt = (int)min((int64_t)32, end - e);
+        const int my = (lane < cnt) ? indices[e + lane] : 0;
+        int t = 0;
+        for (; t + 4 <= cnt; t += 4) {          // 4 neighbours in flight, summed in list order
+          double v[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double* row = X + (int64_t)__shfl_sync(0xffffffffu, my, t + u) * ldx + c0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int64_t c = lane + 32 * q;
+              v[u][q] = (c0 + c < L) ? __ldg(row + c) : 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += v[u][q];
+        }
+        for (; t < cnt; ++t) {
+          const double* row = X + (int64_t)__shfl_sync(0xffffffffu, my, t) * ldx + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int64_t c = lane + 32 * q;
+            acc[q] += (c0 + c < L) ? __ldg(row + c) : 0.0;
+          }
+        }
+      }
+      const double gi = g[i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] *= gi;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tile[lane + 32 * q][il] = acc[q];
+  }
+  __syncthreads();
+
+  double dmax = 0.0, omax = 0.0;
+  const int64_t i = i0 + lane;
+  for (int cl = warp; cl < TC; cl += CSR_THREADS / 32) {
+    const int64_t r = c0 + cl;
+    if (r >= L || i >= row_end) continue;
+    double v = tile[cl][lane];
+    if (kFinal) {
+      v *= epi.coef;
+      if (epi.evidence) v *= evidence_factor(epi.evidence[r * epi.ld_evidence + i]);
+      if (epi.prior) v = (1.0 - epi.lambda) * v + epi.lambda * epi.prior[r * epi.ld_prior + i];
+      if (r == i) v = 1.0; else if (v > omax) omax = v;
+      if (epi.s_old) {
+        const double d = fabs(v - epi.s_old[r * epi.ld_s_old + i]);
+        if (d > dmax) dmax = d;                  // NaN compares false: ignored like SimRank.py:74
+      }
+    }
+    OUT[r * ldo + i] = v;
+  }
+  if (kFinal) {
+    dmax = warp_max(dmax);
+    omax = warp_max(omax);
+    if (lane == 0) { red[0][warp] = dmax; red[1][warp] = omax; }
+    __syncthreads();
+    if (warp == 0) {
+      dmax = (lane < CSR_THREADS / 32) ? red[0][lane] : 0.0;
+      omax = (lane < CSR_THREADS / 32) ? red[1][lane] : 0.0;
+      dmax = warp_max(dmax);
+      omax = warp_max(omax);
+      if (lane == 0) {
+        if (maxdiff && dmax > 0.0) atomic_max_nonneg(maxdiff, dmax);
+        if (maxoff && omax > 0.0) atomic_max_nonneg(maxoff, omax);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// cnt[i, j] = |N(i) & N(j)| by merging the two sorted neighbour lists; one thread per pair.
+__global__ void evidence_counts_kernel(const int64_t* __restrict__ indptr,
+                                       const int32_t* __restrict__ indices,
+                                       const uint8_t* __restrict__ dead, int64_t M,
+                                       int64_t row_begin, int64_t row_end,
+                                       uint8_t* __restrict__ counts, int64_t ldc) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = row_begin + (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= row_end || j >= M) return;
+  unsigned c = 0;
+  if (!(dead && (dead[i] || dead[j]))) {
+    int64_t a = indptr[i], ae = indptr[i + 1], b = indptr[j], be = indptr[j + 1];
+    while (a < ae && b < be) {
+      const int32_t x = indices[a], y = indices[b];
+      c += (x == y);
+      a += (x <= y);
+      b += (y <= x);
+    }
+  }
+  counts[(i - row_begin) * ldc + j] = (uint8_t)min(c, 255u);
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-pass sample variance of the nonzero entries of each CSR row (pandas nanvar, ddof=1).
+__global__ void row_spread_kernel(const int64_t* __restrict__ indptr, const double* __restrict__ vals,
+                                  const double* __restrict__ g, int64_t M, double* __restrict__ spread) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int64_t beg = indptr[i], end = indptr[i + 1];
+  double sum = 0.0;
+  int64_t cnt = 0;
+  for (int64_t e = beg; e < end; ++e) {
+    const double x = vals ? vals[e] : g[i];
+    if (x != 0.0 && x == x) { sum += x; ++cnt; }
+  }
+  double var = 0.0;
+  if (cnt >= 2) {
+    const double mean = sum / (double)cnt;
+    double sq = 0.0;
+    for (int64_t e = beg; e < end; ++e) {
+      const double x = vals ? vals[e] : g[i];
+      if (x != 0.0 && x == x) { const double d = mean - x; sq += d * d; }
+    }
+    var = sq / (double)(cnt - 1);
+    if (var != var) var = 0.0;
+  }
+  spread[i] = exp(-var);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void csr_scatter_u8_kernel(const int64_t* __restrict__ indptr,
+                                      const int32_t* __restrict__ indices, int64_t row_begin,
+                                      int64_t row_end, int64_t K, uint8_t* __restrict__ A8, int64_t lda) {
+  const int64_t i = row_begin + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x & 31;
+  if (i >= row_end) return;
+  for (int64_t e = indptr[i] + lane; e < indptr[i + 1]; e += 32) {
+    const int64_t c = indices[e];
+    if (c < K) A8[(i - row_begin) * lda + c] = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// f64 -> NS uint8 planes; one thread per 16 consecutive columns (16 B store per plane).
+template <int NS>
+__global__ void slice_rows_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int64_t K,
+                                  const srk_rowbound rowbound, int64_t zero_diag_offset,
+                                  uint8_t* __restrict__ planes, int64_t ldp, int64_t plane_stride) {
+  const int64_t chunks = (ldp + 15) / 16;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * chunks) return;
+  const int64_t r = t / chunks, k0 = (t % chunks) * 16;
+  const double qmax = (double)((1ull << (8 * NS)) - 1ull);
+  const double b = row_bound(rowbound, r);
+  const double scale = (b > 0.0) ? (qmax + 1.0) / b : 0.0;
+  uint32_t w[NS][4];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) w[s][x] = 0u;
+#pragma unroll
+  for (int x = 0; x < 16; ++x) {
+    const int64_t k = k0 + x;
+    double v = (k < K) ? V[r * ldv + k] : 0.0;
+    if (zero_diag_offset >= 0 && k == r + zero_diag_offset) v = 0.0;
+    double q = rint(v * scale);
+    if (!(q > 0.0)) q = 0.0;                 // negatives and NaN -> 0
+    if (q > qmax) q = qmax;
+    const unsigned long long qi = (unsigned long long)q;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      w[s][x >> 2] |= (uint32_t)((qi >> (8 * (NS - 1 - s))) & 0xffull) << (8 * (x & 3));
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    *reinterpret_cast<uint4*>(planes + s * plane_stride + r * ldp + k0) =
+        make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-wise top-k by k rounds of arg-max in the total order (value desc, column asc); NaN last.
+constexpr int TOPK_THREADS = 256;
+__device__ __forceinline__ bool topk_before(double va, int ia, double vb, int ib) {
+  // true when (va, ia) ranks strictly before (vb, ib)
+  const bool na = va != va, nb = vb != vb;
+  if (na != nb) return nb;
+  if (!na && va != vb) return va > vb;
+  return ia < ib;
+}
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_rows_kernel(const double* __restrict__ S, int64_t lds, int64_t n, int k,
+                 int32_t* __restrict__ idx, double* __restrict__ vals) {
+  __shared__ double sv[TOPK_THREADS / 32];
+  __shared__ int si[TOPK_THREADS / 32];
+  __shared__ double last_v;
+  __shared__ int last_i;
+  const double* row = S + (int64_t)blockIdx.x * lds;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { last_i = -1; last_v = 0.0; }
+  __syncthreads();
+  for (int round = 0; round < k; ++round) {
+    const int li = last_i;
+    const double lv = last_v;
+    double bv = 0.0;
+    int bi = -1;
+    for (int64_t c = threadIdx.x; c < n; c += TOPK_THREADS) {
+      const double v = row[c];
+      if (li >= 0 && !topk_before(lv, li, v, (int)c)) continue;   // already emitted
+      if (bi < 0 || topk_before(v, (int)c, bv, bi)) { bv = v; bi = (int)c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || topk_before(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = (lane < TOPK_THREADS / 32) ? sv[lane] : 0.0;
+      bi = (lane < TOPK_THREADS / 32) ? si[lane] : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || topk_before(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        idx[(int64_t)blockIdx.x * k + round] = bi;
+        vals[(int64_t)blockIdx.x * k + round] = bv;
+        last_i = bi; last_v = bv;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void set_identity_kernel(double* __restrict__ S, int64_t lds, int64_t R, int64_t n,
+                                    int64_t diag_offset) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * n) return;
+  const int64_t r = t / n, c = t % n;
+  S[r * lds + c] = (c == r + diag_offset) ? 1.0 : 0.0;
+}
+
+}  // namespace srk
+
+// =============================================================================== C ABI
+using namespace srk;
+
+extern "C" int srk_abi_version(void) { return SRK_ABI_VERSION; }
+extern "C" const char* srk_last_error(void) { return error_buffer(); }
+
+extern "C" int srk_device_cc(void) {
+  int dev = 0, major = 0, minor = 0;
+  SRK_CUDA_OK(cudaGetDevice(&dev));
+  SRK_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  SRK_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return major * 10 + minor;
+}
+
+extern "C" int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double* g,
+                                int64_t M, int64_t row_begin, int64_t row_end, const double* X,
+                                int64_t ldx, int64_t L, double* OUT, int64_t ldo,
+                                const srk_epilogue* final_epi, void* stream) {
+  SRK_REQUIRE(indptr && indices && g && X && OUT, "null pointer");
+  SRK_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= M, "row range");
+  SRK_REQUIRE(L >= 0 && ldx >= L && ldo >= row_end, "leading dimensions");
+  if (row_end == row_begin || L == 0) return SRK_OK;
+  const int64_t gx = (row_end - row_begin + TI - 1) / TI, gy = (L + TC - 1) / TC;
+  SRK_REQUIRE(gy <= 65535, "too many column panels");
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (final_epi) {
+    csr_half_kernel<true><<<grid, CSR_THREADS, 0, st>>>(indptr, indices, g, row_begin, row_end, X, ldx,
+                                                        L, OUT, ldo, to_dev(*final_epi),
+                                                        final_epi->maxdiff, final_epi->maxoff);
+  } else {
+    EpilogueDev none = {};
+    csr_half_kernel<false><<<grid, CSR_THREADS, 0, st>>>(indptr, indices, g, row_begin, row_end, X, ldx,
+                                                         L, OUT, ldo, none, nullptr, nullptr);
+  }
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_csr_evidence_counts(const int64_t* indptr, const int32_t* indices,
+                                       const uint8_t* dead, int64_t M, int64_t row_begin,
+                                       int64_t row_end, uint8_t* counts, int64_t ldc, void* stream) {
+  SRK_REQUIRE(indptr && indices && counts, "null pointer");
+  SRK_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= M && ldc >= M, "shape");
+  if (row_end == row_begin) return SRK_OK;
+  dim3 block(32, 8);
+  dim3 grid((unsigned)((M + 31) / 32), (unsigned)((row_end - row_begin + 7) / 8));
+  SRK_REQUIRE(grid.y <= 65535, "row shard too tall for one launch");
+  evidence_counts_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(indptr, indices, dead, M, row_begin,
+                                                                  row_end, counts, ldc);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_csr_row_spread(const int64_t* indptr, const double* vals, const double* g,
+                                  int64_t M, double* spread, void* stream) {
+  SRK_REQUIRE(indptr && spread && (vals || g), "null pointer");
+  if (M == 0) return SRK_OK;
+  row_spread_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(indptr, vals, g, M, spread);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_csr_to_dense_u8(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
+                                   int64_t row_end, int64_t K, uint8_t* A8, int64_t lda, void* stream) {
+  SRK_REQUIRE(indptr && indices && A8, "null pointer");
+  SRK_REQUIRE(row_begin <= row_end && lda >= K, "shape");
+  if (row_end == row_begin) return SRK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  SRK_CUDA_OK(cudaMemsetAsync(A8, 0, (size_t)(row_end - row_begin) * lda, st));
+  const int64_t threads = (row_end - row_begin) * 32;
+  csr_scatter_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(indptr, indices, row_begin,
+                                                                          row_end, K, A8, lda);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_slice_rows_f64(const double* V, int64_t ldv, int64_t R, int64_t K,
+                                  const srk_rowbound* rowbound, int64_t zero_diag_offset, int ns,
+                                  uint8_t* planes, int64_t ldp, int64_t plane_stride, void* stream) {
+  SRK_REQUIRE(V && rowbound && planes, "null pointer");
+  SRK_REQUIRE(ldp % 16 == 0 && ldp >= K && ldv >= K, "ldp must be a multiple of 16 and >= K");
+  SRK_REQUIRE(((uintptr_t)planes % 16) == 0 && plane_stride % 16 == 0, "planes must be 16-byte aligned");
+  if (R == 0 || K == 0) return SRK_OK;
+  const int64_t threads = R * ((ldp + 15) / 16);
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ns) {
+    case 1: slice_rows_kernel<1><<<blocks, 256, 0, st>>>(V, ldv, R, K, *rowbound, zero_diag_offset, planes, ldp, plane_stride); break;
+    case 2: slice_rows_kernel<2><<<blocks, 256, 0, st>>>(V, ldv, R, K, *rowbound, zero_diag_offset, planes, ldp, plane_stride); break;
+    case 3: slice_rows_kernel<3><<<blocks, 256, 0, st>>>(V, ldv, R, K, *rowbound, zero_diag_offset, planes, ldp, plane_stride); break;
+    case 4: slice_rows_kernel<4><<<blocks, 256, 0, st>>>(V, ldv, R, K, *rowbound, zero_diag_offset, planes, ldp, plane_stride); break;
+    default: return srk::fail(SRK_ERR_INVALID, "invalid argument: %s", "ns must be 1..4");
+  }
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_topk_rows(const double* S, int64_t lds, int64_t R, int64_t n, int k, int32_t* idx,
+                             double* vals, void* stream) {
+  SRK_REQUIRE(S && idx && vals, "null pointer");
+  SRK_REQUIRE(k >= 0 && k <= n && lds >= n && n < (1ll << 31), "shape");
+  if (R == 0 || k == 0) return SRK_OK;
+  topk_rows_kernel<<<(unsigned)R, TOPK_THREADS, 0, (cudaStream_t)stream>>>(S, lds, n, k, idx, vals);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_set_identity_f64(double* S, int64_t lds, int64_t R, int64_t n, int64_t diag_offset,
+                                    void* stream) {
+  SRK_REQUIRE(S && lds >= n, "shape");
+  if (R == 0 || n == 0) return SRK_OK;
+  const int64_t t = R * n;
+  set_identity_kernel<<<(unsigned)((t + 255) / 256), 256, 0, (cudaStream_t)stream>>>(S, lds, R, n, diag_offset);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}

@@ -1,0 +1,123 @@
+"""Glue between the drop-in classes (SimRank/SimRank.py) and the device engine."""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import engine as _eng
+from .engine import FitInfo, run_loop  # noqa: F401  (re-exported for SimRank/SimRank.py)
+from .graph import HostOperator, build_bipartite, build_directed  # noqa: F401
+
+
+def _device_op(op: HostOperator, device=None) -> _eng.DeviceOperator:
+    dev = _eng.require_cuda(device)
+    cached = getattr(op, "_dev", None)
+    if cached is None or cached.device != dev:
+        cached = _eng.DeviceOperator(op, dev)
+        op._dev = cached
+    return cached
+
+
+class WeightOperator(HostOperator):
+    """SimRank++ weight matrix ``W = diag(spread) * G`` kept as an operator.  ``np.asarray(W)``
+    materialises the dense ndarray the reference stores in ``self.Weight`` (SimRank.py:333)."""
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.to_dense()
+        return out if dtype is None else out.astype(dtype)
+
+    @property
+    def shape(self):
+        return (self.M, self.K)
+
+
+def weight(G: HostOperator, device=None) -> WeightOperator:
+    """``_cal_Weight`` (SimRank.py:322-337): spread from the row-variance kernel, then an O(n)
+    rescale of the row factors instead of the reference's n^3 ``np.dot(spread, G)``."""
+    dop = _device_op(G, device)
+    spread = dop.row_spread().cpu().numpy()
+    W = WeightOperator(G.M, G.K, G.indptr, G.indices, G.g * spread, G.deg)
+    W._dev = dop.with_scale(spread)
+    W.spread = spread
+    return W
+
+
+class EvidenceMatrix:
+    """Evidence ``1 - 0.5 ** (A A^T)`` (SimRank.py:315-316) held on the device as uint8
+    common-neighbour counts (a count >= 54 already gives exactly 1.0 in float64).
+    ``np.asarray(E)`` materialises the float64 ndarray of the reference."""
+
+    def __init__(self, counts: torch.Tensor, n: int):
+        self.counts, self.n = counts, n
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def __array__(self, dtype=None, copy=None):
+        cnt = self.counts[:, : self.n].cpu().numpy().astype(np.int64)
+        out = 1 - 0.5 ** cnt
+        return out if dtype is None else out.astype(dtype)
+
+
+def evidence(G: HostOperator, device=None, mode: str = "auto") -> EvidenceMatrix:
+    dop = _device_op(G, device)
+    return EvidenceMatrix(dop.evidence_counts(mode), G.M)
+
+
+def _prior_tensor(prior, n, device):
+    if prior is None:
+        return None
+    arr = np.ascontiguousarray(np.asarray(prior, dtype=np.float64))
+    if arr.shape != (n, n):
+        raise ValueError(f"prior must have shape {(n, n)}, got {arr.shape}")
+    return torch.from_numpy(arr).to(device)
+
+
+def _mode_with_prior(mode, *priors):
+    # the fixed-point path needs S >= 0; a negative prior entry can break that
+    if any(p is not None and np.asarray(p).min() < 0 for p in priors):
+        return "csr"
+    return mode
+
+
+def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mode=None, device=None, slices=3):
+    dop = _device_op(op, device)
+    ev = evidence.counts if evidence is not None else None
+    pr = _prior_tensor(prior, op.M, dop.device)
+    return _eng.DirectedSolver(dop, C, ev, pr, lbd, _mode_with_prior(mode, prior), slices)
+
+
+def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=None, evidence2=None, prior1=None,
+                     prior2=None, lbd1=0.0, lbd2=0.0, mode=None, device=None, slices=3):
+    d12, d21 = _device_op(op12, device), _device_op(op21, device)
+    e1 = evidence1.counts if evidence1 is not None else None
+    e2 = evidence2.counts if evidence2 is not None else None
+    p1 = _prior_tensor(prior1, op12.M, d12.device)
+    p2 = _prior_tensor(prior2, op21.M, d21.device)
+    return _eng.BipartiteSolver(d12, d21, C1, C2, e1, e2, p1, p2, lbd1, lbd2,
+                                _mode_with_prior(mode, prior1, prior2), slices)
+
+
+class Result:
+    """Device-resident result of a fit: similarity matrices + their row labels."""
+
+    def __init__(self, mats, labels):
+        self.mats, self.labels = mats, labels
+
+    def frame(self, which: int = 0) -> pd.DataFrame:
+        """The labelled DataFrame the reference returns (SimRank.py:141, 303)."""
+        S = self.mats[which]
+        host = torch.empty(S.shape, dtype=S.dtype, pin_memory=S.numel() >= (1 << 20))
+        host.copy_(S)
+        lab = self.labels[which]
+        return pd.DataFrame(host.numpy(), index=lab, columns=lab, copy=False)
+
+    def top_k(self, k: int, which: int = 0):
+        S = self.mats[which]
+        idx, vals = _eng.topk_rows(S, k)
+        lab = np.asarray(self.labels[which], dtype=object)
+        idx_h = idx.cpu().numpy()
+        return (pd.DataFrame(lab[idx_h], index=self.labels[which]),
+                pd.DataFrame(vals.cpu().numpy(), index=self.labels[which]))

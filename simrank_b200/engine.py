@@ -1,0 +1,325 @@
+"""Device-side SimRank iteration engine (single GPU; the row-sharded variant is in dist.py).
+
+Host orchestration of the kernels behind include/simrank_b200.h.  PyTorch owns device
+memory and streams; every numeric step is a hand-written sm_100a kernel reached through
+the C ABI -- there is no torch/numpy arithmetic on the hot path and no CPU fallback.
+
+One update of the reference loop (SimRank.py:138-140)
+
+    old_S = deepcopy(new_S); new_S = C * G.dot(new_S).dot(G.T); fill_diagonal(new_S, 1)
+
+plus the reduction behind ``_converged`` (SimRank.py:74) is two kernel launches here:
+
+  csr mode   T = (G S)^T                     srk_csr_half_f64   (gather, transposed store)
+             S = epilogue((G T)^T)           srk_csr_half_f64   (fused epilogue, in place)
+  i8 mode    U = A S  (re-quantised planes)  srk_i8_half MID    (tcgen05 kind::i8)
+             S = epilogue(g g^T o (U A^T))   srk_i8_half FINAL  (fused epilogue, in place,
+                                                                 + planes of the new S)
+
+S is updated in place: each epilogue thread reads S_old[r, c] for max|dS| and then writes
+S_new[r, c]; nothing else reads S during the second half.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import HostOperator
+
+_NS_DEFAULT = 3
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("simrank_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _lib.load()
+    return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+
+
+# --------------------------------------------------------------------------- operators
+class DeviceOperator:
+    """``G = diag(g) * A`` resident on the GPU: CSR always, dense uint8 A on demand."""
+
+    def __init__(self, host: HostOperator, device):
+        self.host = host
+        self.M, self.K = host.M, host.K
+        self.device = device
+        self.indptr = torch.from_numpy(host.indptr).to(device)
+        self.indices = torch.from_numpy(host.indices).to(device)
+        self.g_host = np.ascontiguousarray(host.g)
+        self.g = torch.from_numpy(self.g_host).to(device)
+        self.dead = torch.from_numpy(host.dead).to(device)
+        self._a8 = None
+
+    def with_scale(self, factor: np.ndarray) -> "DeviceOperator":
+        """``diag(factor) * G``: same pattern, rescaled rows (SimRank++ W = diag(spread) G,
+        SimRank.py:333 -- an n^3 dgemm there, an O(n) host product here)."""
+        other = object.__new__(DeviceOperator)
+        other.__dict__.update(self.__dict__)
+        other.g_host = np.ascontiguousarray(self.g_host * np.asarray(factor, dtype=np.float64))
+        other.g = torch.from_numpy(other.g_host).to(self.device)
+        return other
+
+    @property
+    def lda(self) -> int:
+        return _round_up(max(self.K, 1), 128)
+
+    def dense_u8(self) -> torch.Tensor:
+        if self._a8 is None:
+            a8 = torch.empty((self.M, self.lda), dtype=torch.uint8, device=self.device)
+            _lib.check(_lib.load().srk_csr_to_dense_u8(_ptr(self.indptr), _ptr(self.indices), 0, self.M, self.K,
+                                                       _ptr(a8), self.lda, _stream()), "srk_csr_to_dense_u8")
+            self._a8 = a8
+        return self._a8
+
+    def row_spread(self, vals: torch.Tensor | None = None) -> torch.Tensor:
+        """exp(-var) of the nonzeros of each row (SimRank.py:326-332)."""
+        out = torch.empty(self.M, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.load().srk_csr_row_spread(_ptr(self.indptr), _ptr(vals), _ptr(self.g), self.M, _ptr(out),
+                                                  _stream()), "srk_csr_row_spread")
+        return out
+
+    def evidence_counts(self, mode: str = "auto") -> torch.Tensor:
+        """uint8 common-neighbour counts (clipped at 255) = the integer matmul of SimRank.py:315."""
+        ld = _round_up(max(self.M, 1), 16)
+        cnt = torch.empty((self.M, ld), dtype=torch.uint8, device=self.device)
+        lib = _lib.load()
+        # rows with G>0 False (g <= 0) must count as empty: only the CSR kernel knows `dead`
+        has_dead = bool((self.host.dead.astype(bool) & (self.host.deg > 0)).any())
+        use_i8 = not has_dead and (mode == "i8" or (mode == "auto" and lib.srk_i8_supported() and
+                                                    self.M >= 2048 and self.M * self.lda <= (8 << 30)))
+        if use_i8:
+            a8 = self.dense_u8()
+            args = _lib.I8Args()
+            args.mode, args.ns = _lib.SRK_I8_COUNTS, 1
+            args.R, args.N, args.K = self.M, self.M, self.K
+            args.in_planes, args.ld_in, args.in_plane_stride = a8.data_ptr(), self.lda, a8.numel()
+            args.A8, args.lda = a8.data_ptr(), self.lda
+            args.out_planes, args.ld_outp, args.out_plane_stride = cnt.data_ptr(), ld, cnt.numel()
+            _lib.check(lib.srk_i8_half(C.byref(args), _stream()), "srk_i8_half(COUNTS)")
+        else:
+            _lib.check(lib.srk_csr_evidence_counts(_ptr(self.indptr), _ptr(self.indices), _ptr(self.dead), self.M,
+                                                   0, self.M, _ptr(cnt), ld, _stream()), "srk_csr_evidence_counts")
+        return cnt
+
+
+def choose_mode(op: HostOperator, requested: str | None = None) -> str:
+    """'csr' (exact f64 gather path) or 'i8' (tcgen05 fixed-point path)."""
+    mode = (requested or os.environ.get("SIMRANK_B200_MODE", "auto")).lower()
+    if mode in ("csr", "i8"):
+        return mode
+    if mode != "auto":
+        raise ValueError(f"unknown mode {mode!r}")
+    ok = bool(_lib.load().srk_i8_supported()) and bool(np.all(op.g >= 0)) and bool(np.all(np.isfinite(op.g)))
+    dense_bytes = op.M * _round_up(op.K, 128)
+    density = op.nnz / max(1, op.M * op.K)
+    return "i8" if ok and min(op.M, op.K) >= 1024 and dense_bytes <= (16 << 30) and density >= 1.0 / 1024 else "csr"
+
+
+# --------------------------------------------------------------------------- one similarity matrix
+class _Half:
+    """State for updating ONE similarity matrix S_out (n_out x n_out) from S_in (n_in x n_in)
+    through ``op`` (n_out x n_in):  S_out <- epilogue(coef * G S_in G^T).  The directed classes
+    use one instance with S_in is S_out; the bipartite classes use two (SimRank.py:297-302)."""
+
+    def __init__(self, op: DeviceOperator, coef: float, mode: str, ns: int, evidence=None, prior=None, lbd=0.0):
+        self.op, self.coef, self.mode, self.ns = op, float(coef), mode, ns
+        self.n_out, self.n_in = op.M, op.K
+        dev = op.device
+        self.ld = _round_up(max(self.n_out, 1), 16)
+        self.S = torch.empty((self.n_out, self.ld), dtype=torch.float64, device=dev)
+        lib = _lib.load()
+        _lib.check(lib.srk_set_identity_f64(_ptr(self.S), self.ld, self.n_out, self.n_out, 0, _stream()),
+                   "srk_set_identity_f64")
+        self.evidence, self.prior, self.lbd = evidence, prior, float(lbd)
+        self.scal = torch.zeros(2, dtype=torch.float64, device=dev)        # [maxdiff, maxoff]
+        self.maxoff = 0.0                                                  # max off-diagonal of current S
+        if mode == "csr":
+            self.ldt = _round_up(max(self.n_out, 1), 16)
+            self.T = torch.empty((self.n_in, self.ldt), dtype=torch.float64, device=dev)
+        else:
+            host = op.host
+            self.rho = op.g_host * host.deg                                # row sums of G
+            self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
+            self.prior_max = float(prior.max()) if prior is not None else 0.0
+            self.ldp = _round_up(max(self.n_out, 1), 128)                  # planes of S_out
+            self.ldu = _round_up(max(self.n_in, 1), 128)                   # planes of U (n_out x n_in)
+            self.planes = torch.zeros((ns, self.n_out, self.ldp), dtype=torch.uint8, device=dev)   # S_off = 0
+            self.planes_U = torch.empty((ns, self.n_out, self.ldu), dtype=torch.uint8, device=dev)
+            self.a8 = op.dense_u8()
+            self.deg_dev = torch.from_numpy(host.deg.astype(np.float64)).to(dev)
+            self.rho_dev = torch.from_numpy(np.ascontiguousarray(self.rho)).to(dev)
+            # bound(r) of the current planes of S_off as (mul, add) over rho, and its maximum
+            self.bound_S = (0.0, 1.0)                                      # planes are all zero: any bound
+            self.bound_S_max = 1.0
+
+    # -- epilogue description shared by both modes
+    def _epilogue(self) -> _lib.Epilogue:
+        e = _lib.Epilogue()
+        e.coef = self.coef
+        if self.evidence is not None:
+            e.evidence, e.ld_evidence = self.evidence.data_ptr(), self.evidence.stride(0)
+        if self.prior is not None:
+            e.prior, e.ld_prior, e.lambda_ = self.prior.data_ptr(), self.prior.stride(0), self.lbd
+        e.s_old, e.ld_s_old = self.S.data_ptr(), self.ld
+        e.maxdiff = self.scal.data_ptr()
+        e.maxoff = self.scal.data_ptr() + 8
+        return e
+
+    def update(self, src: "_Half") -> None:
+        """Launch the two half-products (asynchronous).  ``src`` holds S_in (its S / planes)."""
+        lib = _lib.load()
+        self.scal.zero_()
+        if self.mode == "csr":
+            op = self.op
+            _lib.check(lib.srk_csr_half_f64(_ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M,
+                                            _ptr(src.S), src.ld, self.n_in, _ptr(self.T), self.ldt, None, _stream()),
+                       "srk_csr_half_f64(first)")
+            epi = self._epilogue()
+            _lib.check(lib.srk_csr_half_f64(_ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M,
+                                            _ptr(self.T), self.ldt, self.n_out, _ptr(self.S), self.ld, C.byref(epi),
+                                            _stream()), "srk_csr_half_f64(second)")
+            return
+        # ---- i8: a-priori bounds of the two results, as affine forms over constant node vectors.
+        # The planes of S_in were cut with src.bound_S; the ACTUAL off-diagonal maximum of S_in is
+        # known from its epilogue (src.maxoff) and tightens everything derived from it.
+        guard = 1.0 + 2.0 ** -20          # keeps values that attain a bound exactly off the clip
+        s_off = min(src.bound_S_max, src.maxoff * (1.0 + 1e-6) + src.bound_S_max * 2.0 ** -23)
+        # U[j, r] = A[j, r] + sum_m A[j, m] S_off[r, m]  <=  1 + deg_j * max(S_off)
+        bound_U = _lib.RowBound.of(self.deg_dev.data_ptr(), s_off * guard, guard)
+        # S_new[r, j] <= (1-lbd) * coef * rho_r * rho_max * max(1, max S_in)  +  lbd * max(prior)
+        blend = (1.0 - self.lbd) if self.prior is not None else 1.0
+        mul = blend * self.coef * self.rho_max * max(1.0, s_off) * guard
+        add = self.lbd * self.prior_max * guard if self.prior is not None else 0.0
+        bound_new = _lib.RowBound.of(self.rho_dev.data_ptr(), mul, add)
+
+        a = _lib.I8Args()
+        a.mode, a.ns = _lib.SRK_I8_MID, self.ns
+        a.R, a.N, a.K = src.n_out, self.n_out, self.n_in          # planes of S_in: n_in x n_in
+        a.in_planes, a.ld_in, a.in_plane_stride = src.planes.data_ptr(), src.ldp, src.planes.stride(0)
+        a.in_rowbound = _lib.RowBound.of(src.rho_dev.data_ptr(), *src.bound_S)
+        a.A8, a.lda = self.a8.data_ptr(), self.op.lda
+        a.diag_offset, a.unit_diag = 0, 1
+        a.out_planes, a.ld_outp, a.out_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
+        a.out_rowbound = bound_U
+        _lib.check(lib.srk_i8_half(C.byref(a), _stream()), "srk_i8_half(MID)")
+
+        b = _lib.I8Args()
+        b.mode, b.ns = _lib.SRK_I8_FINAL, self.ns
+        b.R, b.N, b.K = self.n_out, self.n_out, self.n_in
+        b.in_planes, b.ld_in, b.in_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
+        b.in_rowbound = bound_U
+        b.A8, b.lda = self.a8.data_ptr(), self.op.lda
+        b.diag_offset, b.unit_diag = 0, 0
+        b.g_row = b.g_col = self.op.g.data_ptr()
+        b.out_f64, b.ld_out = self.S.data_ptr(), self.ld
+        b.out_planes, b.ld_outp, b.out_plane_stride = self.planes.data_ptr(), self.ldp, self.planes.stride(0)
+        b.out_rowbound = bound_new
+        b.epi = self._epilogue()
+        _lib.check(lib.srk_i8_half(C.byref(b), _stream()), "srk_i8_half(FINAL)")
+        self._pending_bound = ((mul, add), mul * self.rho_max + add)
+
+    def finish(self) -> float:
+        """Read back max|dS| (host sync) and commit the bounds of the new S."""
+        maxdiff, maxoff = self.scal.tolist()
+        self.maxoff = maxoff
+        if self.mode == "i8":
+            self.bound_S, self.bound_S_max = self._pending_bound
+        return maxdiff
+
+    def result(self) -> torch.Tensor:
+        return self.S[:, : self.n_out]
+
+
+@dataclass
+class FitInfo:
+    applied: int          # updates performed (== k of "Converged at iteration k")
+    converged: bool
+    last_maxdiff: tuple
+    mode: str
+
+
+class DirectedSolver:
+    """``S <- [E o] C * W S W^T [blended with a prior]; diag <- 1`` (SimRank.py:139, :361, :453)."""
+
+    def __init__(self, op: DeviceOperator, C_: float, evidence=None, prior=None, lbd=0.0, mode=None, ns=_NS_DEFAULT):
+        self.mode = choose_mode(op.host, mode)
+        self.half = _Half(op, C_, self.mode, ns, evidence, prior, lbd)
+
+    def step(self) -> float:
+        self.half.update(self.half)
+        return self.half.finish()
+
+    @property
+    def S(self) -> torch.Tensor:
+        return self.half.result()
+
+
+class BipartiteSolver:
+    """Gauss-Seidel alternation of SimRank.py:297-302 (and :419-424, :487-492)."""
+
+    def __init__(self, op12: DeviceOperator, op21: DeviceOperator, C1: float, C2: float, evidence1=None,
+                 evidence2=None, prior1=None, prior2=None, lbd1=0.0, lbd2=0.0, mode=None, ns=_NS_DEFAULT):
+        m1, m2 = choose_mode(op12.host, mode), choose_mode(op21.host, mode)
+        self.mode = m1 if m1 == m2 else "csr"
+        self.h1 = _Half(op12, C1, self.mode, ns, evidence1, prior1, lbd1)     # S1 from S2 through G12
+        self.h2 = _Half(op21, C2, self.mode, ns, evidence2, prior2, lbd2)     # S2 from S1 through G21
+
+    def step(self):
+        self.h1.update(self.h2)
+        d1 = self.h1.finish()
+        self.h2.update(self.h1)            # uses the NEW S1 (SimRank.py:301)
+        d2 = self.h2.finish()
+        return d1, d2
+
+    @property
+    def S1(self) -> torch.Tensor:
+        return self.h1.result()
+
+    @property
+    def S2(self) -> torch.Tensor:
+        return self.h2.result()
+
+
+def run_loop(step, iterations: int, eps: float, pair: bool, on_iteration=None):
+    """The reference's loop skeleton (SimRank.py:129-140 / 288-302): test convergence BEFORE each
+    update, using max|dS| of the previous update (``|I - 0|`` = 1 before the first)."""
+    last = (1.0, 1.0) if pair else (1.0,)
+    applied, conv = 0, False
+    for it in range(iterations):
+        if all(not (d > eps) for d in last):
+            conv = True
+            break
+        if on_iteration is not None:
+            on_iteration(it)
+        out = step()
+        last = tuple(out) if pair else (out,)
+        applied += 1
+    return applied, conv, last
+
+
+def topk_rows(S: torch.Tensor, k: int):
+    """Row-wise top-k (stable, ties -> lower column).  -> (idx int32 [R,k], vals f64 [R,k])."""
+    R, n = S.shape
+    idx = torch.empty((R, k), dtype=torch.int32, device=S.device)
+    vals = torch.empty((R, k), dtype=torch.float64, device=S.device)
+    _lib.check(_lib.load().srk_topk_rows(_ptr(S), S.stride(0), R, n, k, _ptr(idx), _ptr(vals), _stream()),
+               "srk_topk_rows")
+    return idx, vals
