@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Headline benchmark: SimRank iterations/sec at n = 32768 (BASELINE.json configs[3], "cfg4").
+
+    python bench.py --gpus N --steps K --warmup W            this engine (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    the reference's CPU path (numpy f64)
+
+A step is ONE iteration of ``S <- C * G S G^T; diag <- 1`` with the fused max|dS| reduction and
+its read-back (SimRank.py:130-140), on the synthetic dense-regime directed graph of
+simrank_b200/synth.py (n = 32768, m = 2097152, seed 4).  Prints one JSON line (see README /
+DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "simrank_iterations_per_sec_n32768"
+UNIT = "iter/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=32768, help="nodes (default: the BASELINE cfg4 size)")
+    ap.add_argument("--mean-degree", type=int, default=64)
+    ap.add_argument("--mode", default="i8", choices=["i8", "csr"], help="dense tensor-core chain (graded) or CSR SpMM")
+    ap.add_argument("--slices", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload(args):
+    from simrank_b200 import graph, synth
+    n, m = args.n, args.n * args.mean_degree
+    frm, to = synth.directed_edges(n, m, 0.5, 4)
+    op = graph.operator_from_edges(to, frm, n, n)            # G[to, from] = 1/indeg(to)
+    name = (f"cfg4: SimRank on a synthetic dense-regime directed graph, n={n}, m={m} unique edges "
+            f"(power-law alpha=0.5, seed 4), unweighted, C=0.8")
+    return op, (frm, to), name
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"], tensor_sustained=p["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = get(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import psutil
+    from oracle import cpu_baseline
+    op, _, name = workload(args)
+    res = cpu_baseline.iterations_per_second(op.indptr, op.indices, op.g, op.M, target_seconds=args.cpu_seconds,
+                                             steps=args.steps, warmup=args.warmup,
+                                             max_bytes=int(psutil.virtual_memory().available * 0.8))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["value"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name},
+            "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- engine arm
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from simrank_b200 import engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = engine.require_cuda(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    op, edges, name = workload(args)
+    n = op.M
+
+    if world > 1:
+        from simrank_b200 import dist as sdist
+        solver = sdist.ShardedDirectedSolver(op, 0.8, mode=args.mode, ns=args.slices, device=dev)
+        halves = solver.halves
+    else:
+        dop = engine.DeviceOperator(op, dev)
+        solver = engine.DirectedSolver(dop, 0.8, mode=args.mode, ns=args.slices)
+        halves = [solver.half]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver.step()
+    for h in halves:
+        h.events = []
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        t0.record()
+        last = None
+        for _ in range(args.steps):
+            last = solver.step()
+        t1.record()
+        sync_all()
+    ms = t0.elapsed_time(t1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # per-kernel durations from the events recorded inside the timed steps
+    per = {}
+    launches = 0
+    for h in halves:
+        for nm, a, b in h.events:
+            per.setdefault(nm, []).append(a.elapsed_time(b))
+            launches += 1
+        h.events = None
+    pk = peaks()
+    flops_half = 2.0 * n * n * n / world                        # algorithmic: one n x n x n product, row-sharded
+    kernels = {k: {"ms": statistics.mean(v), "launches": len(v)} for k, v in per.items()}
+    if args.mode == "i8":
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        ach = flops_half / (kernels[dom]["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tensor_sustained"], "traffic": None,
+                "peak_kind": f"dense bf16 sustained, {pk['source']}; burst {pk['tensor_burst']}",
+                "executed_int8_tops": ach * args.slices,
+                "note": ("achieved = algorithmic 2n^3 flop of one half-product / mean launch time inside the timed "
+                         f"steps; the kernel executes {args.slices} u8 x u8 -> s32 tcgen05 products per algorithmic one")}
+    else:
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        by = (3 if dom.endswith("final") else 2) * n * n * 8.0 / world
+        ach = by / (kernels[dom]["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": ach / pk["hbm"], "traffic": None, "peak_kind": pk["source"],
+                "note": "algorithmic bytes: first half 2 n^2 s, second half 3 n^2 s (s = 8)"}
+
+    line = {"metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "u8 x u8 -> s32 (3 fixed-point planes), f64 epilogue" if args.mode == "i8" else "f64",
+            "data": "synthetic",
+            "config": {"workload": name, "mode": args.mode, "slices": args.slices,
+                       "l2": "operands (>= 1 GB) are far larger than the 126 MB L2; no flush needed",
+                       "parallelism": f"S row-sharded over {world} GPU(s)"},
+            "algorithmic_tflops": 4.0 * n ** 3 / (ms * 1e-3) / 1e12,
+            "roofline": roof, "kernels": kernels, "gpu_launches": launches,
+            "last_maxdiff": last if not isinstance(last, tuple) else list(last)}
+
+    clk = clocks.summary()
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, clk)
+        mhz = [g["sm_mhz"] for g in gathered if g["sm_mhz"]]
+        clk = {"sm_mhz": min(mhz) if mhz else None, "sm_max_mhz": clk["sm_max_mhz"],
+               "reasons": sorted(set(r for g in gathered for r in g["reasons"]))}
+    line["clocks"] = clk
+
+    del solver, halves
+    torch.cuda.empty_cache()
+    # ---- end to end through the public API: DataFrame in -> DataFrame out, host buffers
+    if not args.no_e2e:
+        line["e2e"] = run_e2e(args, edges, n, world, rank)
+        torch.cuda.empty_cache()
+
+    # ---- the reference's CPU path on this host's cores (rank 0, N = 1 only)
+    if world == 1 and not args.no_cpu:
+        import psutil
+        from oracle import cpu_baseline
+        res = cpu_baseline.iterations_per_second(op.indptr, op.indices, op.g, n, target_seconds=args.cpu_seconds,
+                                                 max_bytes=int(psutil.virtual_memory().available * 0.8))
+        line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                                "sample": res["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, edges, n, world, rank):
+    """``SimRank().fit(DataFrame)`` -> DataFrame with K iterations (eps=0): host graph build, H2D of
+    the CSR graph, K device iterations each reading back max|dS|, D2H of the full S."""
+    import pandas as pd
+    import torch
+    from SimRank import SimRank as M
+    frm, to = edges
+    df = pd.DataFrame({"from": frm, "to": to})
+    K = args.steps
+    obj = M.SimRank(mode=args.mode, slices=args.slices)
+    obj.fit(df, iterations=1, eps=0.0, verbose=False)              # warm-up: allocator, pinned pool, library
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    S = obj.fit(df, iterations=K, eps=0.0, verbose=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    assert S.shape == (n, n) and obj.fit_info_.applied == K
+    h2d = (len(frm) * 4 + (n + 1) * 8 + 2 * n * 8) / K
+    d2h = (n * n * 8 / world + 16 * K) / K
+    return {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "seconds_total": dt, "note": "whole fit(): pandas graph build + H2D + K iterations + D2H of S into a DataFrame"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)

@@ -135,6 +135,10 @@ typedef struct srk_i8_args {
   int mode, ns;
   int64_t R, N, K;
   const uint8_t* in_planes; int64_t ld_in; int64_t in_plane_stride;
+  /* K-blocked operand (row-sharded multi-GPU exchange buffers): when in_kblock > 0, column k of
+   * V is at in_planes + (k / in_kblock) * in_kblock_stride + s * in_plane_stride + r * ld_in +
+   * k % in_kblock; in_kblock must be a multiple of 128 and K a multiple of in_kblock.          */
+  int64_t in_kblock; int64_t in_kblock_stride;
   srk_rowbound in_rowbound;             /* bound of V row r */
   const uint8_t* A8; int64_t lda;       /* [N x K] 0/1 */
   int64_t diag_offset; int unit_diag;

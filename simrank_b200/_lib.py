@@ -44,6 +44,7 @@ class I8Args(C.Structure):
     _fields_ = [("mode", C.c_int), ("ns", C.c_int),
                 ("R", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
                 ("in_planes", C.c_void_p), ("ld_in", C.c_int64), ("in_plane_stride", C.c_int64),
+                ("in_kblock", C.c_int64), ("in_kblock_stride", C.c_int64),
                 ("in_rowbound", RowBound),
                 ("A8", C.c_void_p), ("lda", C.c_int64),
                 ("diag_offset", C.c_int64), ("unit_diag", C.c_int),

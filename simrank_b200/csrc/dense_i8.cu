@@ -90,6 +90,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -165,6 +172,7 @@ struct Params {
   EpilogueDev epi;
   double* maxdiff; double* maxoff;
   int tiles_m, tiles_n, group_m;
+  int kblock;                  // > 0: V's K axis is split in blocks of `kblock` columns (4-D tensor map)
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& mb, int& nb) {
@@ -227,7 +235,12 @@ i8_half_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sv = stage_base + stage * C::kStageBytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_3d(sv, &map_v, &full_bar[stage], kb * BK, mb * BM, 0);
+          if (p.kblock > 0) {
+            const int k = kb * BK;
+            tma_load_4d(sv, &map_v, &full_bar[stage], k % p.kblock, mb * BM, k / p.kblock, 0);
+          } else {
+            tma_load_3d(sv, &map_v, &full_bar[stage], kb * BK, mb * BM, 0);
+          }
           tma_load_2d(sv + NS * BM * BK, &map_a, &full_bar[stage], kb * BK, nb * BN);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -457,17 +470,15 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// u8 tensor [planes][rows][cols] (cols contiguous), box = BK x box_rows x box_planes, 128B swizzle.
-static int make_map(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t planes, int64_t ld,
-                    int64_t plane_stride, int box_rows, int box_planes) {
+// u8 tensor map with 128B swizzle.  Dimensions (fastest first): columns, rows, [k-blocks], [planes];
+// the box is BK columns x box_rows rows x 1 k-block x box_planes planes, so that the planes of one
+// BM x BK operand tile land back to back in shared memory.
+static int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SRK_ERR_CUDA, "%s", "cuTensorMapEncodeTiled is not available from the driver");
-  const bool is3d = planes > 0;
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(is3d ? planes : 1)};
-  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)(is3d ? plane_stride : 0)};
-  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, is3d ? 3 : 2, const_cast<void*>(base), dims, strides, box,
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SRK_ERR_CUDA, "cuTensorMapEncodeTiled failed%s (code %lld)", "", (long long)r);
@@ -478,9 +489,25 @@ template <int NS, int BN, int MODE>
 static int launch(const srk_i8_args& a, cudaStream_t st) {
   using C = Cfg<NS, BN>;
   CUtensorMap map_v, map_a;
-  int rc = make_map(&map_v, a.in_planes, a.K, a.R, NS, a.ld_in, a.in_plane_stride, BM, NS);
+  int rc;
+  if (a.in_kblock > 0) {
+    cuuint64_t dims[4] = {(cuuint64_t)a.in_kblock, (cuuint64_t)a.R, (cuuint64_t)(a.K / a.in_kblock), (cuuint64_t)NS};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ld_in, (cuuint64_t)a.in_kblock_stride, (cuuint64_t)a.in_plane_stride};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)BM, 1, (cuuint32_t)NS};
+    rc = make_map(&map_v, a.in_planes, 4, dims, strides, box);
+  } else {
+    cuuint64_t dims[3] = {(cuuint64_t)a.K, (cuuint64_t)a.R, (cuuint64_t)NS};
+    cuuint64_t strides[2] = {(cuuint64_t)a.ld_in, (cuuint64_t)a.in_plane_stride};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, (cuuint32_t)NS};
+    rc = make_map(&map_v, a.in_planes, 3, dims, strides, box);
+  }
   if (rc) return rc;
-  rc = make_map(&map_a, a.A8, a.K, a.N, 0, a.lda, 0, BN, 1);
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};
+    cuuint64_t strides[1] = {(cuuint64_t)a.lda};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    rc = make_map(&map_a, a.A8, 2, dims, strides, box);
+  }
   if (rc) return rc;
   Params p;
   memset(&p, 0, sizeof(p));
@@ -497,6 +524,7 @@ static int launch(const srk_i8_args& a, cudaStream_t st) {
   p.tiles_m = (int)((a.R + BM - 1) / BM);
   p.tiles_n = (int)((a.N + BN - 1) / BN);
   p.group_m = 8;
+  p.kblock = (int)a.in_kblock;
   int dev = 0, sms = 0;
   SRK_CUDA_OK(cudaGetDevice(&dev));
   SRK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -525,7 +553,13 @@ extern "C" int srk_i8_half(const srk_i8_args* a, void* stream) {
   SRK_REQUIRE(a->R > 0 && a->N > 0 && a->K > 0, "empty problem");
   SRK_REQUIRE(a->ld_in % 16 == 0 && a->lda % 16 == 0 && a->in_plane_stride % 16 == 0, "operand strides must be multiples of 16");
   SRK_REQUIRE(((uintptr_t)a->in_planes % 16) == 0 && ((uintptr_t)a->A8 % 16) == 0, "operands must be 16-byte aligned");
-  SRK_REQUIRE(a->ld_in >= a->K && a->lda >= a->K, "leading dimension smaller than K");
+  SRK_REQUIRE(a->lda >= a->K, "lda smaller than K");
+  if (a->in_kblock > 0) {
+    SRK_REQUIRE(a->in_kblock % 128 == 0 && a->K % a->in_kblock == 0 && a->ld_in >= a->in_kblock &&
+                    a->in_kblock_stride % 16 == 0, "K-blocked operand: in_kblock must be a multiple of 128 dividing K");
+  } else {
+    SRK_REQUIRE(a->ld_in >= a->K, "ld_in smaller than K");
+  }
   SRK_REQUIRE(a->K < (1ll << 22), "K too large for exact int32 accumulation");
   if (!srk_i8_supported()) return fail(SRK_ERR_UNSUPPORTED, "%s", "tcgen05 kind::i8 needs an sm_100 device");
   cudaStream_t st = (cudaStream_t)stream;

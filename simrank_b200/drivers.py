@@ -82,10 +82,33 @@ def _mode_with_prior(mode, *priors):
     return mode
 
 
+def _world():
+    """(rank, world) of the default process group, (0, 1) when torch.distributed is not in use."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _local_rows(t, n, rank, world):
+    """Rows of an n-row device matrix owned by ``rank`` under the row sharding of dist.ShardPlan."""
+    if t is None:
+        return None
+    from .dist import ShardPlan
+    plan = ShardPlan(n, world)
+    return t[plan.start(rank):plan.stop(rank)]
+
+
 def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mode=None, device=None, slices=3):
     dop = _device_op(op, device)
     ev = evidence.counts if evidence is not None else None
     pr = _prior_tensor(prior, op.M, dop.device)
+    rank, world = _world()
+    if world > 1:                      # one process per GPU: S row-sharded, tensor-core path
+        from . import dist as _sd
+        return _sd.ShardedDirectedSolver(op, C, _local_rows(ev, op.M, rank, world),
+                                         _local_rows(pr, op.M, rank, world), lbd, _mode_with_prior(mode, prior),
+                                         slices, dop.device)
     return _eng.DirectedSolver(dop, C, ev, pr, lbd, _mode_with_prior(mode, prior), slices)
 
 
@@ -96,6 +119,13 @@ def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=N
     e2 = evidence2.counts if evidence2 is not None else None
     p1 = _prior_tensor(prior1, op12.M, d12.device)
     p2 = _prior_tensor(prior2, op21.M, d21.device)
+    rank, world = _world()
+    if world > 1:
+        from . import dist as _sd
+        return _sd.ShardedBipartiteSolver(op12, op21, C1, C2, _local_rows(e1, op12.M, rank, world),
+                                          _local_rows(e2, op21.M, rank, world), _local_rows(p1, op12.M, rank, world),
+                                          _local_rows(p2, op21.M, rank, world), lbd1, lbd2,
+                                          _mode_with_prior(mode, prior1, prior2), slices, d12.device)
     return _eng.BipartiteSolver(d12, d21, C1, C2, e1, e2, p1, p2, lbd1, lbd2,
                                 _mode_with_prior(mode, prior1, prior2), slices)
 

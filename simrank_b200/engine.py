@@ -150,6 +150,7 @@ class _Half:
                    "srk_set_identity_f64")
         self.evidence, self.prior, self.lbd = evidence, prior, float(lbd)
         self.scal = torch.zeros(2, dtype=torch.float64, device=dev)        # [maxdiff, maxoff]
+        self.events = None          # set to a list to collect (name, start, end) CUDA events per launch
         self.maxoff = 0.0                                                  # max off-diagonal of current S
         if mode == "csr":
             self.ldt = _round_up(max(self.n_out, 1), 16)
@@ -183,19 +184,31 @@ class _Half:
         e.maxoff = self.scal.data_ptr() + 8
         return e
 
+    def _timed(self, name, launch):
+        """Run ``launch()``; when profiling, bracket it with CUDA events on the launching stream."""
+        if self.events is None:
+            return launch()
+        st = torch.cuda.current_stream()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        rc = launch()
+        b.record(st)
+        self.events.append((name, a, b))
+        return rc
+
     def update(self, src: "_Half") -> None:
         """Launch the two half-products (asynchronous).  ``src`` holds S_in (its S / planes)."""
         lib = _lib.load()
         self.scal.zero_()
         if self.mode == "csr":
             op = self.op
-            _lib.check(lib.srk_csr_half_f64(_ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M,
-                                            _ptr(src.S), src.ld, self.n_in, _ptr(self.T), self.ldt, None, _stream()),
-                       "srk_csr_half_f64(first)")
+            _lib.check(self._timed("csr_half_first", lambda: lib.srk_csr_half_f64(
+                _ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M, _ptr(src.S), src.ld, self.n_in,
+                _ptr(self.T), self.ldt, None, _stream())), "srk_csr_half_f64(first)")
             epi = self._epilogue()
-            _lib.check(lib.srk_csr_half_f64(_ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M,
-                                            _ptr(self.T), self.ldt, self.n_out, _ptr(self.S), self.ld, C.byref(epi),
-                                            _stream()), "srk_csr_half_f64(second)")
+            _lib.check(self._timed("csr_half_final", lambda: lib.srk_csr_half_f64(
+                _ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M, _ptr(self.T), self.ldt, self.n_out,
+                _ptr(self.S), self.ld, C.byref(epi), _stream())), "srk_csr_half_f64(second)")
             return
         # ---- i8: a-priori bounds of the two results, as affine forms over constant node vectors.
         # The planes of S_in were cut with src.bound_S; the ACTUAL off-diagonal maximum of S_in is
@@ -219,7 +232,7 @@ class _Half:
         a.diag_offset, a.unit_diag = 0, 1
         a.out_planes, a.ld_outp, a.out_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
         a.out_rowbound = bound_U
-        _lib.check(lib.srk_i8_half(C.byref(a), _stream()), "srk_i8_half(MID)")
+        _lib.check(self._timed("i8_half_mid", lambda: lib.srk_i8_half(C.byref(a), _stream())), "srk_i8_half(MID)")
 
         b = _lib.I8Args()
         b.mode, b.ns = _lib.SRK_I8_FINAL, self.ns
@@ -233,7 +246,8 @@ class _Half:
         b.out_planes, b.ld_outp, b.out_plane_stride = self.planes.data_ptr(), self.ldp, self.planes.stride(0)
         b.out_rowbound = bound_new
         b.epi = self._epilogue()
-        _lib.check(lib.srk_i8_half(C.byref(b), _stream()), "srk_i8_half(FINAL)")
+        _lib.check(self._timed("i8_half_final", lambda: lib.srk_i8_half(C.byref(b), _stream())),
+                   "srk_i8_half(FINAL)")
         self._pending_bound = ((mul, add), mul * self.rho_max + add)
 
     def finish(self) -> float:
