@@ -31,12 +31,13 @@ class _Base(object):
 
     mode   : None/'auto' | 'csr' (float64 gather path) | 'i8' (tcgen05 fixed-point path)
     device : CUDA device (default: current)
-    slices : uint8 planes per matrix in i8 mode (3 -> 24-bit fixed point)
+    slices : uint8 planes per matrix in i8 mode: 2, 3, 4 or None/'auto' = the fewest planes whose
+             guaranteed error bound stays below 5e-7 (simrank_b200.engine.choose_slices)
     label_order : bipartite only -- 'sorted' labels the result rows with the labels they belong
              to; 'reference' reproduces the set-ordered labels of SimRank.py:303
     """
 
-    def _engine_options(self, mode=None, device=None, slices=3, label_order="sorted"):
+    def _engine_options(self, mode=None, device=None, slices=None, label_order="sorted"):
         self._mode, self._device, self._slices, self._label_order = mode, device, slices, label_order
         self.fit_info_ = None
         self._result = None

@@ -36,8 +36,9 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--n", type=int, default=32768, help="nodes (default: the BASELINE cfg4 size)")
     ap.add_argument("--mean-degree", type=int, default=64)
-    ap.add_argument("--mode", default="i8", choices=["i8", "csr"], help="dense tensor-core chain (graded) or CSR SpMM")
-    ap.add_argument("--slices", type=int, default=3)
+    ap.add_argument("--mode", default="i8", choices=["i8", "i8v1", "csr"],
+                    help="dense tensor-core chain (graded; i8v1 = first-generation single-CTA kernel) or CSR SpMM")
+    ap.add_argument("--slices", default="auto", help="uint8 planes per matrix: 2, 3, 4 or auto (error-bound driven)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -137,6 +138,7 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- engine arm
 def run_engine(args):
+    args.slices = None if args.slices in ("auto", None) else int(args.slices)
     import torch
     import torch.distributed as dist
     from simrank_b200 import engine
@@ -196,15 +198,19 @@ def run_engine(args):
     pk = peaks()
     flops_half = 2.0 * n * n * n / world                        # algorithmic: one n x n x n product, row-sharded
     kernels = {k: {"ms": statistics.mean(v), "launches": len(v)} for k, v in per.items()}
-    if args.mode == "i8":
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    used = sorted(set(x for h in halves for x in getattr(h, "slices_used", [])[-args.steps:])) or [args.slices or 3]
+    if args.mode in ("i8", "i8v1"):
+        gemms = {k: v for k, v in kernels.items() if "half" in k}
+        dom = max(gemms, key=lambda k: gemms[k]["ms"])
         ach = flops_half / (kernels[dom]["ms"] * 1e-3) / 1e12
+        sym = args.mode == "i8" and world == 1 and dom.endswith("final")
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["tensor_sustained"], "traffic": None,
                 "peak_kind": f"dense bf16 sustained, {pk['source']}; burst {pk['tensor_burst']}",
-                "executed_int8_tops": ach * args.slices,
+                "executed_int8_tops": ach * used[-1] * (0.5 if sym else 1.0),
                 "note": ("achieved = algorithmic 2n^3 flop of one half-product / mean launch time inside the timed "
-                         f"steps; the kernel executes {args.slices} u8 x u8 -> s32 tcgen05 products per algorithmic one")}
+                         f"steps; the kernel executes {used} u8 x u8 -> s32 tcgen05 products per algorithmic one"
+                         + ("; this launch computes only the upper triangle of the symmetric result" if sym else ""))}
     else:
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
         by = (3 if dom.endswith("final") else 2) * n * n * 8.0 / world
@@ -216,9 +222,9 @@ def run_engine(args):
     line = {"metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "u8 x u8 -> s32 (3 fixed-point planes), f64 epilogue" if args.mode == "i8" else "f64",
+            "dtype": (f"u8 x u8 -> s32 ({used} fixed-point planes), f64 epilogue" if args.mode != "csr" else "f64"),
             "data": "synthetic",
-            "config": {"workload": name, "mode": args.mode, "slices": args.slices,
+            "config": {"workload": name, "mode": args.mode, "slices": args.slices or "auto", "slices_used": used,
                        "l2": "operands (>= 1 GB) are far larger than the 126 MB L2; no flush needed",
                        "parallelism": f"S row-sharded over {world} GPU(s)"},
             "algorithmic_tflops": 4.0 * n ** 3 / (ms * 1e-3) / 1e12,

@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 1
+#define SRK_ABI_VERSION 2
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -151,6 +151,71 @@ typedef struct srk_i8_args {
 int srk_i8_half(const srk_i8_args* args, void* stream);
 /* 1 when the tcgen05 path can run on the current device (sm_100), else 0. */
 int srk_i8_supported(void);
+
+/* ----------------------------------------------------------------------------- paired-SM tensor-core path
+ * The same fixed-point product on a CTA PAIR (tcgen05.mma.cta_group::2, cluster of two SMs):
+ *   D[j, r] = sum_k A8[j,k] * V[r,k]      j < M (dense 0/1 matrix), r < R (NS planes), k < K
+ * A8 is the M-side operand (256 rows per pair) and the NS planes of RT rows of V are concatenated
+ * on the N side of ONE instruction, so the result is row-major in j -- no transposed store between
+ * the two half-products -- and the accumulator is double-buffered in TMEM.
+ *
+ * The unit diagonal of S is carried OUTSIDE the planes (S = I + S_off):
+ *   G S G^T = diag(g) (A S_off A^T + A A^T) diag(g),   A A^T = common-in-neighbour counts,
+ * a constant uint16 matrix computed once per graph (mode COUNTS).  This keeps every plane bound
+ * proportional to max(S_off) instead of 1, which is what lets NS = 2 meet the 1e-6 budget on
+ * graphs whose similarities are small (DESIGN.md "precision").
+ *
+ * mode SRK_X2_MID   : U[j, r] = D[j,r] * bound_in(r) / 256^NS  re-quantised with out_rowbound(j)
+ *                     into out_planes (row j, column r).  With V = planes of S_off this is
+ *                     U = A S_off, the first half `G.dot(S)` of SimRank.py:139 without g.
+ * mode SRK_X2_FINAL : x = coef * g_a[j] * g_v[r] * (D[j,r] * bound_in(r) / 256^NS + counts)
+ *                     followed by the srk_epilogue chain (the evidence factor is taken from `counts`
+ *                     when use_evidence != 0, else from epi.evidence if given), stored as f64.
+ *                     layout DIRECT     element (row j, column r) of out_f64/s_old/prior/counts;
+ *                     layout SYMMETRIC  M == R, only tiles containing j <= r are computed and every
+ *                                       off-diagonal value is written to (j, r) AND (r, j): the second
+ *                                       half `.dot(G.T)` costs n^3 instead of 2 n^3 flop and S is
+ *                                       bit-exactly symmetric (needs symmetric evidence, no prior);
+ *                     layout TRANSPOSED element (row r, column j): row-sharded multi-GPU, where the
+ *                                       local rows of S are the N-side operand.
+ *                     The diagonal is the element with j == r + diag_offset.
+ * mode SRK_X2_COUNTS: out_counts[j, r] = min(D[j,r], 65535) as uint16 (ns must be 1, V = a 0/1
+ *                     matrix as a single plane): `np.dot((G>0).astype(int), (G>0).T.astype(int))`
+ *                     of SimRank.py:315, also the A A^T term above.                              */
+#define SRK_X2_MID 0
+#define SRK_X2_FINAL 1
+#define SRK_X2_COUNTS 2
+#define SRK_X2_DIRECT 0
+#define SRK_X2_SYMMETRIC 1
+#define SRK_X2_TRANSPOSED 2
+typedef struct srk_x2_args {
+  int mode, ns, layout;
+  int64_t M, R, K;
+  const uint8_t* A8; int64_t lda;                                    /* [M x K] 0/1 */
+  const uint8_t* in_planes; int64_t ld_in; int64_t in_plane_stride;  /* V: NS planes [R x K] */
+  int64_t in_kblock; int64_t in_kblock_stride;                       /* as in srk_i8_args */
+  srk_rowbound in_rowbound;                                          /* bound of V row r */
+  uint8_t* out_planes; int64_t ld_outp; int64_t out_plane_stride;    /* MID */
+  srk_rowbound out_rowbound;                                         /* MID: bound of U row j */
+  const double* g_a; const double* g_v;                              /* FINAL: row factors of A8 / V rows */
+  const uint16_t* counts; int64_t ld_counts;                         /* FINAL (indexed like out_f64) */
+  int add_counts, use_evidence;
+  double* out_f64; int64_t ld_out; int64_t diag_offset;              /* FINAL */
+  srk_epilogue epi;                                                  /* FINAL */
+  uint16_t* out_counts; int64_t ld_out_counts;                       /* COUNTS */
+} srk_x2_args;
+int srk_x2_half(const srk_x2_args* args, void* stream);
+
+/* Quantise rows [0,R) of a f64 matrix into NS planes with the EXACT per-row bound: pass 1 takes
+ * m_r = max_k V[r,k] over the row (the element (r, r + zero_diag_offset) excluded and stored as
+ * 0), pass 2 (served by L2) writes q = rint(V * (256^NS - 1) / m_r).  bound_out[r] receives the
+ * bound in the srk_rowbound sense, m_r * 256^NS / (256^NS - 1) (0 for an all-zero row), so the
+ * largest element maps to 256^NS - 1 without clipping and the rounding error is at most half a
+ * step of m_r / (256^NS - 1).  Negative and NaN entries are stored as 0.                      */
+int srk_slice_rows_max_f64(const double* V, int64_t ldv, int64_t R, int64_t K,
+                           int64_t zero_diag_offset, int ns,
+                           uint8_t* planes, int64_t ldp, int64_t plane_stride,
+                           double* bound_out, void* stream);
 
 /* ----------------------------------------------------------------------------- retrieval
  * Row-wise top-k of S (rows [0,R) x n columns): idx[r,:] = argsort(-S[r], kind='stable')[:k]

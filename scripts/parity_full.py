@@ -19,8 +19,9 @@ ref = engine.DirectedSolver(dop, 0.8, mode="csr")
 t = time.time()
 d_ref = [ref.step() for _ in range(K)]
 out["csr_seconds"] = time.time() - t
-for ns in (3, 4):
+for ns in (None, 2, 3):
     sol = engine.DirectedSolver(dop, 0.8, mode="i8", ns=ns)
+    ns = ns or "auto"
     t = time.time()
     d = [sol.step() for _ in range(K)]
     torch.cuda.synchronize()
@@ -28,6 +29,7 @@ for ns in (3, 4):
     diff = (sol.S - ref.S).abs()
     out[f"i8x{ns}_maxabs_vs_csr_f64"] = float(diff.max())
     out[f"i8x{ns}_maxdiff_seq"] = d
+    out[f"i8x{ns}_slices_used"] = sol.half.slices_used
     S = sol.S
     out[f"i8x{ns}_diag_all_one"] = bool((torch.diagonal(S) == 1).all())
     out[f"i8x{ns}_asym"] = float((S - S.T).abs().max())

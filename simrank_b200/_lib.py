@@ -11,9 +11,11 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SRK_I8_MID, SRK_I8_FINAL, SRK_I8_COUNTS = 0, 1, 2
+SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
+SRK_X2_DIRECT, SRK_X2_SYMMETRIC, SRK_X2_TRANSPOSED = 0, 1, 2
 
 
 class EngineError(RuntimeError):
@@ -55,6 +57,23 @@ class I8Args(C.Structure):
                 ("epi", Epilogue)]
 
 
+class X2Args(C.Structure):
+    _fields_ = [("mode", C.c_int), ("ns", C.c_int), ("layout", C.c_int),
+                ("M", C.c_int64), ("R", C.c_int64), ("K", C.c_int64),
+                ("A8", C.c_void_p), ("lda", C.c_int64),
+                ("in_planes", C.c_void_p), ("ld_in", C.c_int64), ("in_plane_stride", C.c_int64),
+                ("in_kblock", C.c_int64), ("in_kblock_stride", C.c_int64),
+                ("in_rowbound", RowBound),
+                ("out_planes", C.c_void_p), ("ld_outp", C.c_int64), ("out_plane_stride", C.c_int64),
+                ("out_rowbound", RowBound),
+                ("g_a", C.c_void_p), ("g_v", C.c_void_p),
+                ("counts", C.c_void_p), ("ld_counts", C.c_int64),
+                ("add_counts", C.c_int), ("use_evidence", C.c_int),
+                ("out_f64", C.c_void_p), ("ld_out", C.c_int64), ("diag_offset", C.c_int64),
+                ("epi", Epilogue),
+                ("out_counts", C.c_void_p), ("ld_out_counts", C.c_int64)]
+
+
 _P, _I64, _INT, _DBL = C.c_void_p, C.c_int64, C.c_int, C.c_double
 # name -> (restype, argtypes); must list every symbol include/simrank_b200.h declares
 SYMBOLS = {
@@ -67,6 +86,8 @@ SYMBOLS = {
     "srk_csr_to_dense_u8": (_INT, [_P, _P, _I64, _I64, _I64, _P, _I64, _P]),
     "srk_slice_rows_f64": (_INT, [_P, _I64, _I64, _I64, C.POINTER(RowBound), _I64, _INT, _P, _I64, _I64, _P]),
     "srk_i8_half": (_INT, [C.POINTER(I8Args), _P]),
+    "srk_x2_half": (_INT, [C.POINTER(X2Args), _P]),
+    "srk_slice_rows_max_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _INT, _P, _I64, _I64, _P, _P]),
     "srk_i8_supported": (_INT, []),
     "srk_topk_rows": (_INT, [_P, _I64, _I64, _I64, _INT, _P, _P, _P]),
     "srk_set_identity_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _P]),

@@ -221,6 +221,86 @@ __global__ void slice_rows_kernel(const double* __restrict__ V, int64_t ldv, int
 }
 
 // ------------------------------------------------------------------------------------------
+// Planes with the exact per-row bound (srk_slice_rows_max_f64): one CTA per row, two passes over
+// the row (the second one is served by L2: a row is at most a few hundred KB).
+constexpr int SLICE_THREADS = 256;
+__device__ __forceinline__ void load16(const double* p, int64_t k0, int64_t K, bool vec, double (&v)[16]) {
+  if (vec && k0 + 16 <= K) {
+#pragma unroll
+    for (int x = 0; x < 16; x += 2) {
+      const double2 d = *reinterpret_cast<const double2*>(p + k0 + x);
+      v[x] = d.x; v[x + 1] = d.y;
+    }
+  } else {
+#pragma unroll
+    for (int x = 0; x < 16; ++x) v[x] = (k0 + x < K) ? p[k0 + x] : 0.0;
+  }
+}
+template <int NS>
+__global__ void __launch_bounds__(SLICE_THREADS)
+slice_rows_max_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
+                      uint8_t* __restrict__ planes, int64_t ldp, int64_t plane_stride,
+                      double* __restrict__ bound_out) {
+  __shared__ double red[SLICE_THREADS / 32];
+  __shared__ double row_max;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double qmax = (double)((1ull << (8 * NS)) - 1ull);
+  const int64_t chunks = (ldp + 15) / 16;
+  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+    const double* row = V + r * ldv;
+    const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+    const int64_t kd = zero_diag_offset >= 0 ? r + zero_diag_offset : -1;
+    double m = 0.0;
+    for (int64_t c = threadIdx.x; c * 16 < K; c += SLICE_THREADS) {
+      double v[16];
+      load16(row, c * 16, K, vec, v);
+#pragma unroll
+      for (int x = 0; x < 16; ++x)
+        if (c * 16 + x != kd && v[x] > m) m = v[x];          // NaN and negatives never win
+    }
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (warp == 0) {
+      m = lane < SLICE_THREADS / 32 ? red[lane] : 0.0;
+      m = warp_max(m);
+      if (lane == 0) {
+        row_max = m;
+        if (bound_out) bound_out[r] = m > 0.0 ? m * ((qmax + 1.0) / qmax) : 0.0;
+      }
+    }
+    __syncthreads();
+    m = row_max;
+    const double scale = m > 0.0 ? qmax / m : 0.0;
+    for (int64_t c = threadIdx.x; c < chunks; c += SLICE_THREADS) {
+      const int64_t k0 = c * 16;
+      double v[16];
+      load16(row, k0, K, vec, v);
+      uint32_t w[NS][4];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) w[s][x] = 0u;
+#pragma unroll
+      for (int x = 0; x < 16; ++x) {
+        double q = (k0 + x == kd) ? 0.0 : rint(v[x] * scale);
+        if (!(q > 0.0)) q = 0.0;
+        if (q > qmax) q = qmax;
+        const unsigned long long qi = (unsigned long long)q;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          w[s][x >> 2] |= (uint32_t)((qi >> (8 * (NS - 1 - s))) & 0xffull) << (8 * (x & 3));
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        *reinterpret_cast<uint4*>(planes + s * plane_stride + r * ldp + k0) =
+            make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+    __syncthreads();                                          // row_max / red are reused by the next row
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Row-wise top-k by k rounds of arg-max in the total order (value desc, column asc); NaN last.
 constexpr int TOPK_THREADS = 256;
 __device__ __forceinline__ bool topk_before(double va, int ia, double vb, int ib) {
@@ -380,6 +460,30 @@ extern "C" int srk_slice_rows_f64(const double* V, int64_t ldv, int64_t R, int64
     case 2: slice_rows_kernel<2><<<blocks, 256, 0, st>>>(V, ldv, R, K, *rowbound, zero_diag_offset, planes, ldp, plane_stride); break;
     case 3: slice_rows_kernel<3><<<blocks, 256, 0, st>>>(V, ldv, R, K, *rowbound, zero_diag_offset, planes, ldp, plane_stride); break;
     case 4: slice_rows_kernel<4><<<blocks, 256, 0, st>>>(V, ldv, R, K, *rowbound, zero_diag_offset, planes, ldp, plane_stride); break;
+    default: return srk::fail(SRK_ERR_INVALID, "invalid argument: %s", "ns must be 1..4");
+  }
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_slice_rows_max_f64(const double* V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
+                                      int ns, uint8_t* planes, int64_t ldp, int64_t plane_stride,
+                                      double* bound_out, void* stream) {
+  SRK_REQUIRE(V && planes, "null pointer");
+  SRK_REQUIRE(ldp % 16 == 0 && ldp >= K && ldv >= K, "ldp must be a multiple of 16 and >= K");
+  SRK_REQUIRE(((uintptr_t)planes % 16) == 0 && plane_stride % 16 == 0, "planes must be 16-byte aligned");
+  if (R == 0 || K == 0) return SRK_OK;
+  int dev = 0, sms = 0;
+  SRK_CUDA_OK(cudaGetDevice(&dev));
+  SRK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t want = (int64_t)sms * 8;
+  const unsigned blocks = (unsigned)(R < want ? R : want);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ns) {
+    case 1: slice_rows_max_kernel<1><<<blocks, SLICE_THREADS, 0, st>>>(V, ldv, R, K, zero_diag_offset, planes, ldp, plane_stride, bound_out); break;
+    case 2: slice_rows_max_kernel<2><<<blocks, SLICE_THREADS, 0, st>>>(V, ldv, R, K, zero_diag_offset, planes, ldp, plane_stride, bound_out); break;
+    case 3: slice_rows_max_kernel<3><<<blocks, SLICE_THREADS, 0, st>>>(V, ldv, R, K, zero_diag_offset, planes, ldp, plane_stride, bound_out); break;
+    case 4: slice_rows_max_kernel<4><<<blocks, SLICE_THREADS, 0, st>>>(V, ldv, R, K, zero_diag_offset, planes, ldp, plane_stride, bound_out); break;
     default: return srk::fail(SRK_ERR_INVALID, "invalid argument: %s", "ns must be 1..4");
   }
   SRK_CUDA_OK(cudaGetLastError());

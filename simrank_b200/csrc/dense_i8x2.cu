@@ -1,0 +1,747 @@
+// Paired-SM tensor-core half-product for the dense SimRank chain on sm_100a.
+//
+//   D[j, r] = sum_k A8[j, k] * V[r, k]          j < M, r < R, k < K
+//
+// A8 is the 0/1 adjacency pattern (the M-side operand: 256 rows per CTA pair), V a non-negative
+// matrix held as NS uint8 fixed-point planes (V[r,k] ~= q[r,k] * bound(r) / 256^NS).  The NS planes
+// of one block of RT rows of V are CONCATENATED on the N side of a single
+// tcgen05.mma.cta_group::2.kind::i8 (u8 x u8 -> s32, M = 256, N = NS*RT, K = 32): column
+// p*RT + c of the accumulator is plane p of row r0 + c.  Products and K-long sums are exact
+// integers; the epilogue recombines the planes in 64-bit integers.  See DESIGN.md "K1/K2".
+//
+// Why this shape.  With M = 128 per CTA the int8 pipe consumes its N-side operand at 64 B/clk and
+// its M-side operand at 8192/N B/clk from shared memory while TMA refills the same bytes: the
+// single-CTA kernel (dense_i8.cu) needed 187 B/clk against a 128 B/clk port and sat at 60-65 % of
+// the pipe.  A CTA pair splits the N-side operand between the two SMs (each holds N/2 rows) and
+// one instruction covers all planes, so the M-side tile is read once per K-step instead of NS
+// times: 128 B/clk (NS = 2, N = 256) / 149 B/clk (NS = 3, N = 192).  The accumulator needs only
+// N <= 256 TMEM columns, so it is double-buffered and the epilogue of tile t overlaps the
+// mainloop of tile t+1.  The result is row-major in j with r along the TMEM columns, so no
+// transposed store is needed between the two half-products.
+//
+// Roles (256 threads per CTA, cluster of 2 CTAs, persistent over pair tiles of 256 x RT):
+//   warp 0    TMA producer (both CTAs): its 128 rows of A8 + its N/2 rows of the planes per K-block
+//             into a kStages-deep 128B-swizzled ring; every copy signals the LEADER's full barrier
+//   warp 1    MMA issuer (leader CTA only): 4 tcgen05.mma per K-block; tcgen05.commit multicasts
+//             the "slot free" / "accumulator full" arrivals to both CTAs
+//   warp 2    TMEM allocator (512 columns = 2 accumulator buffers)
+//   warps 4-7 epilogue: tcgen05.ld -> exact recombination -> fused epilogue (MID / FINAL / COUNTS)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace srk {
+namespace x2 {
+
+constexpr int BMC = 128;        // A8 rows per CTA (= TMEM lanes)
+constexpr int BK = 128;         // bytes of K per pipeline stage (= one 128B swizzle atom)
+constexpr int UMMA_K = 32;      // K per tcgen05.mma for 8-bit operands
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kSmemLimit = 232448;
+constexpr int kAccStride = 256; // TMEM columns per accumulator buffer
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address
+
+template <int NS>
+struct Cfg {
+  static constexpr int RT = NS == 1 ? 256 : NS == 2 ? 128 : 64;     // rows of V per tile
+  static constexpr int N = NS * RT;                                 // UMMA N (multiple of 32)
+  static constexpr int NH = N / 2;                                  // N-side rows held by each CTA
+  static constexpr int BR = NS == 3 ? 32 : (NS == 4 ? 64 : 128);    // rows per TMA box (divides NH and RT)
+  static constexpr int kBoxes = NH / BR;
+  static constexpr int kStageBytes = BMC * BK + NH * BK;
+  static constexpr int kColfacBytes = 2 * 2 * RT * 8;               // 2 buffers x 2 vectors
+  static constexpr int kStagesRaw = (kSmemLimit - 1024 - 256 - kColfacBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kColfacBytes + 256;
+  static_assert(N % 32 == 0 && N <= 256, "invalid UMMA N for cta_group::2 kind::i8");
+  static_assert(NH % BR == 0 && RT % BR == 0, "box rows must divide the CTA half and the plane block");
+  static_assert(kStages >= 3, "not enough shared memory for a pipeline");
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes are
+// counted on the leader CTA's barrier (rank bit cleared).
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs] * B[smem of both CTAs]^T, u8 x u8 -> s32
+__device__ __forceinline__ void mma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives (in both CTAs of the pair) on the barrier at this offset once every tcgen05.mma issued
+// so far by this thread has completed.
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major operand tile, rows of 128 B, 128B swizzle: 8-row groups are 1024 B apart (SBO),
+// LBO unused for swizzled K-major layouts (encoded 1), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::i8 instruction descriptor: D = s32, A = B = u8, both K-major, M = 256 (pair), N
+template <int N>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// exact value of sum_p acc_p * 256^(NS-1-p)
+template <int NS>
+__device__ __forceinline__ double combine(const uint32_t (&a)[NS][16], int x) {
+  long long v = 0;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) v = (v << 8) + (long long)(int)a[s][x];
+  return (double)v;
+}
+
+struct Params {
+  int layout;
+  int64_t M, R, K;
+  srk_rowbound in_rowbound;
+  // MID
+  uint8_t* out_planes; int64_t ld_outp; int64_t out_plane_stride;
+  srk_rowbound out_rowbound;
+  // FINAL
+  const double* g_a; const double* g_v;
+  const uint16_t* counts; int64_t ld_counts; int add_counts, use_evidence;
+  double* out_f64; int64_t ld_out; int64_t diag_offset;
+  EpilogueDev epi;
+  double* maxdiff; double* maxoff;
+  // COUNTS
+  uint16_t* out_counts; int64_t ld_out_counts;
+  // schedule
+  int tiles_j, tiles_r, group_j, total_tiles;
+  int kblock;
+};
+
+// Walks the pair tiles in the order: bands of `group_j` row blocks; inside a band the column
+// blocks are the outer loop and the row blocks the inner one, so the ~74 concurrently running
+// pairs share a compact block of operand panels in L2.  In the symmetric layout only tiles that
+// contain an element with j <= r are visited.
+template <int RT>
+struct TileWalk {
+  int jb, rb, band_lo, band_hi, tiles_j, tiles_r, group_j;
+  bool sym, done;
+  __device__ __forceinline__ bool needed(int j, int r) const { return !sym || (j * 256 <= r * RT + RT - 1); }
+  __device__ __forceinline__ void enter_band(int lo) {
+    band_lo = lo;
+    band_hi = min(lo + group_j, tiles_j);
+    jb = lo;
+    rb = sym ? (lo * 256) / RT : 0;
+    if (lo >= tiles_j || rb >= tiles_r) done = true;
+  }
+  __device__ __forceinline__ void init(const Params& p) {
+    tiles_j = p.tiles_j; tiles_r = p.tiles_r; group_j = p.group_j;
+    sym = p.layout == SRK_X2_SYMMETRIC;
+    done = false;
+    enter_band(0);
+  }
+  __device__ __forceinline__ void step() {
+    ++jb;
+    if (jb < band_hi && needed(jb, rb)) return;
+    ++rb;
+    jb = band_lo;
+    if (rb >= tiles_r) enter_band(band_hi);
+  }
+  __device__ __forceinline__ void advance(int n) {
+    for (int i = 0; i < n && !done; ++i) step();
+  }
+};
+
+template <int NS, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v, const Params p) {
+  using C = Cfg<NS>;
+  constexpr int RT = C::RT, N = C::N, kStages = C::kStages;
+  constexpr double kQ = (double)(1ull << (8 * NS));
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  double* colfac = reinterpret_cast<double*>(smem + kStages * C::kStageBytes);       // [2][2][RT]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes + C::kColfacBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int kblocks = (int)((p.K + BK - 1) / BK);
+  const int my_tiles = p.total_tiles > cluster_id ? (p.total_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_v);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                                  // both CTAs' barriers and TMEM are ready
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      TileWalk<RT> tw;
+      tw.init(p);
+      tw.advance(cluster_id);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int j0 = tw.jb * 256 + (int)cta * BMC;
+        const int r0 = tw.rb * RT;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * C::kStageBytes;
+          uint8_t* sb = sa + BMC * BK;
+          if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, j0);
+#pragma unroll
+          for (int b = 0; b < C::kBoxes; ++b) {
+            const int nrow = (int)cta * C::NH + b * C::BR;         // row of the concatenated N operand
+            const int plane = nrow / RT, rr = nrow % RT;
+            if (p.kblock > 0) {
+              const int k = kb * BK;
+              tma_load_4d(sb + b * C::BR * BK, &map_v, &full_bar[stage], k % p.kblock, r0 + rr, k / p.kblock, plane);
+            } else {
+              tma_load_3d(sb + b * C::BR * BK, &map_v, &full_bar[stage], kb * BK, r0 + rr, plane);
+            }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tw.advance(num_clusters);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && cta == 0) {
+      constexpr uint32_t idesc = make_idesc<N>();
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int b = t & 1;
+        mbar_wait(&tmem_empty[b], ((uint32_t)(t >> 1) & 1u) ^ 1u);    // both CTAs drained this buffer
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(b * kAccStride);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * C::kStageBytes);
+          const uint64_t desc_a = make_desc(sa);
+          const uint64_t desc_b = make_desc(sa + BMC * BK);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            mma_i8_pair(acc, desc_a + (uint64_t)((k * UMMA_K) >> 4), desc_b + (uint64_t)((k * UMMA_K) >> 4), idesc,
+                        (kb | k) ? 1u : 0u);
+          mma_commit_pair(&empty_bar[stage]);                 // slot reusable in both CTAs
+          if (kb == kblocks - 1) mma_commit_pair(&tmem_full[b]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - kEpiWarp0;                     // == warp % 4: TMEM lane quarter
+    const int et = ew * 32 + lane;                       // 0..127: TMEM lane = row of this CTA's half
+    const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+    TileWalk<RT> tw;
+    tw.init(p);
+    tw.advance(cluster_id);
+    double dmax = 0.0, omax = 0.0;
+    const bool sym = p.layout == SRK_X2_SYMMETRIC;
+    const bool trans = p.layout == SRK_X2_TRANSPOSED;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int b = t & 1;
+      const int64_t j = (int64_t)tw.jb * 256 + (int64_t)cta * BMC + et;     // row of A8 owned by this thread
+      const int64_t r0 = (int64_t)tw.rb * RT;
+      const bool jvalid = j < p.M;
+      // per-column factors of this tile (double-buffered; one named barrier per tile)
+      double* cf1 = colfac + (size_t)b * 2 * RT;
+      double* cf2 = cf1 + RT;
+      if (MODE != SRK_X2_COUNTS) {
+        for (int c = et; c < RT; c += 128) {
+          const int64_t r = r0 + c;
+          double f1 = 0.0, f2 = 0.0;
+          if (r < p.R) {
+            f1 = row_bound(p.in_rowbound, r) / kQ;
+            if (MODE == SRK_X2_FINAL) { f2 = p.epi.coef * p.g_v[r]; f1 *= f2; }
+          }
+          cf1[c] = f1;
+          cf2[c] = f2;
+        }
+        epi_bar_sync();
+      }
+      double rowf = 0.0;                                  // MID: Q / bound_out(j); FINAL: g_a[j]
+      if (jvalid) {
+        if (MODE == SRK_X2_MID) { const double bo = row_bound(p.out_rowbound, j); rowf = bo > 0.0 ? kQ / bo : 0.0; }
+        if (MODE == SRK_X2_FINAL) rowf = p.g_a[j];
+      }
+      mbar_wait(&tmem_full[b], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t acc = lane_base + (uint32_t)(b * kAccStride);
+
+      for (int c0 = 0; c0 < RT; c0 += 16) {
+        __syncwarp();                                     // reconverge after the divergent tails below
+        uint32_t a[NS][16];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) tmem_ld16(acc + s * RT + c0, a[s]);
+        tmem_wait_ld();
+        if (c0 + 16 >= RT) {                              // last read of this buffer: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[b], 0);
+        }
+        const int64_t rc = r0 + c0;                       // first V row of this chunk
+        if (!jvalid || rc >= p.R) continue;
+
+        if (MODE == SRK_X2_COUNTS) {
+          uint32_t w[8];
+#pragma unroll
+          for (int x = 0; x < 16; x += 2) {
+            const uint32_t lo = (rc + x < p.R) ? min(a[0][x], 65535u) : 0u;
+            const uint32_t hi = (rc + x + 1 < p.R) ? min(a[0][x + 1], 65535u) : 0u;
+            w[x >> 1] = lo | (hi << 16);
+          }
+          uint16_t* o = p.out_counts + j * p.ld_out_counts + rc;
+          if (rc + 16 <= p.ld_out_counts && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+#pragma unroll
+            for (int x = 0; x < 16; ++x)
+              if (rc + x < p.R) o[x] = (uint16_t)((w[x >> 1] >> (16 * (x & 1))) & 0xffffu);
+          }
+          continue;
+        }
+
+        if (MODE == SRK_X2_MID) {
+          if (rc + 16 > p.ld_outp) continue;
+          uint32_t w[NS][4];
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) w[s][x] = 0u;
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            double q = rint(combine<NS>(a, x) * cf1[c0 + x] * rowf);
+            if (!(q > 0.0)) q = 0.0;
+            if (q > kQ - 1.0) q = kQ - 1.0;
+            const unsigned long long qi = (unsigned long long)q;
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+              w[s][x >> 2] |= (uint32_t)((qi >> (8 * (NS - 1 - s))) & 0xffull) << (8 * (x & 3));
+          }
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            *reinterpret_cast<uint4*>(p.out_planes + s * p.out_plane_stride + j * p.ld_outp + rc) =
+                make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+          continue;
+        }
+
+        // ---------------------------------------------------------------- FINAL
+        const int64_t jd = j - p.diag_offset;             // V row that sits on the diagonal with j
+        if (sym && jd > rc + 15) continue;                // strictly below the diagonal: mirrored from above
+        double v[16];
+        if (!trans) {
+          // element (row j, column rc + x): contiguous for this thread
+          const int64_t base = j * p.ld_out + rc;
+          const bool full = rc + 16 <= p.R;
+          uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          if (p.counts) {
+            const uint16_t* cp = p.counts + j * p.ld_counts + rc;
+            if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+              const uint4 t0 = reinterpret_cast<const uint4*>(cp)[0], t1 = reinterpret_cast<const uint4*>(cp)[1];
+              cw[0] = t0.x; cw[1] = t0.y; cw[2] = t0.z; cw[3] = t0.w;
+              cw[4] = t1.x; cw[5] = t1.y; cw[6] = t1.z; cw[7] = t1.w;
+            } else {
+#pragma unroll
+              for (int x = 0; x < 16; ++x)
+                if (rc + x < p.R) cw[x >> 1] |= (uint32_t)cp[x] << (16 * (x & 1));
+            }
+          }
+          uint32_t ev[4] = {0u, 0u, 0u, 0u};
+          if (p.epi.evidence) {
+            const uint8_t* e = p.epi.evidence + j * p.epi.ld_evidence + rc;
+            if (full && ((reinterpret_cast<uintptr_t>(e) & 15) == 0)) {
+              const uint4 t0 = *reinterpret_cast<const uint4*>(e);
+              ev[0] = t0.x; ev[1] = t0.y; ev[2] = t0.z; ev[3] = t0.w;
+            } else {
+#pragma unroll
+              for (int x = 0; x < 16; ++x)
+                if (rc + x < p.R) ev[x >> 2] |= (uint32_t)e[x] << (8 * (x & 3));
+            }
+          }
+          double so[16];
+          const bool have_old = p.epi.s_old != nullptr;
+          if (have_old) {
+            const double* sp = p.epi.s_old + j * p.epi.ld_s_old + rc;
+            if (full && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+#pragma unroll
+              for (int x = 0; x < 16; x += 2) {
+                const double2 d2 = *reinterpret_cast<const double2*>(sp + x);
+                so[x] = d2.x; so[x + 1] = d2.y;
+              }
+            } else {
+#pragma unroll
+              for (int x = 0; x < 16; ++x) so[x] = (rc + x < p.R) ? sp[x] : 0.0;
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const int64_t r = rc + x;
+            const uint32_t cnt = (cw[x >> 1] >> (16 * (x & 1))) & 0xffffu;
+            double val = combine<NS>(a, x) * cf1[c0 + x];
+            if (p.add_counts) val += (double)cnt * cf2[c0 + x];
+            val *= rowf;
+            if (p.use_evidence) val *= evidence_factor(cnt);
+            else if (p.epi.evidence) val *= evidence_factor((ev[x >> 2] >> (8 * (x & 3))) & 0xffu);
+            if (p.epi.prior && r < p.R) val = (1.0 - p.epi.lambda) * val + p.epi.lambda * p.epi.prior[j * p.epi.ld_prior + r];
+            const bool live = r < p.R && !(sym && jd > r);
+            if (r == jd) val = 1.0; else if (live && val > omax) omax = val;
+            if (have_old && live) {
+              const double d = fabs(val - so[x]);
+              if (d > dmax) dmax = d;
+            }
+            v[x] = val;
+          }
+          double* orow = p.out_f64 + base;
+          if (full && !(sym && jd > rc) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+#pragma unroll
+            for (int x = 0; x < 16; x += 2) *reinterpret_cast<double2*>(orow + x) = make_double2(v[x], v[x + 1]);
+          } else {
+#pragma unroll
+            for (int x = 0; x < 16; ++x)
+              if (rc + x < p.R && !(sym && jd > rc + x)) orow[x] = v[x];
+          }
+          if (sym) {
+            // mirror: element (row r, column j); 32 lanes write 256 contiguous bytes per x
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+              const int64_t r = rc + x;
+              if (r < p.R && jd < r) p.out_f64[r * p.ld_out + j] = v[x];
+            }
+          }
+        } else {
+          // transposed: element (row rc + x, column j); every access is coalesced across lanes
+          uint32_t cnt[16];
+          double so[16];
+          const bool have_old = p.epi.s_old != nullptr;
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const int64_t r = rc + x;
+            cnt[x] = (p.counts && r < p.R) ? (uint32_t)p.counts[r * p.ld_counts + j] : 0u;
+            so[x] = (have_old && r < p.R) ? p.epi.s_old[r * p.epi.ld_s_old + j] : 0.0;
+          }
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const int64_t r = rc + x;
+            double val = combine<NS>(a, x) * cf1[c0 + x];
+            if (p.add_counts) val += (double)cnt[x] * cf2[c0 + x];
+            val *= rowf;
+            if (p.use_evidence) val *= evidence_factor(cnt[x]);
+            else if (p.epi.evidence && r < p.R) val *= evidence_factor(p.epi.evidence[r * p.epi.ld_evidence + j]);
+            if (p.epi.prior && r < p.R) val = (1.0 - p.epi.lambda) * val + p.epi.lambda * p.epi.prior[r * p.epi.ld_prior + j];
+            const bool live = r < p.R;
+            if (r == jd) val = 1.0; else if (live && val > omax) omax = val;
+            if (have_old && live) {
+              const double d = fabs(val - so[x]);
+              if (d > dmax) dmax = d;
+            }
+            if (live) p.out_f64[r * p.ld_out + j] = val;
+          }
+        }
+      }
+      tw.advance(num_clusters);
+    }
+    if (MODE == SRK_X2_FINAL) {
+      dmax = warp_max(dmax);
+      omax = warp_max(omax);
+      if (lane == 0) {
+        if (p.maxdiff && dmax > 0.0) atomic_max_nonneg(p.maxdiff, dmax);
+        if (p.maxoff && omax > 0.0) atomic_max_nonneg(p.maxoff, omax);
+      }
+    }
+  }
+
+  // teardown: no CTA may exit (or free TMEM) while its peer can still signal it
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(SRK_ERR_CUDA, "%s", "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SRK_ERR_CUDA, "cuTensorMapEncodeTiled failed%s (code %lld)", "", (long long)r);
+  return SRK_OK;
+}
+
+static int count_tiles(int tiles_j, int tiles_r, int rt, bool sym) {
+  if (!sym) return tiles_j * tiles_r;
+  long long total = 0;
+  for (int jb = 0; jb < tiles_j; ++jb) {
+    const int first = (jb * 256) / rt;
+    if (first < tiles_r) total += tiles_r - first;
+  }
+  return (int)total;
+}
+
+template <int NS, int MODE>
+static int launch(const srk_x2_args& a, cudaStream_t st) {
+  using C = Cfg<NS>;
+  CUtensorMap map_a, map_v;
+  int rc;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+    cuuint64_t strides[1] = {(cuuint64_t)a.lda};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BMC};
+    rc = make_map(&map_a, a.A8, 2, dims, strides, box);
+  }
+  if (rc) return rc;
+  if (a.in_kblock > 0) {
+    cuuint64_t dims[4] = {(cuuint64_t)a.in_kblock, (cuuint64_t)a.R, (cuuint64_t)(a.K / a.in_kblock), (cuuint64_t)NS};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ld_in, (cuuint64_t)a.in_kblock_stride, (cuuint64_t)a.in_plane_stride};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)C::BR, 1, 1};
+    rc = make_map(&map_v, a.in_planes, 4, dims, strides, box);
+  } else {
+    cuuint64_t dims[3] = {(cuuint64_t)a.K, (cuuint64_t)a.R, (cuuint64_t)NS};
+    const int64_t whole = a.ld_in * a.R;                      // a 1-plane operand still needs a legal stride
+    cuuint64_t strides[2] = {(cuuint64_t)a.ld_in, (cuuint64_t)(NS > 1 ? a.in_plane_stride : whole)};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)C::BR, 1};
+    rc = make_map(&map_v, a.in_planes, 3, dims, strides, box);
+  }
+  if (rc) return rc;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.layout = MODE == SRK_X2_FINAL ? a.layout : SRK_X2_DIRECT;
+  p.M = a.M; p.R = a.R; p.K = a.K;
+  p.in_rowbound = a.in_rowbound;
+  p.out_planes = a.out_planes; p.ld_outp = a.ld_outp; p.out_plane_stride = a.out_plane_stride;
+  p.out_rowbound = a.out_rowbound;
+  p.g_a = a.g_a; p.g_v = a.g_v;
+  p.counts = a.counts; p.ld_counts = a.ld_counts; p.add_counts = a.add_counts; p.use_evidence = a.use_evidence;
+  p.out_f64 = a.out_f64; p.ld_out = a.ld_out; p.diag_offset = a.diag_offset;
+  p.epi = to_dev(a.epi);
+  p.maxdiff = a.epi.maxdiff; p.maxoff = a.epi.maxoff;
+  p.out_counts = a.out_counts; p.ld_out_counts = a.ld_out_counts;
+  p.tiles_j = (int)((a.M + 255) / 256);
+  p.tiles_r = (int)((a.R + C::RT - 1) / C::RT);
+  p.group_j = 8;
+  p.total_tiles = count_tiles(p.tiles_j, p.tiles_r, C::RT, p.layout == SRK_X2_SYMMETRIC);
+  p.kblock = (int)a.in_kblock;
+
+  auto kern = i8x2_kernel<NS, MODE>;
+  SRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  int dev = 0, sms = 0;
+  SRK_CUDA_OK(cudaGetDevice(&dev));
+  SRK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(sms / 2 * 2), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  SRK_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+  if (max_clusters < 1) return fail(SRK_ERR_CUDA, "%s", "no CTA pair can be resident on this device");
+  int clusters = sms / 2 < max_clusters ? sms / 2 : max_clusters;
+  if (p.total_tiles < clusters) clusters = p.total_tiles;
+  if (clusters < 1) return SRK_OK;
+  cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+  SRK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_a, map_v, p));
+  return SRK_OK;
+}
+
+}  // namespace x2
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
+  SRK_REQUIRE(a, "null args");
+  SRK_REQUIRE(a->in_planes && a->A8, "null operand");
+  SRK_REQUIRE(a->M > 0 && a->R > 0 && a->K > 0, "empty problem");
+  SRK_REQUIRE(a->ld_in % 16 == 0 && a->lda % 16 == 0, "operand strides must be multiples of 16");
+  SRK_REQUIRE(((uintptr_t)a->in_planes % 16) == 0 && ((uintptr_t)a->A8 % 16) == 0, "operands must be 16-byte aligned");
+  SRK_REQUIRE(a->lda >= a->K, "lda smaller than K");
+  SRK_REQUIRE(a->M < (1ll << 31) - 512 && a->R < (1ll << 31) - 512, "too many rows for 32-bit tile coordinates");
+  if (a->in_kblock > 0) {
+    SRK_REQUIRE(a->in_kblock % 128 == 0 && a->K % a->in_kblock == 0 && a->ld_in >= a->in_kblock &&
+                    a->in_kblock_stride % 16 == 0, "K-blocked operand: in_kblock must be a multiple of 128 dividing K");
+  } else {
+    SRK_REQUIRE(a->ld_in >= a->K, "ld_in smaller than K");
+  }
+  SRK_REQUIRE(a->K < (1ll << 22), "K too large for exact int32 accumulation");
+  if (!srk_i8_supported()) return fail(SRK_ERR_UNSUPPORTED, "%s", "tcgen05 kind::i8 needs an sm_100 device");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->mode == SRK_X2_COUNTS) {
+    SRK_REQUIRE(a->ns == 1 && a->out_counts && a->ld_out_counts >= a->R, "COUNTS needs ns=1 and a uint16 output");
+    return x2::launch<1, SRK_X2_COUNTS>(*a, st);
+  }
+  SRK_REQUIRE(a->ns == 1 || a->in_plane_stride % 16 == 0, "plane stride must be a multiple of 16");
+  if (a->mode == SRK_X2_MID) {
+    SRK_REQUIRE(a->out_planes, "MID needs output planes");
+    SRK_REQUIRE(a->ld_outp % 16 == 0 && a->out_plane_stride % 16 == 0 && ((uintptr_t)a->out_planes % 16) == 0,
+                "output planes must be 16-byte aligned with ld multiple of 16");
+    SRK_REQUIRE(a->ld_outp >= a->R, "ld_outp smaller than R");
+    switch (a->ns) {
+      case 2: return x2::launch<2, SRK_X2_MID>(*a, st);
+      case 3: return x2::launch<3, SRK_X2_MID>(*a, st);
+      case 4: return x2::launch<4, SRK_X2_MID>(*a, st);
+    }
+    return fail(SRK_ERR_INVALID, "invalid argument: %s", "ns must be 2, 3 or 4");
+  }
+  if (a->mode == SRK_X2_FINAL) {
+    SRK_REQUIRE(a->out_f64 && a->g_a && a->g_v, "FINAL needs out_f64, g_a, g_v");
+    SRK_REQUIRE(a->layout == SRK_X2_DIRECT || a->layout == SRK_X2_SYMMETRIC || a->layout == SRK_X2_TRANSPOSED,
+                "unknown layout");
+    SRK_REQUIRE(!(a->use_evidence && a->epi.evidence), "evidence given twice (counts and epi.evidence)");
+    SRK_REQUIRE(!(a->add_counts || a->use_evidence) || a->counts, "counts missing");
+    if (a->layout == SRK_X2_TRANSPOSED) {
+      SRK_REQUIRE(a->ld_out >= a->M, "ld_out smaller than M (transposed layout)");
+    } else {
+      SRK_REQUIRE(a->ld_out >= a->R, "ld_out smaller than R");
+    }
+    if (a->layout == SRK_X2_SYMMETRIC)
+      SRK_REQUIRE(a->M == a->R && a->diag_offset == 0 && a->epi.prior == nullptr,
+                  "symmetric layout needs a square product without a prior");
+    switch (a->ns) {
+      case 2: return x2::launch<2, SRK_X2_FINAL>(*a, st);
+      case 3: return x2::launch<3, SRK_X2_FINAL>(*a, st);
+      case 4: return x2::launch<4, SRK_X2_FINAL>(*a, st);
+    }
+    return fail(SRK_ERR_INVALID, "invalid argument: %s", "ns must be 2, 3 or 4");
+  }
+  return fail(SRK_ERR_INVALID, "invalid argument: %s", "unknown mode");
+}

@@ -45,11 +45,25 @@ def weight(G: HostOperator, device=None) -> WeightOperator:
 
 class EvidenceMatrix:
     """Evidence ``1 - 0.5 ** (A A^T)`` (SimRank.py:315-316) held on the device as uint8
-    common-neighbour counts (a count >= 54 already gives exactly 1.0 in float64).
-    ``np.asarray(E)`` materialises the float64 ndarray of the reference."""
+    common-neighbour counts (a count >= 54 already gives exactly 1.0 in float64), computed on
+    first use: the tensor-core path reads the evidence of an operator's own pattern from the
+    uint16 ``A A^T`` counts it needs anyway.  ``np.asarray(E)`` materialises the float64 ndarray
+    of the reference."""
 
-    def __init__(self, counts: torch.Tensor, n: int):
-        self.counts, self.n = counts, n
+    def __init__(self, G: HostOperator, device=None, mode: str = "auto"):
+        self.op, self.n, self._device, self._mode, self._counts = G, G.M, device, mode, None
+
+    @property
+    def counts(self) -> torch.Tensor:
+        if self._counts is None:
+            self._counts = _device_op(self.op, self._device).evidence_counts(self._mode)
+        return self._counts
+
+    def is_pattern_of(self, op: HostOperator) -> bool:
+        """True when this evidence was computed from the 0/1 pattern of ``op`` (W = diag(spread) G
+        shares the pattern of G) and no row is dead (g <= 0 rows count as empty, SimRank.py:315)."""
+        same = self.op.indices is op.indices and self.op.indptr is op.indptr and self.op.M == op.M
+        return bool(same and not (self.op.dead.astype(bool) & (self.op.deg > 0)).any())
 
     @property
     def shape(self):
@@ -62,8 +76,8 @@ class EvidenceMatrix:
 
 
 def evidence(G: HostOperator, device=None, mode: str = "auto") -> EvidenceMatrix:
-    dop = _device_op(G, device)
-    return EvidenceMatrix(dop.evidence_counts(mode), G.M)
+    _eng.require_cuda(device)
+    return EvidenceMatrix(G, device, mode)
 
 
 def _prior_tensor(prior, n, device):
@@ -99,35 +113,52 @@ def _local_rows(t, n, rank, world):
     return t[plan.start(rank):plan.stop(rank)]
 
 
-def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mode=None, device=None, slices=3):
+def _evidence_args(evidence, op: HostOperator, mode: str):
+    """(uint8 counts tensor or None, take-it-from-the-pattern flag) for one update."""
+    if evidence is None:
+        return None, False
+    if mode == "i8" and evidence.is_pattern_of(op):
+        return None, True
+    return evidence.counts, False
+
+
+def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mode=None, device=None, slices=None):
     dop = _device_op(op, device)
-    ev = evidence.counts if evidence is not None else None
     pr = _prior_tensor(prior, op.M, dop.device)
     rank, world = _world()
     if world > 1:                      # one process per GPU: S row-sharded, tensor-core path
         from . import dist as _sd
+        ev = evidence.counts if evidence is not None else None
         return _sd.ShardedDirectedSolver(op, C, _local_rows(ev, op.M, rank, world),
                                          _local_rows(pr, op.M, rank, world), lbd, _mode_with_prior(mode, prior),
                                          slices, dop.device)
-    return _eng.DirectedSolver(dop, C, ev, pr, lbd, _mode_with_prior(mode, prior), slices)
+    mode = _eng.choose_mode(op, _mode_with_prior(mode, prior))
+    ev, from_pattern = _evidence_args(evidence, op, mode)
+    return _eng.DirectedSolver(dop, C, ev, pr, lbd, mode, slices,
+                               evidence_from_pattern=from_pattern)
 
 
 def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=None, evidence2=None, prior1=None,
-                     prior2=None, lbd1=0.0, lbd2=0.0, mode=None, device=None, slices=3):
+                     prior2=None, lbd1=0.0, lbd2=0.0, mode=None, device=None, slices=None):
     d12, d21 = _device_op(op12, device), _device_op(op21, device)
-    e1 = evidence1.counts if evidence1 is not None else None
-    e2 = evidence2.counts if evidence2 is not None else None
     p1 = _prior_tensor(prior1, op12.M, d12.device)
     p2 = _prior_tensor(prior2, op21.M, d21.device)
     rank, world = _world()
     if world > 1:
         from . import dist as _sd
+        e1 = evidence1.counts if evidence1 is not None else None
+        e2 = evidence2.counts if evidence2 is not None else None
         return _sd.ShardedBipartiteSolver(op12, op21, C1, C2, _local_rows(e1, op12.M, rank, world),
                                           _local_rows(e2, op21.M, rank, world), _local_rows(p1, op12.M, rank, world),
                                           _local_rows(p2, op21.M, rank, world), lbd1, lbd2,
                                           _mode_with_prior(mode, prior1, prior2), slices, d12.device)
-    return _eng.BipartiteSolver(d12, d21, C1, C2, e1, e2, p1, p2, lbd1, lbd2,
-                                _mode_with_prior(mode, prior1, prior2), slices)
+    mode = _mode_with_prior(mode, prior1, prior2)
+    m1, m2 = _eng.choose_mode(op12, mode), _eng.choose_mode(op21, mode)
+    mode = m1 if m1 == m2 else "csr"
+    e1, pat1 = _evidence_args(evidence1, op12, mode)
+    e2, pat2 = _evidence_args(evidence2, op21, mode)
+    return _eng.BipartiteSolver(d12, d21, C1, C2, e1, e2, p1, p2, lbd1, lbd2, mode, slices,
+                                evidence1_from_pattern=pat1, evidence2_from_pattern=pat2)
 
 
 class Result:

@@ -12,9 +12,13 @@ plus the reduction behind ``_converged`` (SimRank.py:74) is two kernel launches 
 
   csr mode   T = (G S)^T                     srk_csr_half_f64   (gather, transposed store)
              S = epilogue((G T)^T)           srk_csr_half_f64   (fused epilogue, in place)
-  i8 mode    U = A S  (re-quantised planes)  srk_i8_half MID    (tcgen05 kind::i8)
-             S = epilogue(g g^T o (U A^T))   srk_i8_half FINAL  (fused epilogue, in place,
-                                                                 + planes of the new S)
+  i8 mode    planes(S_off), exact row bounds srk_slice_rows_max_f64   (S = I + S_off)
+             U = A S_off (re-quantised)      srk_x2_half MID    (tcgen05 cta_group::2 kind::i8)
+             S = epilogue(g g^T o (A U^T + A A^T))
+                                             srk_x2_half FINAL  (fused epilogue, in place; only
+                                                                 the upper triangle is computed,
+                                                                 the lower one is mirrored)
+  i8v1 mode  the first-generation single-CTA kernel (srk_i8_half), kept for comparison
 
 S is updated in place: each epilogue thread reads S_old[r, c] for max|dS| and then writes
 S_new[r, c]; nothing else reads S during the second half.
@@ -31,7 +35,10 @@ import torch
 from . import _lib
 from .graph import HostOperator
 
-_NS_DEFAULT = 3
+_NS_DEFAULT = None          # None/'auto': fewest planes whose a-priori error bound meets ERR_BUDGET
+# Guaranteed max-abs deviation from the float64 iteration caused by the fixed-point planes
+# (the north-star tolerance is 1e-6; the float64 epilogue itself differs by ~1e-16).
+ERR_BUDGET = 5e-7
 
 
 def _ptr(t):
@@ -67,6 +74,7 @@ class DeviceOperator:
         self.g = torch.from_numpy(self.g_host).to(device)
         self.dead = torch.from_numpy(host.dead).to(device)
         self._a8 = None
+        self._cnt16 = None
 
     def with_scale(self, factor: np.ndarray) -> "DeviceOperator":
         """``diag(factor) * G``: same pattern, rescaled rows (SimRank++ W = diag(spread) G,
@@ -88,6 +96,24 @@ class DeviceOperator:
                                                        _ptr(a8), self.lda, _stream()), "srk_csr_to_dense_u8")
             self._a8 = a8
         return self._a8
+
+    def pattern_counts(self) -> torch.Tensor:
+        """uint16 common-neighbour counts ``A A^T`` of the 0/1 pattern (saturating at 65535), the
+        unit-diagonal term of the tensor-core path: ``A S A^T = A S_off A^T + A A^T``.  Held as an
+        int16 tensor (torch has no arithmetic on uint16; only the bytes matter)."""
+        if self._cnt16 is None:
+            ld = _round_up(max(self.M, 1), 8)
+            cnt = torch.empty((self.M, ld), dtype=torch.int16, device=self.device)
+            a8 = self.dense_u8()
+            a = _lib.X2Args()
+            a.mode, a.ns = _lib.SRK_X2_COUNTS, 1
+            a.M, a.R, a.K = self.M, self.M, self.K
+            a.A8, a.lda = a8.data_ptr(), self.lda
+            a.in_planes, a.ld_in, a.in_plane_stride = a8.data_ptr(), self.lda, a8.numel()
+            a.out_counts, a.ld_out_counts = cnt.data_ptr(), ld
+            _lib.check(_lib.load().srk_x2_half(C.byref(a), _stream()), "srk_x2_half(COUNTS)")
+            self._cnt16 = cnt
+        return self._cnt16
 
     def row_spread(self, vals: torch.Tensor | None = None) -> torch.Tensor:
         """exp(-var) of the nonzeros of each row (SimRank.py:326-332)."""
@@ -123,23 +149,51 @@ class DeviceOperator:
 def choose_mode(op: HostOperator, requested: str | None = None) -> str:
     """'csr' (exact f64 gather path) or 'i8' (tcgen05 fixed-point path)."""
     mode = (requested or os.environ.get("SIMRANK_B200_MODE", "auto")).lower()
-    if mode in ("csr", "i8"):
+    if mode in ("csr", "i8", "i8v1"):
         return mode
     if mode != "auto":
         raise ValueError(f"unknown mode {mode!r}")
     ok = bool(_lib.load().srk_i8_supported()) and bool(np.all(op.g >= 0)) and bool(np.all(np.isfinite(op.g)))
     dense_bytes = op.M * _round_up(op.K, 128)
     density = op.nnz / max(1, op.M * op.K)
+    # the A A^T term of the tensor-core path is held as uint16 counts
+    top2 = np.sort(op.deg)[-2:] if op.M >= 2 else op.deg
+    ok = ok and (op.M < 2 or int(top2[0]) < 65535)
     return "i8" if ok and min(op.M, op.K) >= 1024 and dense_bytes <= (16 << 30) and density >= 1.0 / 1024 else "csr"
 
 
 # --------------------------------------------------------------------------- one similarity matrix
+def choose_slices(requested, coef: float, blend: float, rho_max: float, s_off_max: float) -> int:
+    """Planes per matrix for one update of the tensor-core path.
+
+    Rounding happens twice per update, when S_off and U = A S_off are cut into NS uint8 planes with
+    bounds b_S(r) = max_k S_off[r,k] and b_U(j) = deg_j * max(S_off); each is at most half a step of
+    bound / 256^NS.  Propagated through ``coef * g g^T o (A . A^T)`` the two add up to at most
+    ``delta = blend * coef * rho_max^2 * max(S_off) / 256^NS`` per update (rho = row sums of G,
+    1 for unweighted graphs), and the update contracts earlier errors by kappa = blend * coef *
+    rho_max^2, so the deviation from the float64 iteration never exceeds delta / (1 - kappa).  The
+    smallest NS in {2, 3, 4} that keeps this below ERR_BUDGET is used; an integer request is
+    honoured as is."""
+    if requested not in (None, "auto"):
+        ns = int(requested)
+        if ns not in (2, 3, 4):
+            raise ValueError("slices must be 2, 3, 4 or 'auto'")
+        return ns
+    kappa = blend * coef * rho_max * rho_max
+    amplification = 1.0 / (1.0 - kappa) if kappa < 0.999 else 1000.0
+    for ns in (2, 3, 4):
+        if kappa * s_off_max / 256.0 ** ns * amplification <= ERR_BUDGET:
+            return ns
+    return 4
+
+
 class _Half:
     """State for updating ONE similarity matrix S_out (n_out x n_out) from S_in (n_in x n_in)
     through ``op`` (n_out x n_in):  S_out <- epilogue(coef * G S_in G^T).  The directed classes
     use one instance with S_in is S_out; the bipartite classes use two (SimRank.py:297-302)."""
 
-    def __init__(self, op: DeviceOperator, coef: float, mode: str, ns: int, evidence=None, prior=None, lbd=0.0):
+    def __init__(self, op: DeviceOperator, coef: float, mode: str, ns, evidence=None, prior=None, lbd=0.0,
+                 evidence_from_pattern=False):
         self.op, self.coef, self.mode, self.ns = op, float(coef), mode, ns
         self.n_out, self.n_in = op.M, op.K
         dev = op.device
@@ -152,30 +206,43 @@ class _Half:
         self.scal = torch.zeros(2, dtype=torch.float64, device=dev)        # [maxdiff, maxoff]
         self.events = None          # set to a list to collect (name, start, end) CUDA events per launch
         self.maxoff = 0.0                                                  # max off-diagonal of current S
+        self.slices_used = []                                              # NS of every update (i8 mode)
         if mode == "csr":
             self.ldt = _round_up(max(self.n_out, 1), 16)
             self.T = torch.empty((self.n_in, self.ldt), dtype=torch.float64, device=dev)
-        else:
-            host = op.host
-            self.rho = op.g_host * host.deg                                # row sums of G
-            self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
-            self.prior_max = float(prior.max()) if prior is not None else 0.0
-            self.ldp = _round_up(max(self.n_out, 1), 128)                  # planes of S_out
-            self.ldu = _round_up(max(self.n_in, 1), 128)                   # planes of U (n_out x n_in)
+            return
+        host = op.host
+        self.rho = op.g_host * host.deg                                    # row sums of G
+        self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
+        self.prior_max = float(prior.max()) if prior is not None else 0.0
+        self.ldp = _round_up(max(self.n_out, 1), 128)                      # planes of S_out
+        self.ldu = _round_up(max(self.n_in, 1), 128)                       # planes of U (n_out x n_in)
+        self.a8 = op.dense_u8()
+        self.deg_dev = torch.from_numpy(host.deg.astype(np.float64)).to(dev)
+        if mode == "i8v1":
+            ns = self.ns = 3 if ns in (None, "auto") else int(ns)
             self.planes = torch.zeros((ns, self.n_out, self.ldp), dtype=torch.uint8, device=dev)   # S_off = 0
             self.planes_U = torch.empty((ns, self.n_out, self.ldu), dtype=torch.uint8, device=dev)
-            self.a8 = op.dense_u8()
-            self.deg_dev = torch.from_numpy(host.deg.astype(np.float64)).to(dev)
             self.rho_dev = torch.from_numpy(np.ascontiguousarray(self.rho)).to(dev)
             # bound(r) of the current planes of S_off as (mul, add) over rho, and its maximum
             self.bound_S = (0.0, 1.0)                                      # planes are all zero: any bound
             self.bound_S_max = 1.0
+            return
+        # ---- paired-SM path: planes are cut from S right before they are used, with exact bounds
+        self.ns_alloc = 3 if ns in (None, "auto") else int(ns)
+        self.planes = None                                                 # allocated on first use as a source
+        self.planes_U = torch.empty((self.ns_alloc, self.n_out, self.ldu), dtype=torch.uint8, device=dev)
+        self.bound_vec = torch.zeros(max(self.n_out, 1), dtype=torch.float64, device=dev)
+        self.evidence_from_pattern = bool(evidence_from_pattern)
+        self.counts = op.pattern_counts()                                  # uint16 A A^T, [n_out, ldc]
+        self.version = 0                                                   # bumped by every update of S
+        self._sliced = (-1, 0)                                             # (version, ns) of self.planes
 
     # -- epilogue description shared by both modes
     def _epilogue(self) -> _lib.Epilogue:
         e = _lib.Epilogue()
         e.coef = self.coef
-        if self.evidence is not None:
+        if self.evidence is not None and not getattr(self, "evidence_from_pattern", False):
             e.evidence, e.ld_evidence = self.evidence.data_ptr(), self.evidence.stride(0)
         if self.prior is not None:
             e.prior, e.ld_prior, e.lambda_ = self.prior.data_ptr(), self.prior.stride(0), self.lbd
@@ -196,6 +263,21 @@ class _Half:
         self.events.append((name, a, b))
         return rc
 
+    def _planes_for(self, ns: int) -> torch.Tensor:
+        """Planes of the off-diagonal part of the CURRENT S with the exact row maxima as bounds
+        (srk_slice_rows_max_f64); cached per (version of S, ns)."""
+        if self.planes is None or self.planes.shape[0] < ns:
+            self.planes = torch.empty((max(ns, self.ns_alloc), self.n_out, self.ldp), dtype=torch.uint8,
+                                      device=self.S.device)
+            self._sliced = (-1, 0)
+        if self._sliced != (self.version, ns):
+            lib = _lib.load()
+            _lib.check(self._timed("slice_rows_max", lambda: lib.srk_slice_rows_max_f64(
+                _ptr(self.S), self.ld, self.n_out, self.n_out, 0, ns, _ptr(self.planes), self.ldp,
+                self.planes.stride(0), _ptr(self.bound_vec), _stream())), "srk_slice_rows_max_f64")
+            self._sliced = (self.version, ns)
+        return self.planes
+
     def update(self, src: "_Half") -> None:
         """Launch the two half-products (asynchronous).  ``src`` holds S_in (its S / planes)."""
         lib = _lib.load()
@@ -210,7 +292,50 @@ class _Half:
                 _ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M, _ptr(self.T), self.ldt, self.n_out,
                 _ptr(self.S), self.ld, C.byref(epi), _stream())), "srk_csr_half_f64(second)")
             return
-        # ---- i8: a-priori bounds of the two results, as affine forms over constant node vectors.
+        if self.mode == "i8v1":
+            return self._update_v1(src)
+        # ---- paired-SM tensor-core path
+        blend = (1.0 - self.lbd) if self.prior is not None else 1.0
+        ns = choose_slices(self.ns, self.coef, blend, self.rho_max, src.maxoff)
+        if ns > self.planes_U.shape[0]:
+            self.planes_U = torch.empty((ns, self.n_out, self.ldu), dtype=torch.uint8, device=self.S.device)
+        self.slices_used.append(ns)
+        planes_in = src._planes_for(ns)
+        # U[j, r] = sum_{k in N(j)} S_off[r, k] <= deg_j * max(S_off); the guard keeps a value that
+        # attains the bound below the last level (>= 256^NS / (256^NS - 1) for every NS >= 2)
+        guard = 1.0 + 2.0 ** -14
+        bound_U = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard, 0.0)
+
+        a = _lib.X2Args()
+        a.mode, a.ns = _lib.SRK_X2_MID, ns
+        a.M, a.R, a.K = self.n_out, self.n_in, self.n_in
+        a.A8, a.lda = self.a8.data_ptr(), self.op.lda
+        a.in_planes, a.ld_in, a.in_plane_stride = planes_in.data_ptr(), src.ldp, planes_in.stride(0)
+        a.in_rowbound = _lib.RowBound.of(src.bound_vec.data_ptr(), 1.0, 0.0)
+        a.out_planes, a.ld_outp, a.out_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
+        a.out_rowbound = bound_U
+        _lib.check(self._timed("x2_half_mid", lambda: lib.srk_x2_half(C.byref(a), _stream())), "srk_x2_half(MID)")
+
+        b = _lib.X2Args()
+        b.mode, b.ns = _lib.SRK_X2_FINAL, ns
+        # the mirrored store needs a symmetric epilogue: evidence counts are, an arbitrary prior is not
+        b.layout = _lib.SRK_X2_SYMMETRIC if self.prior is None else _lib.SRK_X2_DIRECT
+        b.M, b.R, b.K = self.n_out, self.n_out, self.n_in
+        b.A8, b.lda = self.a8.data_ptr(), self.op.lda
+        b.in_planes, b.ld_in, b.in_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
+        b.in_rowbound = bound_U
+        b.g_a = b.g_v = self.op.g.data_ptr()
+        b.counts, b.ld_counts, b.add_counts = self.counts.data_ptr(), self.counts.stride(0), 1
+        b.use_evidence = 1 if self.evidence_from_pattern else 0
+        b.out_f64, b.ld_out, b.diag_offset = self.S.data_ptr(), self.ld, 0
+        b.epi = self._epilogue()
+        _lib.check(self._timed("x2_half_final", lambda: lib.srk_x2_half(C.byref(b), _stream())),
+                   "srk_x2_half(FINAL)")
+        self.version += 1
+
+    def _update_v1(self, src: "_Half") -> None:
+        """First-generation kernel: planes written by the FINAL epilogue with a-priori bounds."""
+        lib = _lib.load()
         # The planes of S_in were cut with src.bound_S; the ACTUAL off-diagonal maximum of S_in is
         # known from its epilogue (src.maxoff) and tightens everything derived from it.
         guard = 1.0 + 2.0 ** -20          # keeps values that attain a bound exactly off the clip
@@ -251,10 +376,10 @@ class _Half:
         self._pending_bound = ((mul, add), mul * self.rho_max + add)
 
     def finish(self) -> float:
-        """Read back max|dS| (host sync) and commit the bounds of the new S."""
+        """Read back max|dS| (host sync) and commit the range of the new S."""
         maxdiff, maxoff = self.scal.tolist()
         self.maxoff = maxoff
-        if self.mode == "i8":
+        if self.mode == "i8v1":
             self.bound_S, self.bound_S_max = self._pending_bound
         return maxdiff
 
@@ -273,9 +398,10 @@ class FitInfo:
 class DirectedSolver:
     """``S <- [E o] C * W S W^T [blended with a prior]; diag <- 1`` (SimRank.py:139, :361, :453)."""
 
-    def __init__(self, op: DeviceOperator, C_: float, evidence=None, prior=None, lbd=0.0, mode=None, ns=_NS_DEFAULT):
+    def __init__(self, op: DeviceOperator, C_: float, evidence=None, prior=None, lbd=0.0, mode=None, ns=_NS_DEFAULT,
+                 evidence_from_pattern=False):
         self.mode = choose_mode(op.host, mode)
-        self.half = _Half(op, C_, self.mode, ns, evidence, prior, lbd)
+        self.half = _Half(op, C_, self.mode, ns, evidence, prior, lbd, evidence_from_pattern)
 
     def step(self) -> float:
         self.half.update(self.half)
@@ -290,11 +416,12 @@ class BipartiteSolver:
     """Gauss-Seidel alternation of SimRank.py:297-302 (and :419-424, :487-492)."""
 
     def __init__(self, op12: DeviceOperator, op21: DeviceOperator, C1: float, C2: float, evidence1=None,
-                 evidence2=None, prior1=None, prior2=None, lbd1=0.0, lbd2=0.0, mode=None, ns=_NS_DEFAULT):
+                 evidence2=None, prior1=None, prior2=None, lbd1=0.0, lbd2=0.0, mode=None, ns=_NS_DEFAULT,
+                 evidence1_from_pattern=False, evidence2_from_pattern=False):
         m1, m2 = choose_mode(op12.host, mode), choose_mode(op21.host, mode)
         self.mode = m1 if m1 == m2 else "csr"
-        self.h1 = _Half(op12, C1, self.mode, ns, evidence1, prior1, lbd1)     # S1 from S2 through G12
-        self.h2 = _Half(op21, C2, self.mode, ns, evidence2, prior2, lbd2)     # S2 from S1 through G21
+        self.h1 = _Half(op12, C1, self.mode, ns, evidence1, prior1, lbd1, evidence1_from_pattern)   # S1 from S2 (G12)
+        self.h2 = _Half(op21, C2, self.mode, ns, evidence2, prior2, lbd2, evidence2_from_pattern)   # S2 from S1 (G21)
 
     def step(self):
         self.h1.update(self.h2)

@@ -33,6 +33,29 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.I8Args) == 8 + 3 * 8 + 5 * 8 + 24 + 2 * 8 + 8 + 8 + 2 * 8 + 2 * 8 + 3 * 8 + 24 + 80
 
 
+def test_struct_layouts_match_c_compiler(tmp_path):
+    """sizeof/offsetof of every ABI struct as gcc sees the header == the ctypes mirror."""
+    import ctypes as C
+    import subprocess
+    structs = {"srk_epilogue": _lib.Epilogue, "srk_rowbound": _lib.RowBound, "srk_i8_args": _lib.I8Args,
+               "srk_x2_args": _lib.X2Args}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "simrank_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname.rstrip("_")}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 @pytest.mark.parametrize("weighted", [False, True])
 def test_directed_graph_matches_oracle(weighted):
     df = notebook_directed_df()
