@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 2
+#define SRK_ABI_VERSION 3
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -165,10 +165,13 @@ int srk_i8_supported(void);
  * proportional to max(S_off) instead of 1, which is what lets NS = 2 meet the 1e-6 budget on
  * graphs whose similarities are small (DESIGN.md "precision").
  *
- * mode SRK_X2_MID   : U[j, r] = D[j,r] * bound_in(r) / 256^NS  re-quantised with out_rowbound(j)
+ * The row bounds of U (out_rowbound of MID = in_rowbound of FINAL) are rounded UP to powers of two
+ * by the kernel, 2^f >= bound with f >= 8 NS - 46: the caller passes the same srk_rowbound to both.
+ *
+ * mode SRK_X2_MID   : U[j, r] = D[j,r] * bound_in(r) / 256^NS  re-quantised with 2^f(j) >= out_rowbound(j)
  *                     into out_planes (row j, column r).  With V = planes of S_off this is
  *                     U = A S_off, the first half `G.dot(S)` of SimRank.py:139 without g.
- * mode SRK_X2_FINAL : x = coef * g_a[j] * g_v[r] * (D[j,r] * bound_in(r) / 256^NS + counts)
+ * mode SRK_X2_FINAL : x = coef * g_a[j] * g_v[r] * (D[j,r] * 2^f(r) / 256^NS + counts), 2^f(r) >= bound_in(r),
  *                     followed by the srk_epilogue chain (the evidence factor is taken from `counts`
  *                     when use_evidence != 0, else from epi.evidence if given), stored as f64.
  *                     layout DIRECT     element (row j, column r) of out_f64/s_old/prior/counts;
@@ -178,6 +181,11 @@ int srk_i8_supported(void);
  *                                       bit-exactly symmetric (needs symmetric evidence, no prior);
  *                     layout TRANSPOSED element (row r, column j): row-sharded multi-GPU, where the
  *                                       local rows of S are the N-side operand.
+ *                                       With mirror_out != NULL every value is ALSO stored at
+ *                                       mirror_out[j * ld_mirror + mirror_col0 + r] -- the mirrored
+ *                                       block of the symmetric result, written straight into the
+ *                                       memory of the GPU that owns row j (a peer-mapped pointer over
+ *                                       NVLink), so no rank computes both (q,p) and (p,q).
  *                     The diagonal is the element with j == r + diag_offset.
  * mode SRK_X2_COUNTS: out_counts[j, r] = min(D[j,r], 65535) as uint16 (ns must be 1, V = a 0/1
  *                     matrix as a single plane): `np.dot((G>0).astype(int), (G>0).T.astype(int))`
@@ -201,6 +209,7 @@ typedef struct srk_x2_args {
   const uint16_t* counts; int64_t ld_counts;                         /* FINAL (indexed like out_f64) */
   int add_counts, use_evidence;
   double* out_f64; int64_t ld_out; int64_t diag_offset;              /* FINAL */
+  double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;        /* FINAL, TRANSPOSED: see above */
   srk_epilogue epi;                                                  /* FINAL */
   uint16_t* out_counts; int64_t ld_out_counts;                       /* COUNTS */
 } srk_x2_args;

@@ -223,7 +223,7 @@ __global__ void slice_rows_kernel(const double* __restrict__ V, int64_t ldv, int
 // ------------------------------------------------------------------------------------------
 // Planes with the exact per-row bound (srk_slice_rows_max_f64): one CTA per row, two passes over
 // the row (the second one is served by L2: a row is at most a few hundred KB).
-constexpr int SLICE_THREADS = 256;
+constexpr int SLICE_THREADS = 512;
 __device__ __forceinline__ void load16(const double* p, int64_t k0, int64_t K, bool vec, double (&v)[16]) {
   if (vec && k0 + 16 <= K) {
 #pragma unroll
@@ -476,7 +476,9 @@ extern "C" int srk_slice_rows_max_f64(const double* V, int64_t ldv, int64_t R, i
   int dev = 0, sms = 0;
   SRK_CUDA_OK(cudaGetDevice(&dev));
   SRK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (int64_t)sms * 8;
+  // two rows per SM in flight: 296 rows of a few hundred KB stay inside the 126 MB L2 between the
+  // two passes, and 512 threads x 128 B per row keep enough loads in flight for HBM
+  const int64_t want = (int64_t)sms * 2;
   const unsigned blocks = (unsigned)(R < want ? R : want);
   cudaStream_t st = (cudaStream_t)stream;
   switch (ns) {

@@ -183,14 +183,52 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-// exact value of sum_p acc_p * 256^(NS-1-p)
+// exact value of sum_p acc_p * 256^(NS-1-p) (< 2^(8 NS + 22) for every supported K)
 template <int NS>
-__device__ __forceinline__ double combine(const uint32_t (&a)[NS][16], int x) {
-  long long v = 0;
+__device__ __forceinline__ unsigned long long combine(const uint32_t (&a)[NS][16], int x) {
+  unsigned long long v = 0;
 #pragma unroll
-  for (int s = 0; s < NS; ++s) v = (v << 8) + (long long)(int)a[s][x];
-  return (double)v;
+  for (int s = 0; s < NS; ++s) v = (v << 8) + (unsigned long long)a[s][x];
+  return v;
 }
+
+// The planes of U = A S_off (MID output, FINAL input) are cut with POWER-OF-TWO row bounds: the
+// caller's bound b is rounded up to 2^f.  That costs at most one bit of U's resolution and turns
+// every per-element scaling that involves the bound into integer shifts / exponent arithmetic: in
+// situ (tensor pipe busy) a DMUL/DADD/DSETP costs ~60 issue cycles per warp, so the epilogues are
+// written around "as few FP64-pipe instructions per element as possible" (MID 1, FINAL 3).
+constexpr int kNoBound = -(1 << 30);
+template <int NS>
+__device__ __forceinline__ int pow2_exponent(double b) {
+  if (!(b > 0.0)) return kNoBound;                        // all-zero row
+  const long long bits = __double_as_longlong(b);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  if (bits & 0xfffffffffffffll) ++e;
+  const int lo = 8 * NS - 46;                             // keeps counts << (8 NS - f) inside 62 bits
+  return e < lo ? lo : (e > 1000 ? 1000 : e);
+}
+__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+
+// MID: q = rn(D * alpha * 2^-f), saturated to 256^NS - 1.  One FP64-pipe multiply; the power of
+// two is applied to the exponent field of the converted integer.
+template <int NS>
+__device__ __forceinline__ uint32_t mid_quant(unsigned long long D, double alpha, int f) {
+  long long bits = __double_as_longlong((double)(long long)D);
+  bits -= (long long)f << 52;
+  const double d = D ? __longlong_as_double(bits) : 0.0;
+  uint32_t q = __double2uint_rn(d * alpha);               // saturating; NaN -> 0
+  if (NS < 4) q = min(q, (uint32_t)((1ull << (8 * NS)) - 1ull));
+  return q;
+}
+
+// FINAL: x = coef * g_a[j] * g_v[r] * (D * 2^(f_r - 8 NS) + count).  With sh = s | dl << 8, where
+// s = max(8 NS - f_r, 0) and dl = max(f_r - 8 NS, 0), and cf = coef * g_v[r] * 2^-s this is
+// ((D << dl) + (count << s)) * cf * g_a[j]: integer combine, one conversion, two multiplies.
+__device__ __forceinline__ double final_value(unsigned long long D, uint32_t cnt, int sh, double cf, double gj) {
+  const unsigned long long T = (D << (sh >> 8)) + ((unsigned long long)cnt << (sh & 0xff));
+  return ((double)(long long)T * cf) * gj;
+}
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
 struct Params {
   int layout;
@@ -203,6 +241,7 @@ struct Params {
   const double* g_a; const double* g_v;
   const uint16_t* counts; int64_t ld_counts; int add_counts, use_evidence;
   double* out_f64; int64_t ld_out; int64_t diag_offset;
+  double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;
   EpilogueDev epi;
   double* maxdiff; double* maxoff;
   // COUNTS
@@ -350,35 +389,62 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     TileWalk<RT> tw;
     tw.init(p);
     tw.advance(cluster_id);
-    double dmax = 0.0, omax = 0.0;
+    unsigned long long dmax = 0ull, omax = 0ull;         // bit patterns of non-negative doubles
     const bool sym = p.layout == SRK_X2_SYMMETRIC;
     const bool trans = p.layout == SRK_X2_TRANSPOSED;
+    const bool have_old = p.epi.s_old != nullptr;
+    // everything the vectorised paths assume about the caller's buffers (uniform over the grid)
+    bool fast_ok = false;
+    if (MODE == SRK_X2_FINAL) {
+      fast_ok = have_old && !p.epi.prior && !p.epi.evidence &&
+                ((reinterpret_cast<uintptr_t>(p.out_f64) | reinterpret_cast<uintptr_t>(p.epi.s_old)) & 15) == 0 &&
+                ((p.ld_out | p.epi.ld_s_old) & 1) == 0;
+      if (p.counts) fast_ok = fast_ok && (reinterpret_cast<uintptr_t>(p.counts) & 15) == 0 && (p.ld_counts & 7) == 0;
+      if (p.mirror_out)
+        fast_ok = fast_ok && (reinterpret_cast<uintptr_t>(p.mirror_out) & 15) == 0 && ((p.ld_mirror | p.mirror_col0) & 1) == 0;
+    }
     for (int t = 0; t < my_tiles; ++t) {
       const int b = t & 1;
-      const int64_t j = (int64_t)tw.jb * 256 + (int64_t)cta * BMC + et;     // row of A8 owned by this thread
+      const int64_t jc0 = (int64_t)tw.jb * 256 + (int64_t)cta * BMC;        // first A8 row of this CTA's half
+      const int64_t j = jc0 + et;                                           // row of A8 owned by this thread
       const int64_t r0 = (int64_t)tw.rb * RT;
       const bool jvalid = j < p.M;
       // per-column factors of this tile (double-buffered; one named barrier per tile)
-      double* cf1 = colfac + (size_t)b * 2 * RT;
-      double* cf2 = cf1 + RT;
+      double* cf = colfac + (size_t)b * RT;                                 // [2][RT] doubles
+      int* shv = reinterpret_cast<int*>(colfac + 2 * RT) + (size_t)b * RT;  // [2][RT] ints
       if (MODE != SRK_X2_COUNTS) {
         for (int c = et; c < RT; c += 128) {
           const int64_t r = r0 + c;
-          double f1 = 0.0, f2 = 0.0;
+          double f = 0.0;
+          int sh = 0;
           if (r < p.R) {
-            f1 = row_bound(p.in_rowbound, r) / kQ;
-            if (MODE == SRK_X2_FINAL) { f2 = p.epi.coef * p.g_v[r]; f1 *= f2; }
+            const double bin = row_bound(p.in_rowbound, r);
+            if (MODE == SRK_X2_MID) {
+              f = bin > 0.0 ? bin : 0.0;
+            } else {
+              const int fr = pow2_exponent<NS>(bin);
+              int s = fr == kNoBound ? 0 : 8 * NS - fr, dl = 0;
+              if (s < 0) { dl = -s > 17 ? 17 : -s; s = 0; }
+              sh = s | (dl << 8);
+              f = p.epi.coef * p.g_v[r] * pow2(-s);
+            }
           }
-          cf1[c] = f1;
-          cf2[c] = f2;
+          cf[c] = f;
+          shv[c] = sh;
         }
         epi_bar_sync();
       }
-      double rowf = 0.0;                                  // MID: Q / bound_out(j); FINAL: g_a[j]
+      double rowf = 0.0;                                  // FINAL: g_a[j]
+      int fj = kNoBound;                                  // MID: exponent of the power-of-two bound of row j
       if (jvalid) {
-        if (MODE == SRK_X2_MID) { const double bo = row_bound(p.out_rowbound, j); rowf = bo > 0.0 ? kQ / bo : 0.0; }
+        if (MODE == SRK_X2_MID) fj = pow2_exponent<NS>(row_bound(p.out_rowbound, j));
         if (MODE == SRK_X2_FINAL) rowf = p.g_a[j];
       }
+      // tile-uniform facts that select the vectorised paths
+      const bool full = jc0 + BMC <= p.M && r0 + RT <= p.R;
+      const int64_t dlo = r0 + p.diag_offset, dhi = dlo + RT - 1;           // A8 rows that meet the diagonal
+      const bool nodiag = sym ? (jc0 + BMC - 1 < r0) : (jc0 + BMC - 1 < dlo || jc0 > dhi);
+      const bool fast = fast_ok && full && nodiag;
       mbar_wait(&tmem_full[b], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t acc = lane_base + (uint32_t)(b * kAccStride);
@@ -418,21 +484,18 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
 
         if (MODE == SRK_X2_MID) {
-          if (rc + 16 > p.ld_outp) continue;
           uint32_t w[NS][4];
 #pragma unroll
           for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int x = 0; x < 4; ++x) w[s][x] = 0u;
+          if (fj != kNoBound) {
 #pragma unroll
-          for (int x = 0; x < 16; ++x) {
-            double q = rint(combine<NS>(a, x) * cf1[c0 + x] * rowf);
-            if (!(q > 0.0)) q = 0.0;
-            if (q > kQ - 1.0) q = kQ - 1.0;
-            const unsigned long long qi = (unsigned long long)q;
+            for (int x = 0; x < 16; ++x) {
+              const uint32_t q = mid_quant<NS>(combine<NS>(a, x), cf[c0 + x], fj);
 #pragma unroll
-            for (int s = 0; s < NS; ++s)
-              w[s][x >> 2] |= (uint32_t)((qi >> (8 * (NS - 1 - s))) & 0xffull) << (8 * (x & 3));
+              for (int s = 0; s < NS; ++s) w[s][x >> 2] |= ((q >> (8 * (NS - 1 - s))) & 0xffu) << (8 * (x & 3));
+            }
           }
 #pragma unroll
           for (int s = 0; s < NS; ++s)
@@ -443,125 +506,111 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
         // ---------------------------------------------------------------- FINAL
         const int64_t jd = j - p.diag_offset;             // V row that sits on the diagonal with j
-        if (sym && jd > rc + 15) continue;                // strictly below the diagonal: mirrored from above
         double v[16];
-        if (!trans) {
-          // element (row j, column rc + x): contiguous for this thread
-          const int64_t base = j * p.ld_out + rc;
-          const bool full = rc + 16 <= p.R;
+        if (fast && !trans) {
+          // every element of the tile is off-diagonal, in range and (symmetric layout) above the
+          // diagonal: 128-bit loads/stores along the row, no predicates
           uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           if (p.counts) {
-            const uint16_t* cp = p.counts + j * p.ld_counts + rc;
-            if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-              const uint4 t0 = reinterpret_cast<const uint4*>(cp)[0], t1 = reinterpret_cast<const uint4*>(cp)[1];
-              cw[0] = t0.x; cw[1] = t0.y; cw[2] = t0.z; cw[3] = t0.w;
-              cw[4] = t1.x; cw[5] = t1.y; cw[6] = t1.z; cw[7] = t1.w;
-            } else {
-#pragma unroll
-              for (int x = 0; x < 16; ++x)
-                if (rc + x < p.R) cw[x >> 1] |= (uint32_t)cp[x] << (16 * (x & 1));
-            }
-          }
-          uint32_t ev[4] = {0u, 0u, 0u, 0u};
-          if (p.epi.evidence) {
-            const uint8_t* e = p.epi.evidence + j * p.epi.ld_evidence + rc;
-            if (full && ((reinterpret_cast<uintptr_t>(e) & 15) == 0)) {
-              const uint4 t0 = *reinterpret_cast<const uint4*>(e);
-              ev[0] = t0.x; ev[1] = t0.y; ev[2] = t0.z; ev[3] = t0.w;
-            } else {
-#pragma unroll
-              for (int x = 0; x < 16; ++x)
-                if (rc + x < p.R) ev[x >> 2] |= (uint32_t)e[x] << (8 * (x & 3));
-            }
+            const uint4* cp = reinterpret_cast<const uint4*>(p.counts + j * p.ld_counts + rc);
+            const uint4 t0 = cp[0], t1 = cp[1];
+            cw[0] = t0.x; cw[1] = t0.y; cw[2] = t0.z; cw[3] = t0.w;
+            cw[4] = t1.x; cw[5] = t1.y; cw[6] = t1.z; cw[7] = t1.w;
           }
           double so[16];
-          const bool have_old = p.epi.s_old != nullptr;
-          if (have_old) {
-            const double* sp = p.epi.s_old + j * p.epi.ld_s_old + rc;
-            if (full && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+          const double2* sp = reinterpret_cast<const double2*>(p.epi.s_old + j * p.epi.ld_s_old + rc);
 #pragma unroll
-              for (int x = 0; x < 16; x += 2) {
-                const double2 d2 = *reinterpret_cast<const double2*>(sp + x);
-                so[x] = d2.x; so[x + 1] = d2.y;
-              }
-            } else {
-#pragma unroll
-              for (int x = 0; x < 16; ++x) so[x] = (rc + x < p.R) ? sp[x] : 0.0;
-            }
-          }
+          for (int x = 0; x < 8; ++x) { const double2 d2 = sp[x]; so[2 * x] = d2.x; so[2 * x + 1] = d2.y; }
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
-            const int64_t r = rc + x;
             const uint32_t cnt = (cw[x >> 1] >> (16 * (x & 1))) & 0xffffu;
-            double val = combine<NS>(a, x) * cf1[c0 + x];
-            if (p.add_counts) val += (double)cnt * cf2[c0 + x];
-            val *= rowf;
+            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
             if (p.use_evidence) val *= evidence_factor(cnt);
-            else if (p.epi.evidence) val *= evidence_factor((ev[x >> 2] >> (8 * (x & 3))) & 0xffu);
-            if (p.epi.prior && r < p.R) val = (1.0 - p.epi.lambda) * val + p.epi.lambda * p.epi.prior[j * p.epi.ld_prior + r];
-            const bool live = r < p.R && !(sym && jd > r);
-            if (r == jd) val = 1.0; else if (live && val > omax) omax = val;
-            if (have_old && live) {
-              const double d = fabs(val - so[x]);
-              if (d > dmax) dmax = d;
-            }
+            omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
+            dmax = umax64(dmax, (unsigned long long)__double_as_longlong(val - so[x]) & 0x7fffffffffffffffull);
             v[x] = val;
           }
-          double* orow = p.out_f64 + base;
-          if (full && !(sym && jd > rc) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+          double2* op = reinterpret_cast<double2*>(p.out_f64 + j * p.ld_out + rc);
 #pragma unroll
-            for (int x = 0; x < 16; x += 2) *reinterpret_cast<double2*>(orow + x) = make_double2(v[x], v[x + 1]);
-          } else {
-#pragma unroll
-            for (int x = 0; x < 16; ++x)
-              if (rc + x < p.R && !(sym && jd > rc + x)) orow[x] = v[x];
-          }
+          for (int x = 0; x < 8; ++x) op[x] = make_double2(v[2 * x], v[2 * x + 1]);
           if (sym) {
-            // mirror: element (row r, column j); 32 lanes write 256 contiguous bytes per x
+            double* mp = p.out_f64 + rc * p.ld_out + j;   // mirror: 32 lanes write 256 contiguous bytes per x
 #pragma unroll
-            for (int x = 0; x < 16; ++x) {
-              const int64_t r = rc + x;
-              if (r < p.R && jd < r) p.out_f64[r * p.ld_out + j] = v[x];
-            }
+            for (int x = 0; x < 16; ++x) mp[x * p.ld_out] = v[x];
           }
-        } else {
-          // transposed: element (row rc + x, column j); every access is coalesced across lanes
+          continue;
+        }
+        if (fast && trans) {
+          // element (row rc + x, column j): every access is coalesced across the lanes
           uint32_t cnt[16];
           double so[16];
-          const bool have_old = p.epi.s_old != nullptr;
+          const double* sp = p.epi.s_old + rc * p.epi.ld_s_old + j;
 #pragma unroll
-          for (int x = 0; x < 16; ++x) {
-            const int64_t r = rc + x;
-            cnt[x] = (p.counts && r < p.R) ? (uint32_t)p.counts[r * p.ld_counts + j] : 0u;
-            so[x] = (have_old && r < p.R) ? p.epi.s_old[r * p.epi.ld_s_old + j] : 0.0;
+          for (int x = 0; x < 16; ++x) so[x] = sp[x * p.epi.ld_s_old];
+          if (p.counts) {
+            const uint16_t* cp = p.counts + rc * p.ld_counts + j;
+#pragma unroll
+            for (int x = 0; x < 16; ++x) cnt[x] = cp[x * p.ld_counts];
+          } else {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) cnt[x] = 0u;
           }
+          double* op = p.out_f64 + rc * p.ld_out + j;
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
-            const int64_t r = rc + x;
-            double val = combine<NS>(a, x) * cf1[c0 + x];
-            if (p.add_counts) val += (double)cnt[x] * cf2[c0 + x];
-            val *= rowf;
+            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt[x] : 0u, shv[c0 + x], cf[c0 + x], rowf);
             if (p.use_evidence) val *= evidence_factor(cnt[x]);
-            else if (p.epi.evidence && r < p.R) val *= evidence_factor(p.epi.evidence[r * p.epi.ld_evidence + j]);
-            if (p.epi.prior && r < p.R) val = (1.0 - p.epi.lambda) * val + p.epi.lambda * p.epi.prior[r * p.epi.ld_prior + j];
-            const bool live = r < p.R;
-            if (r == jd) val = 1.0; else if (live && val > omax) omax = val;
-            if (have_old && live) {
-              const double d = fabs(val - so[x]);
-              if (d > dmax) dmax = d;
-            }
-            if (live) p.out_f64[r * p.ld_out + j] = val;
+            omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
+            dmax = umax64(dmax, (unsigned long long)__double_as_longlong(val - so[x]) & 0x7fffffffffffffffull);
+            op[x * p.ld_out] = val;
+            v[x] = val;
           }
+          if (p.mirror_out) {                             // (row j, columns rc..) of the owner of row j
+            double2* mp = reinterpret_cast<double2*>(p.mirror_out + j * p.ld_mirror + p.mirror_col0 + rc);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) mp[x] = make_double2(v[2 * x], v[2 * x + 1]);
+          }
+          continue;
+        }
+
+        // ---- general path: tiles that touch the diagonal or an edge, priors, uint8 evidence
+        if (sym && jd > rc + 15) continue;                // strictly below the diagonal: mirrored from above
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const int64_t r = rc + x;
+          const bool live = r < p.R && !(sym && jd > r);
+          if (!live) continue;
+          const int64_t idx_o = trans ? r * p.ld_out + j : j * p.ld_out + r;
+          uint32_t cnt = 0u;
+          if (p.counts) cnt = trans ? p.counts[r * p.ld_counts + j] : p.counts[j * p.ld_counts + r];
+          double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
+          if (p.use_evidence) val *= evidence_factor(cnt);
+          else if (p.epi.evidence)
+            val *= evidence_factor(trans ? p.epi.evidence[r * p.epi.ld_evidence + j] : p.epi.evidence[j * p.epi.ld_evidence + r]);
+          if (p.epi.prior)
+            val = (1.0 - p.epi.lambda) * val +
+                  p.epi.lambda * (trans ? p.epi.prior[r * p.epi.ld_prior + j] : p.epi.prior[j * p.epi.ld_prior + r]);
+          if (r == jd) val = 1.0;
+          else if (val > 0.0) omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
+          if (have_old) {
+            const double so = trans ? p.epi.s_old[r * p.epi.ld_s_old + j] : p.epi.s_old[j * p.epi.ld_s_old + r];
+            const double d = fabs(val - so);
+            if (d > 0.0) dmax = umax64(dmax, (unsigned long long)__double_as_longlong(d));   // NaN compares false
+          }
+          p.out_f64[idx_o] = val;
+          if (sym && jd < r) p.out_f64[r * p.ld_out + j] = val;
+          if (trans && p.mirror_out && r != jd) p.mirror_out[j * p.ld_mirror + p.mirror_col0 + r] = val;
         }
       }
       tw.advance(num_clusters);
     }
     if (MODE == SRK_X2_FINAL) {
-      dmax = warp_max(dmax);
-      omax = warp_max(omax);
+      double dm = __longlong_as_double((long long)dmax), om = __longlong_as_double((long long)omax);
+      dm = warp_max(dm);
+      om = warp_max(om);
       if (lane == 0) {
-        if (p.maxdiff && dmax > 0.0) atomic_max_nonneg(p.maxdiff, dmax);
-        if (p.maxoff && omax > 0.0) atomic_max_nonneg(p.maxoff, omax);
+        if (p.maxdiff && dm > 0.0) atomic_max_nonneg(p.maxdiff, dm);
+        if (p.maxoff && om > 0.0) atomic_max_nonneg(p.maxoff, om);
       }
     }
   }
@@ -647,6 +696,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.g_a = a.g_a; p.g_v = a.g_v;
   p.counts = a.counts; p.ld_counts = a.ld_counts; p.add_counts = a.add_counts; p.use_evidence = a.use_evidence;
   p.out_f64 = a.out_f64; p.ld_out = a.ld_out; p.diag_offset = a.diag_offset;
+  p.mirror_out = a.mirror_out; p.ld_mirror = a.ld_mirror; p.mirror_col0 = a.mirror_col0;
   p.epi = to_dev(a.epi);
   p.maxdiff = a.epi.maxdiff; p.maxoff = a.epi.maxoff;
   p.out_counts = a.out_counts; p.ld_out_counts = a.ld_out_counts;
@@ -733,6 +783,8 @@ extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
     } else {
       SRK_REQUIRE(a->ld_out >= a->R, "ld_out smaller than R");
     }
+    SRK_REQUIRE(!a->mirror_out || (a->layout == SRK_X2_TRANSPOSED && a->ld_mirror >= a->mirror_col0 + a->R),
+                "mirror_out needs the transposed layout and ld_mirror >= mirror_col0 + R");
     if (a->layout == SRK_X2_SYMMETRIC)
       SRK_REQUIRE(a->M == a->R && a->diag_offset == 0 && a->epi.prior == nullptr,
                   "symmetric layout needs a square product without a prior");

@@ -167,10 +167,11 @@ def choose_slices(requested, coef: float, blend: float, rho_max: float, s_off_ma
     """Planes per matrix for one update of the tensor-core path.
 
     Rounding happens twice per update, when S_off and U = A S_off are cut into NS uint8 planes with
-    bounds b_S(r) = max_k S_off[r,k] and b_U(j) = deg_j * max(S_off); each is at most half a step of
-    bound / 256^NS.  Propagated through ``coef * g g^T o (A . A^T)`` the two add up to at most
-    ``delta = blend * coef * rho_max^2 * max(S_off) / 256^NS`` per update (rho = row sums of G,
-    1 for unweighted graphs), and the update contracts earlier errors by kappa = blend * coef *
+    bounds b_S(r) = max_k S_off[r,k] (exact) and b_U(j) = deg_j * max(S_off) rounded up to a power
+    of two (< 2 b_U): at most half a step of bound / 256^NS each, i.e. 0.5 and < 1 steps of the
+    tight bounds.  Propagated through ``coef * g g^T o (A . A^T)`` the two add up to at most
+    ``delta = 1.5 * blend * coef * rho_max^2 * max(S_off) / 256^NS`` per update (rho = row sums of
+    G, 1 for unweighted graphs), and the update contracts earlier errors by kappa = blend * coef *
     rho_max^2, so the deviation from the float64 iteration never exceeds delta / (1 - kappa).  The
     smallest NS in {2, 3, 4} that keeps this below ERR_BUDGET is used; an integer request is
     honoured as is."""
@@ -182,7 +183,7 @@ def choose_slices(requested, coef: float, blend: float, rho_max: float, s_off_ma
     kappa = blend * coef * rho_max * rho_max
     amplification = 1.0 / (1.0 - kappa) if kappa < 0.999 else 1000.0
     for ns in (2, 3, 4):
-        if kappa * s_off_max / 256.0 ** ns * amplification <= ERR_BUDGET:
+        if 1.5 * kappa * s_off_max / 256.0 ** ns * amplification <= ERR_BUDGET:
             return ns
     return 4
 

@@ -45,6 +45,14 @@ def _join(planes, ns):
     return sum(p[s] << (8 * (ns - 1 - s)) for s in range(ns))
 
 
+def _pow2_exponent(b, ns):
+    """f with 2^f the smallest power of two >= b, clamped to f >= 8 ns - 46 (the kernel's rounding
+    of the row bounds of U)."""
+    m, e = np.frexp(np.asarray(b, dtype=np.float64))          # b = m * 2^e, m in [0.5, 1)
+    f = np.where(m == 0.5, e - 1, e)
+    return np.maximum(f, 8 * ns - 46).astype(np.int64)
+
+
 def _run(a):
     _lib.check(_lib.load().srk_x2_half(C.byref(a), engine._stream()), "srk_x2_half")
     torch.cuda.synchronize()
@@ -99,15 +107,15 @@ def test_x2_mid_against_integer_matmul(dev, ns, M, R, K):
     D = (A.astype(np.int64) @ q.T).astype(np.float64)                  # [M, R] exact
     inb = in_vec.cpu().numpy() * 0.9
     outb = out_vec.cpu().numpy() * 30.0 + 1.0
-    want = np.clip(np.rint((D * (inb / qmax)[None, :]) * (qmax / outb)[:, None]), 0, qmax - 1).astype(np.int64)
+    fj = _pow2_exponent(outb, ns)
+    want = np.clip(np.rint((D * (2.0 ** -fj)[:, None]) * inb[None, :]), 0, qmax - 1).astype(np.int64)
     got = _join(out.cpu().numpy(), ns)
-    assert np.abs(got[:, :R] - want).max() <= 1, np.abs(got[:, :R] - want).max()
-    assert (got[:, :R] != want).mean() < 1e-3
+    np.testing.assert_array_equal(got[:, :R], want)
     pad = got[:, R: engine._round_up(R, 16)]
     assert not pad.any()                                                # chunk padding is written as zeros
 
 
-def _final_case(rng, ns, M, R, K, layout, extras, dev):
+def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False):
     qmax = 256 ** ns
     q = rng.integers(0, qmax, (R, K), dtype=np.int64)
     A = (rng.random((M, K)) < 0.2).astype(np.uint8)
@@ -136,7 +144,7 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev):
     a.mode, a.ns, a.layout, a.M, a.R, a.K = _lib.SRK_X2_FINAL, ns, layout, M, R, K
     a.A8, a.lda = a8.data_ptr(), ldk
     a.in_planes, a.ld_in, a.in_plane_stride = planes.data_ptr(), ldk, R * ldk
-    a.in_rowbound = _lib.RowBound.of(in_vec.data_ptr(), 2.0, 1.0)
+    a.in_rowbound = _lib.RowBound.of(in_vec.data_ptr(), 2.0 * bscale, 1.0 * bscale)
     gad, gvd = torch.from_numpy(ga).to(dev), torch.from_numpy(gv).to(dev)
     a.g_a, a.g_v = gad.data_ptr(), gvd.data_ptr()
     a.out_f64, a.ld_out, a.diag_offset = S.data_ptr(), ld, diag_offset
@@ -161,17 +169,23 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev):
         pr = torch.from_numpy(prior).to(dev)
         keep.append(pr)
         e.prior, e.ld_prior, e.lambda_ = pr.data_ptr(), cols, 0.25
+    mir = None
+    if mirror:                                                          # the block as its owner stores it
+        ldm = engine._round_up(R + 6, 2)
+        mir = torch.full((M, ldm), -3.0, dtype=torch.float64, device=dev)
+        a.mirror_out, a.ld_mirror, a.mirror_col0 = mir.data_ptr(), ldm, 6
     _run(a)
     # ---- numpy restatement, in the (j, r) frame of the kernel
-    D = (A.astype(np.int64) @ q.T).astype(np.float64)                   # [M, R]
-    inb = in_vec.cpu().numpy() * 2.0 + 1.0
-    cf2 = 0.8 * gv
-    cf1 = (inb / qmax) * cf2
+    D = A.astype(np.int64) @ q.T                                        # [M, R] exact
+    inb = (in_vec.cpu().numpy() * 2.0 + 1.0) * bscale
+    s = 8 * ns - _pow2_exponent(inb, ns)                                # bounds of U are powers of two
+    dl = np.maximum(-s, 0)
+    s = np.maximum(s, 0)
     cnt_jr = (cnt.T if trans else cnt).astype(np.float64)
-    val = D * cf1[None, :]
+    T = D << dl[None, :]
     if use_counts:
-        val = val + cnt_jr * cf2[None, :]
-    val = val * ga[:, None]
+        T = T + ((cnt.T if trans else cnt).astype(np.int64) << s[None, :])
+    val = (T.astype(np.float64) * ((0.8 * gv) * 2.0 ** -s)[None, :]) * ga[:, None]
     if a.use_evidence:
         val = val * (1 - 0.5 ** np.minimum(cnt_jr, 60.0))
     if ev8 is not None:
@@ -185,6 +199,12 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev):
         want = np.triu(want) + np.triu(want, 1).T
     got = S[:, :cols].cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+    if mir is not None:
+        mh = mir.cpu().numpy()
+        exp_m = got.T.copy()
+        exp_m[np.arange(M)[:, None] == np.arange(R)[None, :] + diag_offset] = -3.0   # the diagonal has no mirror image
+        np.testing.assert_array_equal(mh[:, 6:6 + R], exp_m)             # same values, mirrored placement
+        assert np.all(mh[:, :6] == -3.0) and np.all(mh[:, 6 + R:] == -3.0)
     if layout == _lib.SRK_X2_SYMMETRIC:
         assert np.array_equal(got, got.T)
     md, mo = scal.tolist()
@@ -221,6 +241,24 @@ def test_x2_final_transposed(dev, ns, M, R, K, extras):
 
 
 @needs_i8
+@pytest.mark.parametrize("ns,bscale", [(2, 3e5), (2, 1e-20), (3, 1e-9), (4, 7.0)])
+def test_x2_final_bound_ranges(dev, ns, bscale):
+    """Bounds of U above 256^NS (left shift of D) and below the clamp (counts << 46)."""
+    _final_case(np.random.default_rng(5), ns, 300, 300, 260, _lib.SRK_X2_SYMMETRIC, "counts", dev, bscale=bscale)
+    _final_case(np.random.default_rng(6), ns, 300, 200, 260, _lib.SRK_X2_DIRECT, "evidence", dev, bscale=bscale)
+
+
+@needs_i8
+def test_x2_final_transposed_with_mirror(dev):
+    """Row-sharded symmetric update: the local block is stored transposed and its mirror image goes
+    to the buffer of the rank that owns row j (here an ordinary device buffer)."""
+    for ns, M, R, K in ((2, 512, 256, 384), (3, 700, 300, 200), (2, 130, 70, 129)):
+        rng = np.random.default_rng(M)
+        # diag_offset of the helper is 3: keep the diagonal out of the picture with M, R as given
+        _final_case(rng, ns, M, R, K, _lib.SRK_X2_TRANSPOSED, "counts", dev, mirror=True)
+
+
+@needs_i8
 def test_x2_kblocked_operand(dev):
     """V given as K-blocks (the receive buffer of the row-sharded exchange)."""
     rng = np.random.default_rng(8)
@@ -247,9 +285,10 @@ def test_x2_kblocked_operand(dev):
     a.out_rowbound = _lib.RowBound.of(None, 0.0, float(K))
     _run(a)
     D = (A.astype(np.int64) @ q.T).astype(np.float64)
-    want = np.clip(np.rint((D * (1.0 / qmax)) * (qmax / float(K))), 0, qmax - 1).astype(np.int64)
+    fj = int(_pow2_exponent(float(K), ns))
+    want = np.clip(np.rint(D * 2.0 ** -fj), 0, qmax - 1).astype(np.int64)
     got = _join(out.cpu().numpy(), ns)[:, :R]
-    assert np.abs(got - want).max() <= 1
+    np.testing.assert_array_equal(got, want)
 
 
 @needs_i8
