@@ -440,11 +440,6 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (MODE == SRK_X2_MID) fj = pow2_exponent<NS>(row_bound(p.out_rowbound, j));
         if (MODE == SRK_X2_FINAL) rowf = p.g_a[j];
       }
-      // tile-uniform facts that select the vectorised paths
-      const bool full = jc0 + BMC <= p.M && r0 + RT <= p.R;
-      const int64_t dlo = r0 + p.diag_offset, dhi = dlo + RT - 1;           // A8 rows that meet the diagonal
-      const bool nodiag = sym ? (jc0 + BMC - 1 < r0) : (jc0 + BMC - 1 < dlo || jc0 > dhi);
-      const bool fast = fast_ok && full && nodiag;
       mbar_wait(&tmem_full[b], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t acc = lane_base + (uint32_t)(b * kAccStride);
@@ -506,10 +501,14 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
         // ---------------------------------------------------------------- FINAL
         const int64_t jd = j - p.diag_offset;             // V row that sits on the diagonal with j
+        // Chunks whose 16 elements are all in range, off the diagonal and (symmetric layout) above it
+        // take the vectorised paths; a warp diverges only where its rows meet the diagonal or an
+        // edge, so every tile costs about the same and the CTA pairs stay in step (which is what
+        // keeps their operand panels shared in L2).
+        const bool fast = fast_ok && rc + 16 <= p.R && (jd < rc || (!sym && jd > rc + 15));
         double v[16];
         if (fast && !trans) {
-          // every element of the tile is off-diagonal, in range and (symmetric layout) above the
-          // diagonal: 128-bit loads/stores along the row, no predicates
+          // 128-bit loads/stores along the row, no predicates
           uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           if (p.counts) {
             const uint4* cp = reinterpret_cast<const uint4*>(p.counts + j * p.ld_counts + rc);

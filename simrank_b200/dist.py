@@ -1,45 +1,55 @@
 """Row-sharded multi-GPU SimRank iteration (one process per GPU, torch.distributed / NCCL).
 
-Partition.  Every similarity matrix is split in row blocks, rank r owning rows
-``plan.start(r) .. plan.stop(r)``; the 0/1 adjacency pattern (dense uint8, 1 GB at n = 32768) is
-replicated.  One update ``S_out <- epilogue(coef * G S_in G^T)`` is then
+Partition.  Every similarity matrix is split in row blocks, rank q owning rows
+``plan.start(q) .. plan.stop(q)`` (blocks are multiples of 16 rows); the 0/1 adjacency pattern
+(dense uint8, 1 GB at n = 32768) is replicated.  One update ``S_out <- epilogue(coef * G S_in G^T)``
+of the tensor-core path (engine.py, ``S = I + S_off``) is, on rank q:
 
-  1. MID   (local)   D[r, j] = sum_m S_in[r, m] A[j, m] for the LOCAL rows r of S_in and ALL j.
-                     Because S_in is symmetric this is the column panel U[:, rows_r] of
-                     U = A S_in; the kernel stores it transposed, one launch per destination
-                     rank q, straight into the send block for q (rows_q of the panel).
-  2. exchange        all-to-all of the uint8 planes: rank q receives U[rows_q, rows_r] from every
-                     r, i.e. its ROW panel U[rows_q, :], K-blocked by source rank.
-  3. FINAL (local)   S_out[rows_q, :] = epilogue(g g^T o (U[rows_q, :] A^T)) reading the receive
-                     buffer in place through a 4-D tensor map (K-blocked operand).
-  4. a 2-double MAX all-reduce gives every rank the same max|dS| (the reference's convergence
-     test, SimRank.py:74) and the range of the new S.
+  1. slice   planes of the LOCAL rows of S_in with their exact row maxima (srk_slice_rows_max_f64).
+  2. MID     for every destination rank p:  U[j, r] = sum_k A[j, k] S_off[r, k] for j in rows_p and
+             the local rows r.  Because S_in is symmetric this is the column block (rows_p x rows_q)
+             of U = A S_off, and the kernel stores it straight into rank p's ROW panel U[rows_p, :]
+             at column offset start(q) -- through a peer-mapped pointer over NVLink (symmetric
+             memory): the exchange is fused into the epilogue of the GEMM, there is no all-to-all.
+  3. barrier every rank's row panel of U is complete.
+  4. FINAL   S_out[rows_q, :] from the own row panel of U.  S_out is symmetric, so each unordered
+             pair of row blocks {q, p} is computed ONCE: rank q computes its diagonal block with the
+             symmetric layout and the blocks (q, p) for p up to half-way round the ring with the
+             transposed layout, whose epilogue also writes the mirror image into rank p's S_out
+             (peer pointer again).  With an even world the blocks half-way round are split in two.
+             Every rank so executes 1/P of the n^3 flop of the single-GPU symmetric FINAL.
+  5. a 2-double MAX all-reduce gives every rank the same max|dS| (the reference's convergence
+     test, SimRank.py:74) and the range of the new S; it is also the barrier that orders the
+     mirror stores before the next update.
 
-The exchange moves NS bytes per element of U (3 with the default planes) instead of 8 for
-float64.  The kernel launches are the same C-ABI calls as the single-GPU engine; the class is
-written so that the two launch methods and the tensor device can be substituted, which is how
-the world_size-2 gloo tests on CPU check every offset of the sharding (tests/test_dist_gloo.py).
+``StagedExchange`` is the same algorithm without peer pointers: the kernels store into local
+staging blocks that torch.distributed moves (all-to-all) -- the fallback when symmetric memory is
+not available and the way the host logic runs under gloo on CPU (tests/test_dist_gloo.py, with the
+numpy emulator of the C ABI).
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import _ptr, _round_up, _stream
+from .engine import _ptr, _round_up, _stream, choose_slices
 from .graph import HostOperator
+
+_NO_DIAGONAL = -(1 << 40)
 
 
 class ShardPlan:
-    """Row blocks of an n-row matrix over ``world`` ranks, padded to 128-row blocks for exchange."""
+    """Row blocks of an n-row matrix over ``world`` ranks; every block starts at a multiple of 16
+    (the kernels store 16-element chunks at the block's column offset)."""
 
     def __init__(self, n: int, world: int):
         self.n, self.world = n, world
-        self.per = -(-n // world) if n else 0
-        self.blk = _round_up(max(self.per, 1), 128)
+        self.per = _round_up(-(-n // world), 16) if n else 0
 
     def start(self, r):
         return min(self.n, r * self.per)
@@ -50,54 +60,135 @@ class ShardPlan:
     def count(self, r):
         return self.stop(r) - self.start(r)
 
-    @property
-    def padded(self):
-        return self.world * self.blk
 
-    def pad_index(self, k: np.ndarray) -> np.ndarray:
-        """Position of node k in the block-padded layout (block = owning rank)."""
-        if self.per == 0:
-            return k
-        return (k // self.per) * self.blk + k % self.per
+def pair_tasks(plan: ShardPlan, q: int, symmetric: bool):
+    """Blocks of the symmetric result that rank ``q`` computes in FINAL, as tuples
+    (p, j_lo, j_hi, r_lo, r_hi, mirror): A8 rows j_lo..j_hi of rank p's block against the local
+    rows r_lo..r_hi; ``mirror`` says whether the transposed block also goes to rank p.  The own
+    block (p == q) is computed with the symmetric layout.  Without symmetry (a prior) every rank
+    computes all its rows."""
+    P = plan.world
+    rows_q = plan.count(q)
+    tasks = []
+    if rows_q == 0:
+        return tasks
+    if not symmetric:
+        return [(p, 0, plan.count(p), 0, rows_q, False) for p in range(P) if plan.count(p)]
+    tasks.append((q, 0, rows_q, 0, rows_q, False))
+    for d in range(1, P):
+        p = (q + d) % P
+        rows_p = plan.count(p)
+        if rows_p == 0:
+            continue
+        if 2 * d < P:
+            tasks.append((p, 0, rows_p, 0, rows_q, True))
+        elif 2 * d == P:
+            # the pair meets half-way round the ring in both directions: split the block by the
+            # rows of the HIGHER rank
+            hi, lo = max(q, p), min(q, p)
+            h = min(_round_up(plan.count(hi) // 2, 16), plan.count(hi))
+            if q == lo:
+                if h > 0:
+                    tasks.append((p, 0, h, 0, rows_q, True))
+            elif h < rows_q:
+                tasks.append((p, 0, rows_p, h, rows_q, True))
+    return tasks
+
+
+# --------------------------------------------------------------------------- exchange strategies
+class StagedExchange:
+    """Kernels store into local staging blocks; torch.distributed collectives move them."""
+
+    peer = False
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def alloc(self, shape, dtype, device):
+        return torch.zeros(shape, dtype=dtype, device=device), None
+
+    def barrier(self):
+        pass
+
+
+class PeerExchange:
+    """Symmetric memory: every rank maps the others' buffers; kernels store into them directly."""
+
+    peer = True
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.group = group if group is not None else dist.group.WORLD
+        self._handles = []
+
+    def alloc(self, shape, dtype, device):
+        t = self.symm.empty(*shape, dtype=dtype, device=device)
+        t.zero_()
+        h = self.symm.rendezvous(t, self.group)
+        self._handles.append(h)
+        return t, [int(x) for x in h.buffer_ptrs]
+
+    def barrier(self):
+        self._handles[0].barrier(channel=0)
+
+
+def make_exchange(device, group=None):
+    want = os.environ.get("SIMRANK_B200_EXCHANGE", "auto").lower()
+    if want == "staged" or torch.device(device).type != "cuda":
+        return StagedExchange(group)
+    try:
+        return PeerExchange(group)
+    except Exception:
+        if want == "peer":
+            raise
+        return StagedExchange(group)
 
 
 class ShardedHalf:
-    """Rank-local state of one similarity matrix in the tensor-core (int8 planes) mode."""
+    """Rank-local state of one similarity matrix in the tensor-core (paired-SM) mode."""
 
-    def __init__(self, op: HostOperator, coef, rank, world, device, ns=3, evidence=None, prior=None, lbd=0.0,
-                 group=None):
+    def __init__(self, op: HostOperator, coef, rank, world, device, ns=None, evidence=None, prior=None, lbd=0.0,
+                 group=None, evidence_from_pattern=False, exchange=None):
         self.op, self.coef, self.rank, self.world, self.device, self.ns = op, float(coef), rank, world, device, ns
         self.group = group
         self.n_out, self.n_in = op.M, op.K
-        self.out_plan, self.in_plan = ShardPlan(self.n_out, world), ShardPlan(self.n_in, world)
-        self.row0, self.rows = self.out_plan.start(rank), self.out_plan.count(rank)
-        self.ld = _round_up(max(self.n_out, 1), 16)
-        self.ldp = _round_up(max(self.n_out, 1), 128)
-        self.lda = max(_round_up(max(self.n_in, 1), 128), self.in_plan.padded)
+        self.plan = ShardPlan(self.n_out, world)
+        self.row0, self.rows, self.per = self.plan.start(rank), self.plan.count(rank), max(self.plan.per, 16)
+        self.ld = _round_up(max(self.n_out, 1), 16)                 # S, counts: columns of the output
+        self.ldp = _round_up(max(self.n_out, 1), 128)               # planes of S_out (used as a source)
+        self.ldu = _round_up(max(self.n_in, 1), 128)                # row panel of U
+        self.lda = _round_up(max(self.n_in, 1), 128)
         self.evidence, self.prior, self.lbd = evidence, prior, float(lbd)     # LOCAL rows
+        self.evidence_from_pattern = bool(evidence_from_pattern)
+        self.symmetric = prior is None
         self.events = None
+        self.slices_used = []
+        self.ns_alloc = 3 if ns in (None, "auto") else int(ns)
+        self.ex = exchange if exchange is not None else make_exchange(device, group)
         dev = device
-        self.S = torch.zeros((max(self.rows, 1), self.ld), dtype=torch.float64, device=dev)
+        # S and the row panel of U are written by other ranks in peer mode
+        self.S, self.S_ptrs = self.ex.alloc((self.per, self.ld), torch.float64, dev)
         self._init_identity()
+        self.U, self.U_ptrs = self.ex.alloc((self.ns_alloc, self.per, self.ldu), torch.uint8, dev)
+        self.planes = None
+        self.bound_vec = torch.zeros(self.per, dtype=torch.float64, device=dev)
         self.scal = torch.zeros(2, dtype=torch.float64, device=dev)
         self.maxoff = 0.0
-        self.planes = torch.zeros((ns, max(self.rows, 1), self.ldp), dtype=torch.uint8, device=dev)
-        bo, bi = self.out_plan.blk, self.in_plan.blk
-        self.sendbuf = torch.zeros((world, ns, bo, bi), dtype=torch.uint8, device=dev)
-        self.recvbuf = torch.zeros((world, ns, bo, bi), dtype=torch.uint8, device=dev)
         g = np.ascontiguousarray(op.g, dtype=np.float64)
-        self.rho = g * op.deg
-        self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
-        self.prior_max = float(prior.max()) if prior is not None else 0.0
+        self.rho_max = float((g * op.deg).max()) if g.size else 0.0
         self.g = torch.from_numpy(g).to(dev)
         self.deg_dev = torch.from_numpy(op.deg.astype(np.float64)).to(dev)
-        self.rho_dev = torch.from_numpy(np.ascontiguousarray(self.rho)).to(dev)
-        self.bound_S, self.bound_S_max = (0.0, 1.0), 1.0
-        # adjacency pattern, natural column layout (MID) and block-padded column layout (FINAL)
-        self.a8_mid = self._dense_pattern(op.indices)
-        padded_cols = self.in_plan.pad_index(op.indices.astype(np.int64)).astype(np.int32)
-        same = bool(np.array_equal(padded_cols, op.indices))
-        self.a8_fin = self.a8_mid if same else self._dense_pattern(padded_cols)
+        self.a8 = self._dense_pattern()
+        self.counts = self._pattern_counts()
+        self.tasks = pair_tasks(self.plan, rank, self.symmetric)
+        if not self.ex.peer:
+            # staging: U blocks per destination rank, mirror blocks per partner rank
+            self.send_U = torch.zeros((world, self.ns_alloc, self.per, 16), dtype=torch.uint8, device=dev)
+            self.mirror_send = torch.zeros((world, self.per, self.per), dtype=torch.float64, device=dev) \
+                if self.symmetric and world > 1 else None
+            self.mirror_recv = torch.zeros_like(self.mirror_send) if self.mirror_send is not None else None
+        self.version, self._sliced = 0, (-1, 0)
 
     # ---- device hooks (replaced by numpy stand-ins in the CPU tests) ------------------------
     def _init_identity(self):
@@ -105,24 +196,40 @@ class ShardedHalf:
             _lib.check(_lib.load().srk_set_identity_f64(_ptr(self.S), self.ld, self.rows, self.n_out, self.row0,
                                                         _stream()), "srk_set_identity_f64")
 
-    def _dense_pattern(self, cols: np.ndarray) -> torch.Tensor:
+    def _dense_pattern(self) -> torch.Tensor:
         a8 = torch.empty((self.n_out, self.lda), dtype=torch.uint8, device=self.device)
         ptr = torch.from_numpy(self.op.indptr).to(self.device)
-        idx = torch.from_numpy(np.ascontiguousarray(cols)).to(self.device)
+        idx = torch.from_numpy(np.ascontiguousarray(self.op.indices)).to(self.device)
         _lib.check(_lib.load().srk_csr_to_dense_u8(_ptr(ptr), _ptr(idx), 0, self.n_out, self.lda, _ptr(a8),
                                                    self.lda, _stream()), "srk_csr_to_dense_u8")
         return a8
 
-    def _launch(self, args: _lib.I8Args, name: str):
-        _lib.check(_lib.load().srk_i8_half(C.byref(args), _stream()), name)
+    def _launch(self, args: _lib.X2Args, name: str):
+        _lib.check(_lib.load().srk_x2_half(C.byref(args), _stream()), name)
 
-    def _exchange(self):
-        dist.all_to_all_single(self.recvbuf, self.sendbuf, group=self.group)
+    def _launch_slice(self, ns: int):
+        _lib.check(_lib.load().srk_slice_rows_max_f64(
+            _ptr(self.S), self.ld, self.rows, self.n_out, self.row0, ns, _ptr(self.planes), self.ldp,
+            self.planes.stride(0), _ptr(self.bound_vec), _stream()), "srk_slice_rows_max_f64")
 
     def _reduce_scalars(self):
         dist.all_reduce(self.scal, op=dist.ReduceOp.MAX, group=self.group)
 
-    # ---- one update ----------------------------------------------------------------------------
+    # ---- pieces of one update ------------------------------------------------------------------
+    def _pattern_counts(self) -> torch.Tensor:
+        """uint16 ``A A^T`` for the LOCAL rows (rows_q x n_out), see DeviceOperator.pattern_counts."""
+        ldc = _round_up(max(self.n_out, 1), 16)
+        cnt = torch.zeros((self.per, ldc), dtype=torch.int16, device=self.device)
+        if self.rows:
+            a = _lib.X2Args()
+            a.mode, a.ns = _lib.SRK_X2_COUNTS, 1
+            a.M, a.R, a.K = self.rows, self.n_out, self.n_in
+            a.A8, a.lda = self.a8.data_ptr() + self.row0 * self.lda, self.lda
+            a.in_planes, a.ld_in, a.in_plane_stride = self.a8.data_ptr(), self.lda, self.a8.numel()
+            a.out_counts, a.ld_out_counts = cnt.data_ptr(), ldc
+            self._launch(a, "srk_x2_half(COUNTS)")
+        return cnt
+
     def _timed(self, name, fn):
         if self.events is None:
             return fn()
@@ -133,71 +240,132 @@ class ShardedHalf:
         b.record(st)
         self.events.append((name, a, b))
 
-    def update(self, src: "ShardedHalf") -> None:
-        ns = self.ns
-        self.scal.zero_()
-        guard = 1.0 + 2.0 ** -20
-        s_off = min(src.bound_S_max, src.maxoff * (1.0 + 1e-6) + src.bound_S_max * 2.0 ** -23)
-        u_mul, u_add = s_off * guard, guard
-        blend = (1.0 - self.lbd) if self.prior is not None else 1.0
-        mul = blend * self.coef * self.rho_max * max(1.0, s_off) * guard
-        add = self.lbd * self.prior_max * guard if self.prior is not None else 0.0
-        bo, bi = self.out_plan.blk, self.in_plan.blk
+    def _planes_for(self, ns: int) -> torch.Tensor:
+        if self.planes is None or self.planes.shape[0] < ns:
+            self.planes = torch.zeros((max(ns, self.ns_alloc), self.per, self.ldp), dtype=torch.uint8,
+                                      device=self.device)
+            self._sliced = (-1, 0)
+        if self._sliced != (self.version, ns):
+            if self.rows:
+                self._timed("slice_rows_max", lambda: self._launch_slice(ns))
+            self._sliced = (self.version, ns)
+        return self.planes
 
-        def mids():
-            for step in range(self.world):
-                q = (self.rank + 1 + step) % self.world            # own block last
-                nq = self.out_plan.count(q)
-                if nq == 0 or src.rows == 0:
-                    continue
-                a = _lib.I8Args()
-                a.mode, a.ns = _lib.SRK_I8_MID, ns
-                a.R, a.N, a.K = src.rows, nq, self.n_in
-                a.in_planes, a.ld_in, a.in_plane_stride = src.planes.data_ptr(), src.ldp, src.planes.stride(0)
-                a.in_rowbound = _lib.RowBound.of(src.rho_dev.data_ptr() + 8 * src.row0, *src.bound_S)
-                a.A8, a.lda = self.a8_mid.data_ptr() + self.out_plan.start(q) * self.lda, self.lda
-                a.diag_offset, a.unit_diag = src.row0, 1
-                a.out_planes = self.sendbuf.data_ptr() + q * ns * bo * bi
-                a.ld_outp, a.out_plane_stride = bi, bo * bi
-                a.out_rowbound = _lib.RowBound.of(self.deg_dev.data_ptr() + 8 * self.out_plan.start(q), u_mul, u_add)
-                self._launch(a, "srk_i8_half(MID)")
+    def _mid(self, src: "ShardedHalf", ns: int, bound_mul: float):
+        """Column block (rows_p x src rows) of U for every destination rank p."""
+        planes_in = src._planes_for(ns)
+        if not self.ex.peer and self.send_U.shape[-1] != src.per:
+            self.send_U = torch.zeros((self.world, self.ns_alloc, self.per, src.per), dtype=torch.uint8,
+                                      device=self.device)
+        if src.rows == 0:
+            return
+        for step in range(self.world):
+            p = (self.rank + 1 + step) % self.world               # own block last
+            rows_p = self.plan.count(p)
+            if rows_p == 0:
+                continue
+            a = _lib.X2Args()
+            a.mode, a.ns = _lib.SRK_X2_MID, ns
+            a.M, a.R, a.K = rows_p, src.rows, self.n_in
+            a.A8, a.lda = self.a8.data_ptr() + self.plan.start(p) * self.lda, self.lda
+            a.in_planes, a.ld_in, a.in_plane_stride = planes_in.data_ptr(), src.ldp, planes_in.stride(0)
+            a.in_rowbound = _lib.RowBound.of(src.bound_vec.data_ptr(), 1.0, 0.0)
+            if self.ex.peer:                                      # rank p's row panel, my columns
+                a.out_planes = self.U_ptrs[p] + src.row0
+                a.ld_outp, a.out_plane_stride = self.ldu, self.per * self.ldu
+            else:
+                a.out_planes = self.send_U[p].data_ptr()
+                a.ld_outp, a.out_plane_stride = src.per, self.per * src.per
+            a.out_rowbound = _lib.RowBound.of(self.deg_dev.data_ptr() + 8 * self.plan.start(p), bound_mul, 0.0)
+            self._launch(a, "srk_x2_half(MID)")
 
-        self._timed("i8_half_mid", mids)
-        self._timed("exchange", self._exchange)
+    def _exchange_U(self, src: "ShardedHalf", ns: int):
+        if self.ex.peer:
+            self.ex.barrier()
+            return
+        recv = torch.empty_like(self.send_U)
+        dist.all_to_all_single(recv, self.send_U, group=self.group)
+        for s in range(self.world):                               # block from rank s = its rows as my columns
+            cnt = src.plan.count(s)
+            if cnt:
+                self.U[:ns, :, src.plan.start(s):src.plan.start(s) + cnt] = recv[s, :ns, :, :cnt]
 
-        def final():
-            if self.rows == 0:
-                return
-            b = _lib.I8Args()
-            b.mode, b.ns = _lib.SRK_I8_FINAL, ns
-            b.R, b.N, b.K = self.rows, self.n_out, self.in_plan.padded
-            b.in_planes, b.ld_in, b.in_plane_stride = self.recvbuf.data_ptr(), bi, bo * bi
-            b.in_kblock, b.in_kblock_stride = bi, ns * bo * bi
-            b.in_rowbound = _lib.RowBound.of(self.deg_dev.data_ptr() + 8 * self.row0, u_mul, u_add)
-            b.A8, b.lda = self.a8_fin.data_ptr(), self.lda
-            b.diag_offset, b.unit_diag = self.row0, 0
-            b.g_row, b.g_col = self.g.data_ptr() + 8 * self.row0, self.g.data_ptr()
-            b.out_f64, b.ld_out = self.S.data_ptr(), self.ld
-            b.out_planes, b.ld_outp, b.out_plane_stride = self.planes.data_ptr(), self.ldp, self.planes.stride(0)
-            b.out_rowbound = _lib.RowBound.of(self.rho_dev.data_ptr() + 8 * self.row0, mul, add)
+    def _final(self, ns: int, bound_mul: float):
+        for (p, j_lo, j_hi, r_lo, r_hi, mirror) in self.tasks:
+            b = _lib.X2Args()
+            b.mode, b.ns = _lib.SRK_X2_FINAL, ns
+            own = p == self.rank and self.symmetric
+            col0 = self.plan.start(p) + j_lo                       # first output column of this block
+            b.M, b.R, b.K = j_hi - j_lo, r_hi - r_lo, self.n_in
+            b.A8, b.lda = self.a8.data_ptr() + col0 * self.lda, self.lda
+            b.in_planes = self.U.data_ptr() + r_lo * self.ldu
+            b.ld_in, b.in_plane_stride = self.ldu, self.per * self.ldu
+            b.in_rowbound = _lib.RowBound.of(self.deg_dev.data_ptr() + 8 * (self.row0 + r_lo), bound_mul, 0.0)
+            b.g_a, b.g_v = self.g.data_ptr() + 8 * col0, self.g.data_ptr() + 8 * (self.row0 + r_lo)
+            off = r_lo * self.ld + col0                            # element offset of the block inside S / counts
+            ldc = self.counts.stride(0)
+            b.counts, b.ld_counts, b.add_counts = self.counts.data_ptr() + 2 * (r_lo * ldc + col0), ldc, 1
+            b.use_evidence = 1 if self.evidence_from_pattern else 0
+            b.out_f64, b.ld_out = self.S.data_ptr() + 8 * off, self.ld
             e = b.epi
             e.coef = self.coef
-            if self.evidence is not None:
-                e.evidence, e.ld_evidence = self.evidence.data_ptr(), self.evidence.stride(0)
-            if self.prior is not None:
-                e.prior, e.ld_prior, e.lambda_ = self.prior.data_ptr(), self.prior.stride(0), self.lbd
-            e.s_old, e.ld_s_old = self.S.data_ptr(), self.ld
+            e.s_old, e.ld_s_old = self.S.data_ptr() + 8 * off, self.ld
             e.maxdiff, e.maxoff = self.scal.data_ptr(), self.scal.data_ptr() + 8
-            self._launch(b, "srk_i8_half(FINAL)")
+            if self.evidence is not None and not self.evidence_from_pattern:
+                e.evidence = self.evidence.data_ptr() + r_lo * self.evidence.stride(0) + col0
+                e.ld_evidence = self.evidence.stride(0)
+            if self.prior is not None:
+                e.prior = self.prior.data_ptr() + 8 * (r_lo * self.prior.stride(0) + col0)
+                e.ld_prior, e.lambda_ = self.prior.stride(0), self.lbd
+            if own:
+                b.layout, b.diag_offset = _lib.SRK_X2_SYMMETRIC, 0
+            else:
+                b.layout = _lib.SRK_X2_TRANSPOSED
+                # the diagonal runs through the own block only: j + col0 == row0 + r_lo + r
+                b.diag_offset = (self.row0 + r_lo - col0) if p == self.rank else _NO_DIAGONAL
+                if mirror:
+                    if self.ex.peer:                               # rows j of rank p's S, my columns
+                        b.mirror_out = self.S_ptrs[p] + 8 * (j_lo * self.ld)
+                        b.ld_mirror, b.mirror_col0 = self.ld, self.row0 + r_lo
+                    else:
+                        b.mirror_out = self.mirror_send[p].data_ptr() + 8 * (j_lo * self.per)
+                        b.ld_mirror, b.mirror_col0 = self.per, r_lo
+            self._launch(b, "srk_x2_half(FINAL)")
 
-        self._timed("i8_half_final", final)
-        self._pending_bound = ((mul, add), mul * self.rho_max + add)
+    def _exchange_mirrors(self):
+        """Staged mode: deliver the mirrored blocks and place them (peer mode stored them already)."""
+        if self.ex.peer or self.mirror_send is None:
+            return
+        dist.all_to_all_single(self.mirror_recv, self.mirror_send, group=self.group)
+        for s in range(self.world):
+            if s == self.rank:
+                continue
+            for (p, j_lo, j_hi, r_lo, r_hi, mirror) in pair_tasks(self.plan, s, True):
+                if p == self.rank and mirror:                      # rank s computed rows j_lo..j_hi of mine
+                    c0 = self.plan.start(s) + r_lo
+                    self.S[j_lo:j_hi, c0:c0 + (r_hi - r_lo)] = self.mirror_recv[s, j_lo:j_hi, r_lo:r_hi]
+
+    # ---- one update ----------------------------------------------------------------------------
+    def update(self, src: "ShardedHalf") -> None:
+        self.scal.zero_()
+        blend = (1.0 - self.lbd) if self.prior is not None else 1.0
+        ns = choose_slices(self.ns, self.coef, blend, self.rho_max, src.maxoff)
+        if ns > self.U.shape[0]:
+            raise RuntimeError(f"update needs {ns} planes but the row panel of U was allocated for {self.U.shape[0]}: "
+                               "construct the solver with slices=4")
+        self.slices_used.append(ns)
+        guard = 1.0 + 2.0 ** -14
+        bound_mul = src.maxoff * guard                             # U[j, :] <= deg_j * max(S_off)
+        self._timed("x2_half_mid", lambda: self._mid(src, ns, bound_mul))
+        self._timed("exchange", lambda: self._exchange_U(src, ns))
+        self._timed("x2_half_final", lambda: self._final(ns, bound_mul))
+        self._timed("mirror_exchange", self._exchange_mirrors)
+        self.version += 1
 
     def finish(self) -> float:
         self._reduce_scalars()
         maxdiff, maxoff = self.scal.tolist()
         self.maxoff = maxoff
-        self.bound_S, self.bound_S_max = self._pending_bound
         return maxdiff
 
     def local_result(self) -> torch.Tensor:
@@ -205,7 +373,7 @@ class ShardedHalf:
 
     def gathered_result(self) -> torch.Tensor:
         """Full n_out x n_out matrix on every rank (all-gather of the row blocks)."""
-        per = self.out_plan.per
+        per = self.per
         pad = torch.zeros((per, self.n_out), dtype=self.S.dtype, device=self.S.device)
         pad[: self.rows] = self.local_result()
         full = torch.empty((self.world * per, self.n_out), dtype=self.S.dtype, device=self.S.device)
@@ -217,18 +385,23 @@ def _rank_world(group=None):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
+def _check_mode(mode):
+    if mode not in (None, "auto", "i8"):
+        raise NotImplementedError("the row-sharded solver runs the tensor-core (i8) path")
+
+
 class ShardedDirectedSolver:
     """Row-sharded ``S <- [E o] C * W S W^T; diag <- 1`` (SimRank.py:139, :361)."""
 
     half_cls = ShardedHalf
 
-    def __init__(self, op: HostOperator, C_, evidence=None, prior=None, lbd=0.0, mode="i8", ns=3, device=None,
-                 group=None):
-        if mode not in (None, "auto", "i8"):
-            raise NotImplementedError("the row-sharded solver runs the tensor-core (i8) path")
+    def __init__(self, op: HostOperator, C_, evidence=None, prior=None, lbd=0.0, mode="i8", ns=None, device=None,
+                 group=None, evidence_from_pattern=False):
+        _check_mode(mode)
         rank, world = _rank_world(group)
         self.mode = "i8"
-        self.half = self.half_cls(op, C_, rank, world, device, ns, evidence, prior, lbd, group)
+        self.half = self.half_cls(op, C_, rank, world, device, ns, evidence, prior, lbd, group,
+                                  evidence_from_pattern)
         self.halves = [self.half]
 
     def step(self) -> float:
@@ -246,13 +419,15 @@ class ShardedBipartiteSolver:
     half_cls = ShardedHalf
 
     def __init__(self, op12: HostOperator, op21: HostOperator, C1, C2, evidence1=None, evidence2=None, prior1=None,
-                 prior2=None, lbd1=0.0, lbd2=0.0, mode="i8", ns=3, device=None, group=None):
-        if mode not in (None, "auto", "i8"):
-            raise NotImplementedError("the row-sharded solver runs the tensor-core (i8) path")
+                 prior2=None, lbd1=0.0, lbd2=0.0, mode="i8", ns=None, device=None, group=None,
+                 evidence1_from_pattern=False, evidence2_from_pattern=False):
+        _check_mode(mode)
         rank, world = _rank_world(group)
         self.mode = "i8"
-        self.h1 = self.half_cls(op12, C1, rank, world, device, ns, evidence1, prior1, lbd1, group)
-        self.h2 = self.half_cls(op21, C2, rank, world, device, ns, evidence2, prior2, lbd2, group)
+        self.h1 = self.half_cls(op12, C1, rank, world, device, ns, evidence1, prior1, lbd1, group,
+                                evidence1_from_pattern)
+        self.h2 = self.half_cls(op21, C2, rank, world, device, ns, evidence2, prior2, lbd2, group,
+                                evidence2_from_pattern, exchange=self.h1.ex if self.h1.ex.peer else None)
         self.halves = [self.h1, self.h2]
 
     def step(self):

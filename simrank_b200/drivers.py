@@ -128,10 +128,10 @@ def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mod
     rank, world = _world()
     if world > 1:                      # one process per GPU: S row-sharded, tensor-core path
         from . import dist as _sd
-        ev = evidence.counts if evidence is not None else None
+        ev, from_pattern = _evidence_args(evidence, op, "i8")
         return _sd.ShardedDirectedSolver(op, C, _local_rows(ev, op.M, rank, world),
                                          _local_rows(pr, op.M, rank, world), lbd, _mode_with_prior(mode, prior),
-                                         slices, dop.device)
+                                         slices, dop.device, evidence_from_pattern=from_pattern)
     mode = _eng.choose_mode(op, _mode_with_prior(mode, prior))
     ev, from_pattern = _evidence_args(evidence, op, mode)
     return _eng.DirectedSolver(dop, C, ev, pr, lbd, mode, slices,
@@ -146,12 +146,13 @@ def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=N
     rank, world = _world()
     if world > 1:
         from . import dist as _sd
-        e1 = evidence1.counts if evidence1 is not None else None
-        e2 = evidence2.counts if evidence2 is not None else None
+        e1, pat1 = _evidence_args(evidence1, op12, "i8")
+        e2, pat2 = _evidence_args(evidence2, op21, "i8")
         return _sd.ShardedBipartiteSolver(op12, op21, C1, C2, _local_rows(e1, op12.M, rank, world),
                                           _local_rows(e2, op21.M, rank, world), _local_rows(p1, op12.M, rank, world),
                                           _local_rows(p2, op21.M, rank, world), lbd1, lbd2,
-                                          _mode_with_prior(mode, prior1, prior2), slices, d12.device)
+                                          _mode_with_prior(mode, prior1, prior2), slices, d12.device,
+                                          evidence1_from_pattern=pat1, evidence2_from_pattern=pat2)
     mode = _mode_with_prior(mode, prior1, prior2)
     m1, m2 = _eng.choose_mode(op12, mode), _eng.choose_mode(op21, mode)
     mode = m1 if m1 == m2 else "csr"

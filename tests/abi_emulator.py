@@ -1,8 +1,9 @@
-"""Host-memory emulator of ``srk_i8_half`` (include/simrank_b200.h) in numpy.  TEST ONLY.
+"""Host-memory emulator of ``srk_x2_half`` and ``srk_slice_rows_max_f64`` (include/simrank_b200.h)
+in numpy.  TEST ONLY.
 
-It interprets the very ``srk_i8_args`` struct the product passes to the CUDA library, but on
-CPU tensors, so the multi-rank host logic (shard offsets, send/receive block layout, K-blocked
-operands, bounds) can run under gloo without a GPU.  It is never imported by the package."""
+It interprets the very structs the product passes to the CUDA library, but on CPU tensors, so the
+multi-rank host logic (shard offsets, block assignment of the symmetric update, staging layouts,
+bounds) can run under gloo without a GPU.  It is never imported by the package."""
 import ctypes as C
 
 import numpy as np
@@ -10,8 +11,11 @@ import numpy as np
 from simrank_b200 import _lib
 
 
-def _bytes(ptr, n):
-    return np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr))
+def _view(ptr, ctype, rows, cols, ld):
+    """2-D numpy view [rows, cols] of a row-major matrix with leading dimension ld (elements)."""
+    n = (rows - 1) * ld + cols
+    raw = np.ctypeslib.as_array((ctype * n).from_address(ptr))
+    return np.lib.stride_tricks.as_strided(raw, (rows, cols), (ld * raw.itemsize, raw.itemsize))
 
 
 def _f64(ptr, n):
@@ -24,88 +28,110 @@ def _bound(rb, n):
     return np.full(n, rb.add)
 
 
+def pow2_exponent(b, ns):
+    """f with 2^f the smallest power of two >= b, clamped to f >= 8 ns - 46; None-like -2^30 for b <= 0."""
+    b = np.asarray(b, dtype=np.float64)
+    m, e = np.frexp(np.where(b > 0, b, 1.0))
+    f = np.maximum(np.where(m == 0.5, e - 1, e), 8 * ns - 46)
+    return np.where(b > 0, f, -(1 << 30)).astype(np.int64)
+
+
 def _read_planes(a):
-    ns, R, K = a.ns, a.R, a.K
-    q = np.zeros((R, K), dtype=np.int64)
-    for s in range(ns):
+    q = np.zeros((a.R, a.K), dtype=np.int64)
+    for s in range(a.ns):
         if a.in_kblock > 0:
             kb = a.in_kblock
-            plane = np.zeros((R, K), dtype=np.int64)
-            for b in range(K // kb):
+            for b in range(a.K // kb):
                 base = a.in_planes + b * a.in_kblock_stride + s * a.in_plane_stride
-                raw = _bytes(base, (R - 1) * a.ld_in + kb)
-                blk = np.lib.stride_tricks.as_strided(raw, (R, kb), (a.ld_in, 1))
-                plane[:, b * kb:(b + 1) * kb] = blk
+                q[:, b * kb:(b + 1) * kb] += _view(base, C.c_uint8, a.R, kb, a.ld_in).astype(np.int64) << (8 * (a.ns - 1 - s))
         else:
-            raw = _bytes(a.in_planes + s * a.in_plane_stride, (R - 1) * a.ld_in + K)
-            plane = np.lib.stride_tricks.as_strided(raw, (R, K), (a.ld_in, 1)).astype(np.int64)
-        q += plane << (8 * (ns - 1 - s))
+            q += _view(a.in_planes + s * a.in_plane_stride, C.c_uint8, a.R, a.K, a.ld_in).astype(np.int64) << (8 * (a.ns - 1 - s))
     return q
 
 
-def _a8(a):
-    raw = _bytes(a.A8, (a.N - 1) * a.lda + a.K)
-    return np.lib.stride_tricks.as_strided(raw, (a.N, a.K), (a.lda, 1)).astype(np.int64)
-
-
-def _write_planes(base, plane_stride, ld, ns, rows, cols, q):
-    for s in range(ns):
-        raw = _bytes(base + s * plane_stride, (rows - 1) * ld + cols)
-        out = np.lib.stride_tricks.as_strided(raw, (rows, cols), (ld, 1))
-        out[:, :] = ((q >> (8 * (ns - 1 - s))) & 0xFF).astype(np.uint8)
-
-
-def srk_i8_half(a: _lib.I8Args) -> None:
-    ns, R, N, K = a.ns, a.R, a.N, a.K
-    kq = float(256 ** ns)
-    A = _a8(a)
-    D = _read_planes(a) @ A.T                                    # exact integers
-    if a.mode == _lib.SRK_I8_COUNTS:
-        _write_planes(a.out_planes, 0, a.ld_outp, 1, R, N, np.minimum(D, 255))
+def srk_x2_half(a: _lib.X2Args) -> None:
+    ns, M, R, K = a.ns, a.M, a.R, a.K
+    A = _view(a.A8, C.c_uint8, M, K, a.lda).astype(np.int64)
+    D = A @ _read_planes(a).T                                     # [M, R] exact integers
+    if a.mode == _lib.SRK_X2_COUNTS:
+        _view(a.out_counts, C.c_uint16, M, R, a.ld_out_counts)[:, :] = np.minimum(D, 65535).astype(np.uint16)
         return
+    qmax = 256 ** ns
     inb = _bound(a.in_rowbound, R)
-    if a.mode == _lib.SRK_I8_MID:
-        U = D * (inb / kq)[:, None]
-        if a.unit_diag:
-            U = U + A[:, a.diag_offset:a.diag_offset + R].T
-        outb = _bound(a.out_rowbound, N)
-        scale = np.where(outb > 0, kq / np.where(outb > 0, outb, 1.0), 0.0)
-        q = np.clip(np.rint(U * scale[None, :]), 0, kq - 1).astype(np.int64)
-        _write_planes(a.out_planes, a.out_plane_stride, a.ld_outp, ns, N, R, q.T.copy())
+    if a.mode == _lib.SRK_X2_MID:
+        fj = pow2_exponent(_bound(a.out_rowbound, M), ns)
+        live = fj > -(1 << 29)
+        scale = np.where(live, 2.0 ** -np.where(live, fj, 0).astype(np.float64), 0.0)
+        q = np.clip(np.rint((D * scale[:, None]) * np.maximum(inb, 0.0)[None, :]), 0, qmax - 1).astype(np.int64)
+        cols = -(-R // 16) * 16                                   # whole 16-column chunks are written
+        for s in range(ns):
+            out = _view(a.out_planes + s * a.out_plane_stride, C.c_uint8, M, cols, a.ld_outp)
+            out[:, :R] = ((q >> (8 * (ns - 1 - s))) & 0xFF).astype(np.uint8)
+            out[:, R:] = 0
         return
+    # ---- FINAL, in the (j, r) frame of the kernel
     e = a.epi
-    g_row, g_col = _f64(a.g_row, R), _f64(a.g_col, N)
-    val = D * (inb / kq * g_row * e.coef)[:, None] * g_col[None, :]
-    if e.evidence:
-        raw = _bytes(e.evidence, (R - 1) * e.ld_evidence + N)
-        cnt = np.lib.stride_tricks.as_strided(raw, (R, N), (e.ld_evidence, 1)).astype(np.int64)
-        val = val * (1 - 0.5 ** cnt)
+    trans = a.layout == _lib.SRK_X2_TRANSPOSED
+    sym = a.layout == _lib.SRK_X2_SYMMETRIC
+    rows, cols = (R, M) if trans else (M, R)
+
+    def mat(ptr, ctype, ld):                                      # caller's matrix in the (j, r) frame
+        v = _view(ptr, ctype, rows, cols, ld)
+        return v.T if trans else v
+
+    fr = pow2_exponent(inb, ns)
+    s = np.where(fr > -(1 << 29), 8 * ns - fr, 0)
+    dl = np.minimum(np.maximum(-s, 0), 17)
+    s = np.maximum(s, 0)
+    T = D << dl[None, :]
+    cnt = mat(a.counts, C.c_uint16, a.ld_counts).astype(np.int64) if a.counts else np.zeros((M, R), dtype=np.int64)
+    if a.add_counts:
+        T = T + (cnt << s[None, :])
+    g_a, g_v = _f64(a.g_a, M), _f64(a.g_v, R)
+    val = (T.astype(np.float64) * ((e.coef * g_v) * 2.0 ** -s.astype(np.float64))[None, :]) * g_a[:, None]
+    if a.use_evidence:
+        val = val * (1 - 0.5 ** np.minimum(cnt, 60).astype(np.float64))
+    elif e.evidence:
+        val = val * (1 - 0.5 ** mat(e.evidence, C.c_uint8, e.ld_evidence).astype(np.float64))
     if e.prior:
-        raw = _f64(e.prior, (R - 1) * e.ld_prior + N)
-        pr = np.lib.stride_tricks.as_strided(raw, (R, N), (e.ld_prior * 8, 8))
-        val = (1 - e.lambda_) * val + e.lambda_ * pr
-    rr = np.arange(R)
-    dj = rr + a.diag_offset
-    on = dj < N
-    val[rr[on], dj[on]] = 1.0
-    off = val.copy()
-    off[rr[on], dj[on]] = 0.0
-    raw = _f64(a.out_f64, (R - 1) * a.ld_out + N)
-    out = np.lib.stride_tricks.as_strided(raw, (R, N), (a.ld_out * 8, 8))
+        val = (1 - e.lambda_) * val + e.lambda_ * mat(e.prior, C.c_double, e.ld_prior)
+    jj, rr = np.meshgrid(np.arange(M), np.arange(R), indexing="ij")
+    diag = jj == rr + a.diag_offset
+    val[diag] = 1.0
+    live = np.ones((M, R), dtype=bool) if not sym else (jj <= rr)
+    out = mat(a.out_f64, C.c_double, a.ld_out)
     if e.s_old:
-        raw = _f64(e.s_old, (R - 1) * e.ld_s_old + N)
-        old = np.lib.stride_tricks.as_strided(raw, (R, N), (e.ld_s_old * 8, 8))
-        d = np.abs(val - old)
+        d = np.abs(val - mat(e.s_old, C.c_double, e.ld_s_old))[live]
         d = d[~np.isnan(d)]
         if e.maxdiff and d.size:
             m = _f64(e.maxdiff, 1)
             m[0] = max(m[0], d.max())
     if e.maxoff:
         m = _f64(e.maxoff, 1)
-        m[0] = max(m[0], off.max(initial=0.0))
-    out[:, :] = val
-    if a.out_planes:
-        outb = _bound(a.out_rowbound, R)
-        scale = np.where(outb > 0, kq / np.where(outb > 0, outb, 1.0), 0.0)
-        q = np.clip(np.rint(off * scale[:, None]), 0, kq - 1).astype(np.int64)
-        _write_planes(a.out_planes, a.out_plane_stride, a.ld_outp, ns, R, N, q)
+        m[0] = max(m[0], val[live & ~diag].max(initial=0.0))
+    if sym:
+        up = np.triu(val)
+        out[:, :] = up + np.triu(val, 1).T
+    else:
+        out[:, :] = val
+    if a.mirror_out:
+        mir = _view(a.mirror_out + 8 * a.mirror_col0, C.c_double, M, R, a.ld_mirror)
+        mir[~diag] = val[~diag]
+
+
+def srk_slice_rows_max_f64(V_ptr, ldv, R, K, zero_diag_offset, ns, planes_ptr, ldp, plane_stride, bound_ptr):
+    V = _view(V_ptr, C.c_double, R, K, ldv).copy()
+    V[np.isnan(V) | (V < 0)] = 0.0
+    if zero_diag_offset >= 0:
+        r = np.arange(R)
+        ok = r + zero_diag_offset < K
+        V[r[ok], r[ok] + zero_diag_offset] = 0.0
+    m = V.max(axis=1)
+    qmax = 256.0 ** ns - 1
+    _f64(bound_ptr, R)[:] = m * ((qmax + 1) / qmax)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = np.where(m[:, None] > 0, np.rint(V * (qmax / np.where(m > 0, m, 1.0))[:, None]), 0.0).astype(np.int64)
+    for s in range(ns):
+        out = _view(planes_ptr + s * plane_stride, C.c_uint8, R, ldp, ldp)
+        out[:, :K] = ((q >> (8 * (ns - 1 - s))) & 0xFF).astype(np.uint8)
+        out[:, K:] = 0

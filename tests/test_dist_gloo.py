@@ -1,9 +1,10 @@
-"""World-size 2 and 3 tests of the row-sharded solver's HOST logic on CPU (gloo backend).
+"""World-size 2, 3 and 4 tests of the row-sharded solver's HOST logic on CPU (gloo backend).
 
-The two CUDA launch hooks of simrank_b200.dist.ShardedHalf are replaced by the numpy emulator
-of the C ABI (tests/abi_emulator.py); everything else -- shard plans, send/receive block
-layout, the K-blocked operand description, bound propagation, the all-to-all and the MAX
-all-reduce -- is the product code, and the gathered result must match the oracle."""
+The CUDA launch hooks of simrank_b200.dist.ShardedHalf are replaced by the numpy emulator of the
+C ABI (tests/abi_emulator.py); everything else -- shard plans, the assignment of the blocks of the
+symmetric update to ranks, staging layouts, pointer offsets, bound propagation, the all-to-alls
+and the MAX all-reduce -- is the product code (the StagedExchange strategy; on the GPU box the
+same offsets address peer memory), and the gathered result must match the oracle."""
 import os
 import socket
 
@@ -26,14 +27,19 @@ class CpuHalf(sdist.ShardedHalf):
         for i in range(self.rows):
             self.S[i, self.row0 + i] = 1.0
 
-    def _dense_pattern(self, cols):
+    def _dense_pattern(self):
         a8 = torch.zeros((self.n_out, self.lda), dtype=torch.uint8)
         rows = np.repeat(np.arange(self.n_out), self.op.deg)
-        a8[torch.from_numpy(rows), torch.from_numpy(cols.astype(np.int64))] = 1
+        a8[torch.from_numpy(rows), torch.from_numpy(self.op.indices.astype(np.int64))] = 1
         return a8
 
     def _launch(self, args, name):
-        abi_emulator.srk_i8_half(args)
+        abi_emulator.srk_x2_half(args)
+
+    def _launch_slice(self, ns):
+        abi_emulator.srk_slice_rows_max_f64(self.S.data_ptr(), self.ld, self.rows, self.n_out, self.row0, ns,
+                                            self.planes.data_ptr(), self.ldp, self.planes.stride(0),
+                                            self.bound_vec.data_ptr())
 
     def _timed(self, name, fn):
         return fn()
@@ -61,7 +67,7 @@ def _worker(rank, world, port, case, out):
         if case == "directed":
             frm, to = synth.directed_edges(300, 3000, 0.8, 11)
             op = graph.operator_from_edges(to, frm, 300, 300)
-            sol = CpuDirected(op, 0.8, ns=3, device=dev)
+            sol = CpuDirected(op, 0.8, ns=None, device=dev)
             diffs = [sol.step() for _ in range(4)]
             S = sol.S.numpy()
             So, _, _ = orc.simrank(op.to_dense(), 0.8, 4, 0.0)
@@ -81,10 +87,7 @@ def _worker(rank, world, port, case, out):
             op12 = graph.operator_from_edges(u, i, 130, 77, g1)
             op21 = graph.operator_from_edges(i, u, 77, 130, g2)
             A12 = (op12.to_dense() > 0).astype(np.int64)
-            cnt1 = np.minimum(A12 @ A12.T, 255).astype(np.uint8)
-            plan1 = sdist.ShardPlan(130, world)
-            ev_local = torch.from_numpy(np.ascontiguousarray(cnt1[plan1.start(rank):plan1.stop(rank)]))
-            sol = CpuBipartite(op12, op21, 0.8, 0.7, evidence1=ev_local if ev_local.numel() else None, ns=3, device=dev)
+            sol = CpuBipartite(op12, op21, 0.8, 0.7, ns=3, device=dev, evidence1_from_pattern=True)
             for _ in range(3):
                 sol.step()
             S1, S2 = sol.S1.numpy(), sol.S2.numpy()
@@ -101,7 +104,7 @@ def _worker(rank, world, port, case, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("case", ["directed", "bipartite"])
 def test_sharded_solver_matches_oracle(world, case):
     ctx = mp.get_context("spawn")
@@ -122,16 +125,29 @@ def test_sharded_solver_matches_oracle(world, case):
     assert sum(r[3] for r in results) == n              # the row blocks tile the matrix
 
 
-def test_shard_plan_and_padded_layout():
+def test_shard_plan_and_block_assignment():
     p = sdist.ShardPlan(700, 3)
-    assert (p.per, p.blk, p.padded) == (234, 256, 768)
-    assert [p.count(r) for r in range(3)] == [234, 234, 232]
-    k = np.arange(700)
-    pk = p.pad_index(k)
-    assert pk[0] == 0 and pk[233] == 233 and pk[234] == 256 and pk[699] == 2 * 256 + 231
-    assert len(set(pk.tolist())) == 700
+    assert p.per == 240 and [p.count(r) for r in range(3)] == [240, 240, 220]
     q = sdist.ShardPlan(32768, 8)
-    assert (q.per, q.blk, q.padded) == (4096, 4096, 32768)
-    assert np.array_equal(q.pad_index(np.arange(32768)), np.arange(32768))   # no re-layout at cfg4
+    assert q.per == 4096 and q.start(7) == 28672
     e = sdist.ShardPlan(5, 8)
-    assert [e.count(r) for r in range(8)] == [1, 1, 1, 1, 1, 0, 0, 0]
+    assert [e.count(r) for r in range(8)] == [5, 0, 0, 0, 0, 0, 0, 0]
+    # every unordered pair of row blocks is computed exactly once, by one of its two owners
+    for n, world in ((700, 3), (32768, 8), (1000, 4), (300, 2), (5, 8), (4096, 5)):
+        plan = sdist.ShardPlan(n, world)
+        cover = np.zeros((n, n), dtype=np.int32)
+        for rank in range(world):
+            for (pp, j_lo, j_hi, r_lo, r_hi, mirror) in sdist.pair_tasks(plan, rank, True):
+                rows = slice(plan.start(rank) + r_lo, plan.start(rank) + r_hi)
+                cols = slice(plan.start(pp) + j_lo, plan.start(pp) + j_hi)
+                cover[rows, cols] += 1
+                if mirror:
+                    cover[cols, rows] += 1
+                else:
+                    assert pp == rank
+        assert (cover == 1).all(), (n, world)
+        # balanced: no rank computes more than its share plus one split block
+        work = [sum((j_hi - j_lo) * (r_hi - r_lo) * (0.5 if pp == rank else 1.0)
+                    for (pp, j_lo, j_hi, r_lo, r_hi, _) in sdist.pair_tasks(plan, rank, True)) for rank in range(world)]
+        if n >= 256 * world:
+            assert max(work) <= 1.35 * (sum(work) / world), (n, world, work)
