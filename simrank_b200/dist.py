@@ -351,8 +351,11 @@ class ShardedHalf:
         blend = (1.0 - self.lbd) if self.prior is not None else 1.0
         ns = choose_slices(self.ns, self.coef, blend, self.rho_max, src.maxoff)
         if ns > self.U.shape[0]:
-            raise RuntimeError(f"update needs {ns} planes but the row panel of U was allocated for {self.U.shape[0]}: "
-                               "construct the solver with slices=4")
+            # every rank takes this branch together: ns derives from the all-reduced range of S_in
+            self.ns_alloc = ns
+            self.U, self.U_ptrs = self.ex.alloc((ns, self.per, self.ldu), torch.uint8, self.device)
+            if not self.ex.peer:
+                self.send_U = torch.zeros((self.world, ns, self.per, 16), dtype=torch.uint8, device=self.device)
         self.slices_used.append(ns)
         guard = 1.0 + 2.0 ** -14
         bound_mul = src.maxoff * guard                             # U[j, :] <= deg_j * max(S_off)
