@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 3
+#define SRK_ABI_VERSION 4
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -187,6 +187,10 @@ int srk_i8_supported(void);
  *                                       memory of the GPU that owns row j (a peer-mapped pointer over
  *                                       NVLink), so no rank computes both (q,p) and (p,q).
  *                     The diagonal is the element with j == r + diag_offset.
+ *                     rowmax_hi (optional, caller-zeroed, one uint32 per output row): receives with
+ *                     atomicMax a key of the largest off-diagonal value of every row of the result,
+ *                     key = high word of the double + 1, so that (double)(key << 32) bounds the row
+ *                     within 2^-20: the input of srk_slice_rows_key_f64, which then needs one pass.
  * mode SRK_X2_COUNTS: out_counts[j, r] = min(D[j,r], 65535) as uint16 (ns must be 1, V = a 0/1
  *                     matrix as a single plane): `np.dot((G>0).astype(int), (G>0).T.astype(int))`
  *                     of SimRank.py:315, also the A A^T term above.                              */
@@ -210,6 +214,7 @@ typedef struct srk_x2_args {
   int add_counts, use_evidence;
   double* out_f64; int64_t ld_out; int64_t diag_offset;              /* FINAL */
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;        /* FINAL, TRANSPOSED: see above */
+  uint32_t* rowmax_hi;                                               /* FINAL, DIRECT/SYMMETRIC: see below */
   srk_epilogue epi;                                                  /* FINAL */
   uint16_t* out_counts; int64_t ld_out_counts;                       /* COUNTS */
 } srk_x2_args;
@@ -223,6 +228,12 @@ int srk_x2_half(const srk_x2_args* args, void* stream);
  * step of m_r / (256^NS - 1).  Negative and NaN entries are stored as 0.                      */
 int srk_slice_rows_max_f64(const double* V, int64_t ldv, int64_t R, int64_t K,
                            int64_t zero_diag_offset, int ns,
+                           uint8_t* planes, int64_t ldp, int64_t plane_stride,
+                           double* bound_out, void* stream);
+/* The same planes in ONE pass when the row maxima are already known as keys (rowmax_hi of
+ * srk_x2_args): m_r = (double)(key_r << 32) >= max_k V[r,k].  bound_out as above.            */
+int srk_slice_rows_key_f64(const double* V, int64_t ldv, int64_t R, int64_t K,
+                           int64_t zero_diag_offset, int ns, const uint32_t* rowmax_hi,
                            uint8_t* planes, int64_t ldp, int64_t plane_stride,
                            double* bound_out, void* stream);
 

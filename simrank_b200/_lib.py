@@ -11,7 +11,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 SRK_I8_MID, SRK_I8_FINAL, SRK_I8_COUNTS = 0, 1, 2
 SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
@@ -71,6 +71,7 @@ class X2Args(C.Structure):
                 ("add_counts", C.c_int), ("use_evidence", C.c_int),
                 ("out_f64", C.c_void_p), ("ld_out", C.c_int64), ("diag_offset", C.c_int64),
                 ("mirror_out", C.c_void_p), ("ld_mirror", C.c_int64), ("mirror_col0", C.c_int64),
+                ("rowmax_hi", C.c_void_p),
                 ("epi", Epilogue),
                 ("out_counts", C.c_void_p), ("ld_out_counts", C.c_int64)]
 
@@ -89,6 +90,7 @@ SYMBOLS = {
     "srk_i8_half": (_INT, [C.POINTER(I8Args), _P]),
     "srk_x2_half": (_INT, [C.POINTER(X2Args), _P]),
     "srk_slice_rows_max_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _INT, _P, _I64, _I64, _P, _P]),
+    "srk_slice_rows_key_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _INT, _P, _P, _I64, _I64, _P, _P]),
     "srk_i8_supported": (_INT, []),
     "srk_topk_rows": (_INT, [_P, _I64, _I64, _I64, _INT, _P, _P, _P]),
     "srk_set_identity_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _P]),

@@ -300,6 +300,45 @@ slice_rows_max_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int6
   }
 }
 
+// One-pass variant: the row maxima come as keys from the FINAL epilogue (srk_x2_args.rowmax_hi).
+template <int NS>
+__global__ void slice_rows_key_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int64_t K,
+                                      int64_t zero_diag_offset, const uint32_t* __restrict__ key,
+                                      uint8_t* __restrict__ planes, int64_t ldp, int64_t plane_stride,
+                                      double* __restrict__ bound_out) {
+  const int64_t chunks = (ldp + 15) / 16;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * chunks) return;
+  const int64_t r = t / chunks, k0 = (t % chunks) * 16;
+  const double qmax = (double)((1ull << (8 * NS)) - 1ull);
+  const uint32_t kr = key[r];
+  const double m = kr > 1u ? __longlong_as_double((long long)kr << 32) : 0.0;
+  const double scale = m > 0.0 ? qmax / m : 0.0;
+  if (k0 == 0 && bound_out) bound_out[r] = m > 0.0 ? m * ((qmax + 1.0) / qmax) : 0.0;
+  const double* row = V + r * ldv;
+  double v[16];
+  load16(row, k0, K, (reinterpret_cast<uintptr_t>(row) & 15) == 0, v);
+  const int64_t kd = zero_diag_offset >= 0 ? r + zero_diag_offset : -1;
+  uint32_t w[NS][4];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) w[s][x] = 0u;
+#pragma unroll
+  for (int x = 0; x < 16; ++x) {
+    double q = (k0 + x == kd) ? 0.0 : rint(v[x] * scale);
+    if (!(q > 0.0)) q = 0.0;
+    if (q > qmax) q = qmax;
+    const unsigned long long qi = (unsigned long long)q;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      w[s][x >> 2] |= (uint32_t)((qi >> (8 * (NS - 1 - s))) & 0xffull) << (8 * (x & 3));
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    *reinterpret_cast<uint4*>(planes + s * plane_stride + r * ldp + k0) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+}
+
 // ------------------------------------------------------------------------------------------
 // Row-wise top-k by k rounds of arg-max in the total order (value desc, column asc); NaN last.
 constexpr int TOPK_THREADS = 256;
@@ -486,6 +525,27 @@ extern "C" int srk_slice_rows_max_f64(const double* V, int64_t ldv, int64_t R, i
     case 2: slice_rows_max_kernel<2><<<blocks, SLICE_THREADS, 0, st>>>(V, ldv, R, K, zero_diag_offset, planes, ldp, plane_stride, bound_out); break;
     case 3: slice_rows_max_kernel<3><<<blocks, SLICE_THREADS, 0, st>>>(V, ldv, R, K, zero_diag_offset, planes, ldp, plane_stride, bound_out); break;
     case 4: slice_rows_max_kernel<4><<<blocks, SLICE_THREADS, 0, st>>>(V, ldv, R, K, zero_diag_offset, planes, ldp, plane_stride, bound_out); break;
+    default: return srk::fail(SRK_ERR_INVALID, "invalid argument: %s", "ns must be 1..4");
+  }
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" int srk_slice_rows_key_f64(const double* V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
+                                      int ns, const uint32_t* rowmax_hi, uint8_t* planes, int64_t ldp,
+                                      int64_t plane_stride, double* bound_out, void* stream) {
+  SRK_REQUIRE(V && planes && rowmax_hi, "null pointer");
+  SRK_REQUIRE(ldp % 16 == 0 && ldp >= K && ldv >= K, "ldp must be a multiple of 16 and >= K");
+  SRK_REQUIRE(((uintptr_t)planes % 16) == 0 && plane_stride % 16 == 0, "planes must be 16-byte aligned");
+  if (R == 0 || K == 0) return SRK_OK;
+  const int64_t threads = R * ((ldp + 15) / 16);
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ns) {
+    case 1: slice_rows_key_kernel<1><<<blocks, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, rowmax_hi, planes, ldp, plane_stride, bound_out); break;
+    case 2: slice_rows_key_kernel<2><<<blocks, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, rowmax_hi, planes, ldp, plane_stride, bound_out); break;
+    case 3: slice_rows_key_kernel<3><<<blocks, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, rowmax_hi, planes, ldp, plane_stride, bound_out); break;
+    case 4: slice_rows_key_kernel<4><<<blocks, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, rowmax_hi, planes, ldp, plane_stride, bound_out); break;
     default: return srk::fail(SRK_ERR_INVALID, "invalid argument: %s", "ns must be 1..4");
   }
   SRK_CUDA_OK(cudaGetLastError());

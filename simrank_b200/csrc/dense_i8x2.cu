@@ -229,6 +229,45 @@ __device__ __forceinline__ double final_value(unsigned long long D, uint32_t cnt
   return ((double)(long long)T * cf) * gj;
 }
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+// High word of a non-negative double, rounded up: a 32-bit key that is monotone in the value
+// (keys order like the doubles) and whose "value" (key << 32) is an upper bound within 2^-20.
+__device__ __forceinline__ uint32_t hi_key(double x) { return (uint32_t)__double2hiint(x) + 1u; }
+// Column maxima of a 32 x 16 block held as 16 keys per lane: after the call lane l holds the
+// maximum over all 32 lanes of column col_of_lane(l) = bits 4..1 of l (both lanes of a pair hold
+// the same column).  Reduce-scatter: 16 shuffles instead of 80.
+__device__ __forceinline__ uint32_t column_max16(const uint32_t (&k)[16], int lane) {
+  uint32_t a[8], b[4], c[2], d;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t mine = h16 ? k[i + 8] : k[i], other = h16 ? k[i] : k[i + 8];
+    a[i] = max(mine, __shfl_xor_sync(0xffffffffu, other, 16));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t mine = h8 ? a[i + 4] : a[i], other = h8 ? a[i] : a[i + 4];
+    b[i] = max(mine, __shfl_xor_sync(0xffffffffu, other, 8));
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t mine = h4 ? b[i + 2] : b[i], other = h4 ? b[i] : b[i + 2];
+    c[i] = max(mine, __shfl_xor_sync(0xffffffffu, other, 4));
+  }
+  {
+    const uint32_t mine = h2 ? c[1] : c[0], other = h2 ? c[0] : c[1];
+    d = max(mine, __shfl_xor_sync(0xffffffffu, other, 2));
+  }
+  return max(d, __shfl_xor_sync(0xffffffffu, d, 1));
+}
+__device__ __forceinline__ int column_of_lane(int lane) { return (lane >> 1) & 15; }   // h16*8 + h8*4 + h4*2 + h2
+// bit pattern of |x|, taken with an integer AND (asm: the compiler would turn the C++ form back
+// into a DADD with an |x| modifier, and FP64-pipe instructions are what this epilogue rations)
+__device__ __forceinline__ unsigned long long abs_bits(double x) {
+  unsigned lo, hi;
+  asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "d"(x));
+  asm volatile("and.b32 %0, %0, 0x7fffffff;" : "+r"(hi));
+  return ((unsigned long long)hi << 32) | lo;
+}
 
 struct Params {
   int layout;
@@ -242,6 +281,7 @@ struct Params {
   const uint16_t* counts; int64_t ld_counts; int add_counts, use_evidence;
   double* out_f64; int64_t ld_out; int64_t diag_offset;
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;
+  uint32_t* rowmax_hi;
   EpilogueDev epi;
   double* maxdiff; double* maxoff;
   // COUNTS
@@ -434,6 +474,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         epi_bar_sync();
       }
+      unsigned long long rmax = 0ull;                     // FINAL, row-major layouts: max of row j inside this tile
       double rowf = 0.0;                                  // FINAL: g_a[j]
       int fj = kNoBound;                                  // MID: exponent of the power-of-two bound of row j
       if (jvalid) {
@@ -525,8 +566,8 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const uint32_t cnt = (cw[x >> 1] >> (16 * (x & 1))) & 0xffffu;
             double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
             if (p.use_evidence) val *= evidence_factor(cnt);
-            omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
-            dmax = umax64(dmax, (unsigned long long)__double_as_longlong(val - so[x]) & 0x7fffffffffffffffull);
+            rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
+            dmax = umax64(dmax, abs_bits(val - so[x]));
             v[x] = val;
           }
           double2* op = reinterpret_cast<double2*>(p.out_f64 + j * p.ld_out + rc);
@@ -536,6 +577,13 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             double* mp = p.out_f64 + rc * p.ld_out + j;   // mirror: 32 lanes write 256 contiguous bytes per x
 #pragma unroll
             for (int x = 0; x < 16; ++x) mp[x * p.ld_out] = v[x];
+            if (p.rowmax_hi) {                            // the mirrored values belong to rows rc + x
+              uint32_t key[16];
+#pragma unroll
+              for (int x = 0; x < 16; ++x) key[x] = hi_key(v[x]);
+              const uint32_t cm = column_max16(key, lane);
+              if (!(lane & 1) && cm > 1u) atomicMax(p.rowmax_hi + rc + column_of_lane(lane), cm);
+            }
           }
           continue;
         }
@@ -560,7 +608,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             double val = final_value(combine<NS>(a, x), p.add_counts ? cnt[x] : 0u, shv[c0 + x], cf[c0 + x], rowf);
             if (p.use_evidence) val *= evidence_factor(cnt[x]);
             omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
-            dmax = umax64(dmax, (unsigned long long)__double_as_longlong(val - so[x]) & 0x7fffffffffffffffull);
+            dmax = umax64(dmax, abs_bits(val - so[x]));
             op[x * p.ld_out] = val;
             v[x] = val;
           }
@@ -590,7 +638,11 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             val = (1.0 - p.epi.lambda) * val +
                   p.epi.lambda * (trans ? p.epi.prior[r * p.epi.ld_prior + j] : p.epi.prior[j * p.epi.ld_prior + r]);
           if (r == jd) val = 1.0;
-          else if (val > 0.0) omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
+          else if (val > 0.0) {
+            if (trans) omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
+            else rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
+            if (sym && p.rowmax_hi) atomicMax(p.rowmax_hi + r, hi_key(val));
+          }
           if (have_old) {
             const double so = trans ? p.epi.s_old[r * p.epi.ld_s_old + j] : p.epi.s_old[j * p.epi.ld_s_old + r];
             const double d = fabs(val - so);
@@ -600,6 +652,10 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (sym && jd < r) p.out_f64[r * p.ld_out + j] = val;
           if (trans && p.mirror_out && r != jd) p.mirror_out[j * p.ld_mirror + p.mirror_col0 + r] = val;
         }
+      }
+      if (MODE == SRK_X2_FINAL && rmax) {
+        omax = umax64(omax, rmax);
+        if (p.rowmax_hi) atomicMax(p.rowmax_hi + j, (uint32_t)(rmax >> 32) + 1u);
       }
       tw.advance(num_clusters);
     }
@@ -696,6 +752,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.counts = a.counts; p.ld_counts = a.ld_counts; p.add_counts = a.add_counts; p.use_evidence = a.use_evidence;
   p.out_f64 = a.out_f64; p.ld_out = a.ld_out; p.diag_offset = a.diag_offset;
   p.mirror_out = a.mirror_out; p.ld_mirror = a.ld_mirror; p.mirror_col0 = a.mirror_col0;
+  p.rowmax_hi = a.rowmax_hi;
   p.epi = to_dev(a.epi);
   p.maxdiff = a.epi.maxdiff; p.maxoff = a.epi.maxoff;
   p.out_counts = a.out_counts; p.ld_out_counts = a.ld_out_counts;
@@ -782,6 +839,7 @@ extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
     } else {
       SRK_REQUIRE(a->ld_out >= a->R, "ld_out smaller than R");
     }
+    SRK_REQUIRE(!a->rowmax_hi || a->layout != SRK_X2_TRANSPOSED, "rowmax_hi needs a row-major layout");
     SRK_REQUIRE(!a->mirror_out || (a->layout == SRK_X2_TRANSPOSED && a->ld_mirror >= a->mirror_col0 + a->R),
                 "mirror_out needs the transposed layout and ld_mirror >= mirror_col0 + R");
     if (a->layout == SRK_X2_SYMMETRIC)

@@ -234,6 +234,8 @@ class _Half:
         self.planes = None                                                 # allocated on first use as a source
         self.planes_U = torch.empty((self.ns_alloc, self.n_out, self.ldu), dtype=torch.uint8, device=dev)
         self.bound_vec = torch.zeros(max(self.n_out, 1), dtype=torch.float64, device=dev)
+        # keys of the row maxima of the current S_off, collected by the FINAL epilogue (S = I: all zero)
+        self.rowmax_hi = torch.zeros(max(self.n_out, 1), dtype=torch.int32, device=dev)
         self.evidence_from_pattern = bool(evidence_from_pattern)
         self.counts = op.pattern_counts()                                  # uint16 A A^T, [n_out, ldc]
         self.version = 0                                                   # bumped by every update of S
@@ -265,17 +267,18 @@ class _Half:
         return rc
 
     def _planes_for(self, ns: int) -> torch.Tensor:
-        """Planes of the off-diagonal part of the CURRENT S with the exact row maxima as bounds
-        (srk_slice_rows_max_f64); cached per (version of S, ns)."""
+        """Planes of the off-diagonal part of the CURRENT S, bounded per row by the maxima the FINAL
+        epilogue collected while writing it (srk_slice_rows_key_f64: one pass); cached per
+        (version of S, ns)."""
         if self.planes is None or self.planes.shape[0] < ns:
             self.planes = torch.empty((max(ns, self.ns_alloc), self.n_out, self.ldp), dtype=torch.uint8,
                                       device=self.S.device)
             self._sliced = (-1, 0)
         if self._sliced != (self.version, ns):
             lib = _lib.load()
-            _lib.check(self._timed("slice_rows_max", lambda: lib.srk_slice_rows_max_f64(
-                _ptr(self.S), self.ld, self.n_out, self.n_out, 0, ns, _ptr(self.planes), self.ldp,
-                self.planes.stride(0), _ptr(self.bound_vec), _stream())), "srk_slice_rows_max_f64")
+            _lib.check(self._timed("slice_rows_key", lambda: lib.srk_slice_rows_key_f64(
+                _ptr(self.S), self.ld, self.n_out, self.n_out, 0, ns, _ptr(self.rowmax_hi), _ptr(self.planes),
+                self.ldp, self.planes.stride(0), _ptr(self.bound_vec), _stream())), "srk_slice_rows_key_f64")
             self._sliced = (self.version, ns)
         return self.planes
 
@@ -329,6 +332,8 @@ class _Half:
         b.counts, b.ld_counts, b.add_counts = self.counts.data_ptr(), self.counts.stride(0), 1
         b.use_evidence = 1 if self.evidence_from_pattern else 0
         b.out_f64, b.ld_out, b.diag_offset = self.S.data_ptr(), self.ld, 0
+        self.rowmax_hi.zero_()                                     # after the slice above read the old keys
+        b.rowmax_hi = self.rowmax_hi.data_ptr()
         b.epi = self._epilogue()
         _lib.check(self._timed("x2_half_final", lambda: lib.srk_x2_half(C.byref(b), _stream())),
                    "srk_x2_half(FINAL)")

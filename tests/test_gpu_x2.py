@@ -169,6 +169,10 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False)
         pr = torch.from_numpy(prior).to(dev)
         keep.append(pr)
         e.prior, e.ld_prior, e.lambda_ = pr.data_ptr(), cols, 0.25
+    rk = None
+    if not trans:                                                       # keys of the row maxima
+        rk = torch.zeros(rows, dtype=torch.int32, device=dev)
+        a.rowmax_hi = rk.data_ptr()
     mir = None
     if mirror:                                                          # the block as its owner stores it
         ldm = engine._round_up(R + 6, 2)
@@ -213,6 +217,10 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False)
     dmask = (jj == rr + diag_offset).T if trans else (jj == rr + diag_offset)
     off[dmask] = 0.0
     assert mo == off.max()
+    if rk is not None:
+        m = off.max(axis=1)
+        want_key = np.where(m > 0, (m.view(np.int64) >> 32) + 1, 0)
+        np.testing.assert_array_equal(rk.cpu().numpy().astype(np.int64), want_key)
     assert not S[:, cols:].cpu().numpy().any()                          # nothing written past the matrix
 
 
@@ -297,6 +305,36 @@ def test_x2_many_tiles_per_pair(dev):
     shared-memory ring wrap-around and the symmetric tile walk across several bands."""
     _final_case(np.random.default_rng(77), 2, 5000, 5000, 384, _lib.SRK_X2_SYMMETRIC, "counts", dev)
     _final_case(np.random.default_rng(78), 3, 4100, 3000, 256, _lib.SRK_X2_DIRECT, "none", dev)
+
+
+@pytest.mark.parametrize("ns", [1, 2, 3, 4])
+def test_slice_rows_key(dev, ns):
+    """One-pass slicer: bounds come as keys (high word + 1) of the row maxima."""
+    rng = np.random.default_rng(40 + ns)
+    R, K = 37, 530
+    V = rng.random((R, K)) * (rng.random(R) * 3 + 0.01)[:, None]
+    V[4] = 0.0
+    off = 1
+    Vz = V.copy()
+    Vz[np.arange(R), np.arange(R) + off] = 0.0
+    m = Vz.max(axis=1)
+    key = np.where(m > 0, (m.view(np.int64) >> 32) + 1, 0).astype(np.int32)
+    mk = (key.astype(np.int64) << 32).view(np.float64)                  # the bound the kernel derives
+    assert np.all(mk >= m) and np.all(mk <= m * (1 + 2.0 ** -19) + 1e-300)
+    ldp = engine._round_up(K, 128)
+    planes = torch.full((ns, R, ldp), 3, dtype=torch.uint8, device=dev)
+    bound = torch.zeros(R, dtype=torch.float64, device=dev)
+    Vd, kd = torch.from_numpy(V).to(dev), torch.from_numpy(key).to(dev)
+    _lib.check(_lib.load().srk_slice_rows_key_f64(engine._ptr(Vd), K, R, K, off, ns, engine._ptr(kd), engine._ptr(planes),
+                                                  ldp, R * ldp, engine._ptr(bound), engine._stream()))
+    torch.cuda.synchronize()
+    qmax = 256.0 ** ns - 1
+    np.testing.assert_allclose(bound.cpu().numpy(), mk * ((qmax + 1) / qmax), rtol=1e-15)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = np.where(mk[:, None] > 0, np.rint(Vz * (qmax / np.where(mk > 0, mk, 1.0))[:, None]), 0.0).astype(np.int64)
+    got = _join(planes.cpu().numpy(), ns)
+    assert np.abs(got[:, :K] - want).max() <= 1
+    assert not got[:, K:].any() and not got[4].any()
 
 
 @pytest.mark.parametrize("ns", [1, 2, 3, 4])
