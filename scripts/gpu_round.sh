@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-echo "== x2 unit tests"; timeout -k 10 600 python -m pytest tests/test_gpu_x2.py -x -q > gpurun_out/x2_tests.log 2>&1
+echo "== x2 unit tests"; timeout -k 5 150 python -m pytest tests/test_gpu_x2.py -x -q > gpurun_out/x2_tests.log 2>&1
 rc=$?; tail -15 gpurun_out/x2_tests.log; echo "x2 tests rc=$rc"
 if [ $rc -ne 0 ]; then exit $rc; fi
 echo "== full gpu suite"; timeout -k 10 1500 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1

@@ -5,7 +5,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-echo "== x2 unit tests (quick)"; timeout -k 10 300 python -m pytest tests/test_gpu_x2.py -x -q > gpurun_out/x2_tests.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/x2_tests.log
+echo "== x2 unit tests (quick)"; timeout -k 5 150 python -m pytest tests/test_gpu_x2.py -x -q > gpurun_out/x2_tests.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/x2_tests.log
 echo "== dist test"; timeout -k 10 900 python -m pytest tests/test_gpu_dist.py -x -q > gpurun_out/dist_tests_n$N.log 2>&1
 rc=$?; echo "rc=$rc"; tail -30 gpurun_out/dist_tests_n$N.log
 if [ $rc -ne 0 ]; then

@@ -497,9 +497,10 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (lane == 0) mbar_arrive_cluster(&tmem_empty[b], 0);
         }
         const int64_t rc = r0 + c0;                       // first V row of this chunk
-        if (!jvalid || rc >= p.R) continue;
+        if (rc >= p.R) continue;                          // warp-uniform
 
         if (MODE == SRK_X2_COUNTS) {
+          if (!jvalid) continue;
           uint32_t w[8];
 #pragma unroll
           for (int x = 0; x < 16; x += 2) {
@@ -520,6 +521,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
 
         if (MODE == SRK_X2_MID) {
+          if (!jvalid) continue;
           uint32_t w[NS][4];
 #pragma unroll
           for (int s = 0; s < NS; ++s)
@@ -541,6 +543,11 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
 
         // ---------------------------------------------------------------- FINAL
+        // keys of the values this lane mirrors into rows rc + x (symmetric layout); their column
+        // maxima are taken by ALL lanes of the warp after the possibly divergent paths below
+        uint32_t key[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) key[x] = 0u;
         const int64_t jd = j - p.diag_offset;             // V row that sits on the diagonal with j
         // Chunks whose 16 elements are all in range, off the diagonal and (symmetric layout) above it
         // take the vectorised paths; a warp diverges only where its rows meet the diagonal or an
@@ -548,7 +555,9 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // keeps their operand panels shared in L2).
         const bool fast = fast_ok && rc + 16 <= p.R && (jd < rc || (!sym && jd > rc + 15));
         double v[16];
-        if (fast && !trans) {
+        if (!jvalid) {
+          // rows past the end of A8: nothing to store, but stay for the warp-wide reduction
+        } else if (fast && !trans) {
           // 128-bit loads/stores along the row, no predicates
           uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           if (p.counts) {
@@ -576,18 +585,9 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (sym) {
             double* mp = p.out_f64 + rc * p.ld_out + j;   // mirror: 32 lanes write 256 contiguous bytes per x
 #pragma unroll
-            for (int x = 0; x < 16; ++x) mp[x * p.ld_out] = v[x];
-            if (p.rowmax_hi) {                            // the mirrored values belong to rows rc + x
-              uint32_t key[16];
-#pragma unroll
-              for (int x = 0; x < 16; ++x) key[x] = hi_key(v[x]);
-              const uint32_t cm = column_max16(key, lane);
-              if (!(lane & 1) && cm > 1u) atomicMax(p.rowmax_hi + rc + column_of_lane(lane), cm);
-            }
+            for (int x = 0; x < 16; ++x) { mp[x * p.ld_out] = v[x]; key[x] = hi_key(v[x]); }
           }
-          continue;
-        }
-        if (fast && trans) {
+        } else if (fast && trans) {
           // element (row rc + x, column j): every access is coalesced across the lanes
           uint32_t cnt[16];
           double so[16];
@@ -617,40 +617,43 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int x = 0; x < 8; ++x) mp[x] = make_double2(v[2 * x], v[2 * x + 1]);
           }
-          continue;
-        }
-
-        // ---- general path: tiles that touch the diagonal or an edge, priors, uint8 evidence
-        if (sym && jd > rc + 15) continue;                // strictly below the diagonal: mirrored from above
+        } else if (!(sym && jd > rc + 15)) {              // (strictly below the diagonal: mirrored from above)
+          // ---- general path: chunks that touch the diagonal or an edge, priors, uint8 evidence
 #pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          const int64_t r = rc + x;
-          const bool live = r < p.R && !(sym && jd > r);
-          if (!live) continue;
-          const int64_t idx_o = trans ? r * p.ld_out + j : j * p.ld_out + r;
-          uint32_t cnt = 0u;
-          if (p.counts) cnt = trans ? p.counts[r * p.ld_counts + j] : p.counts[j * p.ld_counts + r];
-          double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
-          if (p.use_evidence) val *= evidence_factor(cnt);
-          else if (p.epi.evidence)
-            val *= evidence_factor(trans ? p.epi.evidence[r * p.epi.ld_evidence + j] : p.epi.evidence[j * p.epi.ld_evidence + r]);
-          if (p.epi.prior)
-            val = (1.0 - p.epi.lambda) * val +
-                  p.epi.lambda * (trans ? p.epi.prior[r * p.epi.ld_prior + j] : p.epi.prior[j * p.epi.ld_prior + r]);
-          if (r == jd) val = 1.0;
-          else if (val > 0.0) {
-            if (trans) omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
-            else rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
-            if (sym && p.rowmax_hi) atomicMax(p.rowmax_hi + r, hi_key(val));
+          for (int x = 0; x < 16; ++x) {
+            const int64_t r = rc + x;
+            const bool live = r < p.R && !(sym && jd > r);
+            if (!live) continue;
+            const int64_t idx_o = trans ? r * p.ld_out + j : j * p.ld_out + r;
+            uint32_t cnt = 0u;
+            if (p.counts) cnt = trans ? p.counts[r * p.ld_counts + j] : p.counts[j * p.ld_counts + r];
+            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
+            if (p.use_evidence) val *= evidence_factor(cnt);
+            else if (p.epi.evidence)
+              val *= evidence_factor(trans ? p.epi.evidence[r * p.epi.ld_evidence + j] : p.epi.evidence[j * p.epi.ld_evidence + r]);
+            if (p.epi.prior)
+              val = (1.0 - p.epi.lambda) * val +
+                    p.epi.lambda * (trans ? p.epi.prior[r * p.epi.ld_prior + j] : p.epi.prior[j * p.epi.ld_prior + r]);
+            if (r == jd) val = 1.0;
+            else if (val > 0.0) {
+              if (trans) omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
+              else rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
+              if (sym) key[x] = hi_key(val);              // r > jd here: this value is mirrored to row r
+            }
+            if (have_old) {
+              const double so = trans ? p.epi.s_old[r * p.epi.ld_s_old + j] : p.epi.s_old[j * p.epi.ld_s_old + r];
+              const double d = fabs(val - so);
+              if (d > 0.0) dmax = umax64(dmax, (unsigned long long)__double_as_longlong(d));   // NaN compares false
+            }
+            p.out_f64[idx_o] = val;
+            if (sym && jd < r) p.out_f64[r * p.ld_out + j] = val;
+            if (trans && p.mirror_out && r != jd) p.mirror_out[j * p.ld_mirror + p.mirror_col0 + r] = val;
           }
-          if (have_old) {
-            const double so = trans ? p.epi.s_old[r * p.epi.ld_s_old + j] : p.epi.s_old[j * p.epi.ld_s_old + r];
-            const double d = fabs(val - so);
-            if (d > 0.0) dmax = umax64(dmax, (unsigned long long)__double_as_longlong(d));   // NaN compares false
-          }
-          p.out_f64[idx_o] = val;
-          if (sym && jd < r) p.out_f64[r * p.ld_out + j] = val;
-          if (trans && p.mirror_out && r != jd) p.mirror_out[j * p.ld_mirror + p.mirror_col0 + r] = val;
+        }
+        if (sym && p.rowmax_hi) {                         // warp-uniform
+          __syncwarp();
+          const uint32_t cm = column_max16(key, lane);
+          if (!(lane & 1) && cm > 1u) atomicMax(p.rowmax_hi + rc + column_of_lane(lane), cm);
         }
       }
       if (MODE == SRK_X2_FINAL && rmax) {
