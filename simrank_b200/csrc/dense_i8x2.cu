@@ -27,6 +27,7 @@
 //   warp 2    TMEM allocator (512 columns = 2 accumulator buffers)
 //   warps 4-7 epilogue: tcgen05.ld -> exact recombination -> fused epilogue (MID / FINAL / COUNTS)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -289,6 +290,7 @@ struct Params {
   // schedule
   int tiles_j, tiles_r, group_j, total_tiles;
   int kblock;
+  int debug;                   // SRK_X2_DEBUG (profiling experiments only): 1 no S_old, 2 no mirror, 4 no direct store
 };
 
 // Walks the pair tiles in the order: bands of `group_j` row blocks; inside a band the column
@@ -481,6 +483,20 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (MODE == SRK_X2_MID) fj = pow2_exponent<NS>(row_bound(p.out_rowbound, j));
         if (MODE == SRK_X2_FINAL) rowf = p.g_a[j];
       }
+      if (MODE == SRK_X2_FINAL && !trans && jvalid && have_old && !(sym && j > r0 + RT - 1)) {
+        // The accumulator of this tile is still being computed: pull the rows of S_old and of the
+        // counts that its epilogue will read into L2 now, so that the eight dependent
+        // load -> compute -> store rounds below see L2 latency instead of DRAM latency.  (An
+        // epilogue that outlasts a mainloop stalls the MMA issuer, the CTA pairs drift apart in k
+        // and stop sharing operand panels in L2 -- measured as 2x the DRAM traffic of MID.)
+        const int64_t cols = min((int64_t)RT, p.R - r0);
+        const char* sp = reinterpret_cast<const char*>(p.epi.s_old + j * p.epi.ld_s_old + r0);
+        for (int64_t o = 0; o < cols * 8; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + o));
+        if (p.counts) {
+          const char* cp = reinterpret_cast<const char*>(p.counts + j * p.ld_counts + r0);
+          for (int64_t o = 0; o < cols * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o));
+        }
+      }
       mbar_wait(&tmem_full[b], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t acc = lane_base + (uint32_t)(b * kAccStride);
@@ -568,21 +584,25 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
           double so[16];
           const double2* sp = reinterpret_cast<const double2*>(p.epi.s_old + j * p.epi.ld_s_old + rc);
+          if (!(p.debug & 1)) {
 #pragma unroll
-          for (int x = 0; x < 8; ++x) { const double2 d2 = sp[x]; so[2 * x] = d2.x; so[2 * x + 1] = d2.y; }
+            for (int x = 0; x < 8; ++x) { const double2 d2 = sp[x]; so[2 * x] = d2.x; so[2 * x + 1] = d2.y; }
+          }
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
             const uint32_t cnt = (cw[x >> 1] >> (16 * (x & 1))) & 0xffffu;
             double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
             if (p.use_evidence) val *= evidence_factor(cnt);
             rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
-            dmax = umax64(dmax, abs_bits(val - so[x]));
+            if (!(p.debug & 1)) dmax = umax64(dmax, abs_bits(val - so[x]));
             v[x] = val;
           }
           double2* op = reinterpret_cast<double2*>(p.out_f64 + j * p.ld_out + rc);
+          if (!(p.debug & 4)) {
 #pragma unroll
-          for (int x = 0; x < 8; ++x) op[x] = make_double2(v[2 * x], v[2 * x + 1]);
-          if (sym) {
+            for (int x = 0; x < 8; ++x) op[x] = make_double2(v[2 * x], v[2 * x + 1]);
+          }
+          if (sym && !(p.debug & 2)) {
             double* mp = p.out_f64 + rc * p.ld_out + j;   // mirror: 32 lanes write 256 contiguous bytes per x
 #pragma unroll
             for (int x = 0; x < 16; ++x) { mp[x * p.ld_out] = v[x]; key[x] = hi_key(v[x]); }
@@ -764,6 +784,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.group_j = 8;
   p.total_tiles = count_tiles(p.tiles_j, p.tiles_r, C::RT, p.layout == SRK_X2_SYMMETRIC);
   p.kblock = (int)a.in_kblock;
+  { const char* e = getenv("SRK_X2_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
   auto kern = i8x2_kernel<NS, MODE>;
   SRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
