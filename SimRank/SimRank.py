@@ -33,14 +33,27 @@ class _Base(object):
     device : CUDA device (default: current)
     slices : uint8 planes per matrix in i8 mode: 2, 3, 4 or None/'auto' = the fewest planes whose
              guaranteed error bound stays below 5e-7 (simrank_b200.engine.choose_slices)
+    gather : under torch.distributed (one process per GPU, S row-sharded): 'all' returns the whole
+             matrix on every rank, 'local' returns each rank's own row block (all columns)
     label_order : bipartite only -- 'sorted' labels the result rows with the labels they belong
              to; 'reference' reproduces the set-ordered labels of SimRank.py:303
     """
 
-    def _engine_options(self, mode=None, device=None, slices=None, label_order="sorted"):
+    def _engine_options(self, mode=None, device=None, slices=None, label_order="sorted", gather="all"):
         self._mode, self._device, self._slices, self._label_order = mode, device, slices, label_order
+        self._gather = gather
         self.fit_info_ = None
         self._result = None
+
+    def _tick(self, stage=None):
+        """Wall-clock stages of the last fit (graph build, device setup, iterations, result
+        transfer), kept in ``fit_timings_`` for the bench and for users who ask where time went."""
+        now = time.perf_counter()
+        if stage is None:
+            self.fit_timings_ = {}
+        else:
+            self.fit_timings_[stage] = self.fit_timings_.get(stage, 0.0) + now - self._t_last
+        self._t_last = now
 
     def _converged(self, s1, s2, eps):
         """True when no entry differs by more than ``eps`` (SimRank.py:54-77).  The engine fuses
@@ -96,11 +109,17 @@ class SimRank(_Base):
 
     def fit(self, data, C=0.8, weighted=False, from_node_column='from', to_node_column='to',
             weight_column='weight', iterations=100, eps=1e-4, verbose=True):
+        self._tick()
         self._create_graph(data, weighted, from_node_column, to_node_column, weight_column)
+        self._tick("graph")
         solver = _drv.directed_solver(self._graph_op, C, mode=self._mode, device=self._device, slices=self._slices)
+        self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
-        self._result = _drv.Result([solver.S], [self._node_order])
-        return self._result.frame(0)
+        self._tick("iterate")
+        self._result = _drv.collect(solver, [self._node_order], self._gather)
+        out = self._result.frame(0)
+        self._tick("result")
+        return out
 
 
 class SimRankPP(SimRank):
@@ -140,13 +159,19 @@ class SimRankPP(SimRank):
 
     def fit(self, data, C=0.8, weighted=False, from_node_column='from', to_node_column='to',
             weight_column='weight', iterations=100, eps=1e-4, verbose=True):
+        self._tick()
         self._create_graph(data, weighted, from_node_column, to_node_column, weight_column)
         self._prepare_pp(verbose)
+        self._tick("graph")
         solver = _drv.directed_solver(self.Weight, C, evidence=self.Evidence, mode=self._mode,
                                       device=self._device, slices=self._slices)
+        self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
-        self._result = _drv.Result([solver.S], [self._node_order])
-        return self._result.frame(0)
+        self._tick("iterate")
+        self._result = _drv.collect(solver, [self._node_order], self._gather)
+        out = self._result.frame(0)
+        self._tick("result")
+        return out
 
 
 class AprioriSimRank(SimRankPP):
@@ -157,13 +182,19 @@ class AprioriSimRank(SimRankPP):
 
     def fit(self, data, AprioriSim, C=0.8, lbd=0.5, weighted=False, from_node_column='from',
             to_node_column='to', weight_column='weight', iterations=100, eps=1e-4, verbose=True):
+        self._tick()
         self._create_graph(data, weighted, from_node_column, to_node_column, weight_column)
         self._prepare_pp(verbose)
+        self._tick("graph")
         solver = _drv.directed_solver(self.Weight, C, evidence=self.Evidence, prior=AprioriSim, lbd=lbd,
                                       mode=self._mode, device=self._device, slices=self._slices)
+        self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
-        self._result = _drv.Result([solver.S], [self._node_order])
-        return self._result.frame(0)
+        self._tick("iterate")
+        self._result = _drv.collect(solver, [self._node_order], self._gather)
+        out = self._result.frame(0)
+        self._tick("result")
+        return out
 
 
 # =========================================================================== bipartite
@@ -210,12 +241,18 @@ class BipartiteSimRank(_BipartiteGraphs, _Base):
 
     def fit(self, data, C1=0.8, C2=0.8, weighted=False, node_group1_column='user',
             node_group2_column='item', weight_column='weight', iterations=100, eps=1e-4, verbose=True):
+        self._tick()
         self._create_graph(data, weighted, node_group1_column, node_group2_column, weight_column)
+        self._tick("graph")
         solver = _drv.bipartite_solver(self._op12, self._op21, C1, C2, mode=self._mode, device=self._device,
                                        slices=self._slices)
+        self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
-        self._result = _drv.Result([solver.S1, solver.S2], list(self._labels()))
-        return self._result.frame(0), self._result.frame(1)
+        self._tick("iterate")
+        self._result = _drv.collect(solver, list(self._labels()), self._gather)
+        out = self._result.frame(0), self._result.frame(1)
+        self._tick("result")
+        return out
 
 
 class BipartiteSimRankPP(_BipartiteGraphs, SimRankPP):
@@ -245,14 +282,20 @@ class BipartiteSimRankPP(_BipartiteGraphs, SimRankPP):
 
     def fit(self, data, C1=0.8, C2=0.8, weighted=False, node_group1_column='user',
             node_group2_column='item', weight_column='weight', iterations=100, eps=1e-4, verbose=True):
+        self._tick()
         self._create_graph(data, weighted, node_group1_column, node_group2_column, weight_column)
         self._prepare_pp(verbose)
+        self._tick("graph")
         solver = _drv.bipartite_solver(self.Weight_N1, self.Weight_N2, C1, C2, evidence1=self.Evidence_N1,
                                        evidence2=self._group2_evidence(), mode=self._mode,
                                        device=self._device, slices=self._slices)
+        self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
-        self._result = _drv.Result([solver.S1, solver.S2], list(self._labels()))
-        return self._result.frame(0), self._result.frame(1)
+        self._tick("iterate")
+        self._result = _drv.collect(solver, list(self._labels()), self._gather)
+        out = self._result.frame(0), self._result.frame(1)
+        self._tick("result")
+        return out
 
 
 class BipartitleAprioriSimRank(BipartiteSimRankPP):
@@ -265,15 +308,21 @@ class BipartitleAprioriSimRank(BipartiteSimRankPP):
     def fit(self, data, AprioriSim1, AprioriSim2, C1=0.8, C2=0.8, lbd1=0.5, lbd2=0.5, weighted=False,
             node_group1_column='user', node_group2_column='item', weight_column='weight',
             iterations=100, eps=1e-4, verbose=True):
+        self._tick()
         self._create_graph(data, weighted, node_group1_column, node_group2_column, weight_column)
         self._prepare_pp(verbose)
+        self._tick("graph")
         solver = _drv.bipartite_solver(self.Weight_N1, self.Weight_N2, C1, C2, evidence1=self.Evidence_N1,
                                        evidence2=self._group2_evidence(), prior1=AprioriSim1, prior2=AprioriSim2,
                                        lbd1=lbd1, lbd2=lbd2, mode=self._mode, device=self._device,
                                        slices=self._slices)
+        self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
-        self._result = _drv.Result([solver.S1, solver.S2], list(self._labels()))
-        return self._result.frame(0), self._result.frame(1)
+        self._tick("iterate")
+        self._result = _drv.collect(solver, list(self._labels()), self._gather)
+        out = self._result.frame(0), self._result.frame(1)
+        self._tick("result")
+        return out
 
 
 # README.md:16 of the reference (and BASELINE.json) spell these "Bipartitle..."

@@ -92,15 +92,17 @@ csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
     double v = tile[cl][lane];
     if (kFinal) {
       v *= epi.coef;
-      if (epi.evidence) v *= evidence_factor(epi.evidence[r * epi.ld_evidence + i]);
-      if (epi.prior) v = (1.0 - epi.lambda) * v + epi.lambda * epi.prior[r * epi.ld_prior + i];
+      // the epilogue streams (evidence, prior, S_old, the result) are touched once: evict-first
+      // loads/stores keep them from pushing the gathered panel of X out of L2
+      if (epi.evidence) v *= evidence_factor(__ldcs(epi.evidence + r * epi.ld_evidence + i));
+      if (epi.prior) v = (1.0 - epi.lambda) * v + epi.lambda * __ldcs(epi.prior + r * epi.ld_prior + i);
       if (r == i) v = 1.0; else if (v > omax) omax = v;
       if (epi.s_old) {
-        const double d = fabs(v - epi.s_old[r * epi.ld_s_old + i]);
+        const double d = fabs(v - __ldcs(epi.s_old + r * epi.ld_s_old + i));
         if (d > dmax) dmax = d;                  // NaN compares false: ignored like SimRank.py:74
       }
     }
-    OUT[r * ldo + i] = v;
+    __stcs(OUT + r * ldo + i, v);
   }
   if (kFinal) {
     dmax = warp_max(dmax);

@@ -163,23 +163,44 @@ def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=N
 
 
 class Result:
-    """Device-resident result of a fit: similarity matrices + their row labels."""
+    """Device-resident result of a fit: similarity matrices + their labels.  ``rows[w]`` is the
+    (first, last+1) range of rows of matrix ``w`` held here: everything on a single GPU or with
+    ``gather="all"``, the local row block of a row-sharded fit with ``gather="local"``."""
 
-    def __init__(self, mats, labels):
+    def __init__(self, mats, labels, rows=None):
         self.mats, self.labels = mats, labels
+        self.rows = rows if rows is not None else [(0, len(lab)) for lab in labels]
+
+    def _row_labels(self, which):
+        lo, hi = self.rows[which]
+        lab = self.labels[which]
+        return lab if (lo, hi) == (0, len(lab)) else lab[lo:hi]
 
     def frame(self, which: int = 0) -> pd.DataFrame:
         """The labelled DataFrame the reference returns (SimRank.py:141, 303)."""
         S = self.mats[which]
         host = torch.empty(S.shape, dtype=S.dtype, pin_memory=S.numel() >= (1 << 20))
         host.copy_(S)
-        lab = self.labels[which]
-        return pd.DataFrame(host.numpy(), index=lab, columns=lab, copy=False)
+        return pd.DataFrame(host.numpy(), index=self._row_labels(which), columns=self.labels[which], copy=False)
 
     def top_k(self, k: int, which: int = 0):
         S = self.mats[which]
         idx, vals = _eng.topk_rows(S, k)
         lab = np.asarray(self.labels[which], dtype=object)
         idx_h = idx.cpu().numpy()
-        return (pd.DataFrame(lab[idx_h], index=self.labels[which]),
-                pd.DataFrame(vals.cpu().numpy(), index=self.labels[which]))
+        rows = self._row_labels(which)
+        return (pd.DataFrame(lab[idx_h], index=rows), pd.DataFrame(vals.cpu().numpy(), index=rows))
+
+
+def collect(solver, labels, gather: str = "all") -> Result:
+    """Result of a finished solver.  A row-sharded solver either all-gathers every matrix onto
+    every rank (``gather="all"``: each rank returns what the reference returns) or keeps the local
+    row blocks (``gather="local"``: rank r returns rows ``plan.start(r):plan.stop(r)`` of each
+    matrix, nothing crosses NVLink or PCIe twice)."""
+    halves = getattr(solver, "halves", None)
+    pair = hasattr(solver, "S1")
+    if halves is None or gather == "all":
+        return Result([solver.S1, solver.S2] if pair else [solver.S], labels)
+    if gather != "local":
+        raise ValueError("gather must be 'all' or 'local'")
+    return Result([h.local_result() for h in halves], labels, [(h.row0, h.row0 + h.rows) for h in halves])

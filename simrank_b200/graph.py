@@ -69,11 +69,11 @@ def _inverse_or_zero(x: np.ndarray) -> np.ndarray:
 def _csr(rows: np.ndarray, cols: np.ndarray, M: int, K: int):
     if rows.size and M * K < (1 << 62):
         key = rows.astype(np.int64) * K + cols.astype(np.int64)
-        order = np.argsort(key, kind="stable")
-        key = key[order]
+        key.sort()                                   # values only: rows and columns are recovered from the key
         if key.size > 1 and np.any(key[1:] == key[:-1]):
             raise ValueError(_DUPLICATE_MSG)
-        rows, cols = rows[order], cols[order]
+        rows = key // K
+        cols = key - rows * K
     indptr = np.zeros(M + 1, dtype=np.int64)
     np.cumsum(np.bincount(rows, minlength=M), out=indptr[1:])
     return indptr, cols.astype(np.int32)

@@ -32,6 +32,16 @@ def main():
     S = obj.fit(df, iterations=50, eps=1e-4, verbose=False)
     assert (obj.fit_info_.applied, obj.fit_info_.converged) == (ko, co), (obj.fit_info_, ko, co)
     worst = max(worst, float(np.abs(S.to_numpy() - So).max()))
+    # gather="local": every rank keeps its own row block (all columns)
+    Sl = M.SimRank(mode="i8", gather="local").fit(df, iterations=50, eps=1e-4, verbose=False)
+    pos = {lab: i for i, lab in enumerate(nodes)}
+    mine = [pos[lab] for lab in Sl.index]
+    assert list(Sl.columns) == nodes and mine == list(range(mine[0], mine[0] + len(mine))) if mine else True
+    if mine:
+        worst = max(worst, float(np.abs(Sl.to_numpy() - So[mine]).max()))
+    tot = torch.tensor([len(mine)], device="cuda")
+    dist.all_reduce(tot)
+    assert int(tot.item()) == len(nodes)
     # SimRank++ (evidence rows are sharded with S)
     df = synth.directed_frame(1500, 30000, 1.0, 22, weights="lognormal")
     nodes, So, _, _ = orc.fit_directed(df, kind="simrank_pp", weighted=True, iterations=4, eps=0.0)
