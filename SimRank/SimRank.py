@@ -35,13 +35,18 @@ class _Base(object):
              guaranteed error bound stays below 5e-7 (simrank_b200.engine.choose_slices)
     gather : under torch.distributed (one process per GPU, S row-sharded): 'all' returns the whole
              matrix on every rank, 'local' returns each rank's own row block (all columns)
+    result : 'frame' (the reference's DataFrames) or 'device' (fit returns the device-resident
+             simrank_b200.drivers.Result; nothing is copied to the host until asked)
     label_order : bipartite only -- 'sorted' labels the result rows with the labels they belong
              to; 'reference' reproduces the set-ordered labels of SimRank.py:303
     """
 
-    def _engine_options(self, mode=None, device=None, slices=None, label_order="sorted", gather="all"):
+    def _engine_options(self, mode=None, device=None, slices=None, label_order="sorted", gather="all",
+                        result="frame"):
         self._mode, self._device, self._slices, self._label_order = mode, device, slices, label_order
-        self._gather = gather
+        if result not in ("frame", "device"):
+            raise ValueError("result must be 'frame' or 'device'")
+        self._gather, self._result_kind = gather, result
         self.fit_info_ = None
         self._result = None
 
@@ -70,6 +75,21 @@ class _Base(object):
             sys.stdout.flush()
         self.fit_info_ = _drv.FitInfo(applied, conv, last, solver.mode)
         return applied, conv
+
+    def _finish(self, solver, labels):
+        """Turn the finished solver into what ``fit`` returns: the reference's DataFrame(s)
+        (SimRank.py:141, 303), or -- ``result="device"`` -- the device-resident Result itself
+        (``.frame(i)``, ``.top_k(k, i)``, ``.mats[i]``), for matrices that must not be copied to the
+        host as a whole (cfg5: S1 is 153 GB)."""
+        self._result = _drv.collect(solver, labels, self._gather)
+        if self._result_kind == "device":
+            out = self._result
+        elif len(labels) == 1:
+            out = self._result.frame(0)
+        else:
+            out = tuple(self._result.frame(i) for i in range(len(labels)))
+        self._tick("result")
+        return out
 
     def top_k(self, k, which=0):
         """Row-wise top-k of the last fitted similarity matrix, computed on the device.
@@ -116,10 +136,7 @@ class SimRank(_Base):
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
         self._tick("iterate")
-        self._result = _drv.collect(solver, [self._node_order], self._gather)
-        out = self._result.frame(0)
-        self._tick("result")
-        return out
+        return self._finish(solver, [self._node_order])
 
 
 class SimRankPP(SimRank):
@@ -168,10 +185,7 @@ class SimRankPP(SimRank):
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
         self._tick("iterate")
-        self._result = _drv.collect(solver, [self._node_order], self._gather)
-        out = self._result.frame(0)
-        self._tick("result")
-        return out
+        return self._finish(solver, [self._node_order])
 
 
 class AprioriSimRank(SimRankPP):
@@ -191,10 +205,7 @@ class AprioriSimRank(SimRankPP):
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
         self._tick("iterate")
-        self._result = _drv.collect(solver, [self._node_order], self._gather)
-        out = self._result.frame(0)
-        self._tick("result")
-        return out
+        return self._finish(solver, [self._node_order])
 
 
 # =========================================================================== bipartite
@@ -249,10 +260,7 @@ class BipartiteSimRank(_BipartiteGraphs, _Base):
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
         self._tick("iterate")
-        self._result = _drv.collect(solver, list(self._labels()), self._gather)
-        out = self._result.frame(0), self._result.frame(1)
-        self._tick("result")
-        return out
+        return self._finish(solver, list(self._labels()))
 
 
 class BipartiteSimRankPP(_BipartiteGraphs, SimRankPP):
@@ -292,10 +300,7 @@ class BipartiteSimRankPP(_BipartiteGraphs, SimRankPP):
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
         self._tick("iterate")
-        self._result = _drv.collect(solver, list(self._labels()), self._gather)
-        out = self._result.frame(0), self._result.frame(1)
-        self._tick("result")
-        return out
+        return self._finish(solver, list(self._labels()))
 
 
 class BipartitleAprioriSimRank(BipartiteSimRankPP):
@@ -319,10 +324,7 @@ class BipartitleAprioriSimRank(BipartiteSimRankPP):
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
         self._tick("iterate")
-        self._result = _drv.collect(solver, list(self._labels()), self._gather)
-        out = self._result.frame(0), self._result.frame(1)
-        self._tick("result")
-        return out
+        return self._finish(solver, list(self._labels()))
 
 
 # README.md:16 of the reference (and BASELINE.json) spell these "Bipartitle..."

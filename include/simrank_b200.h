@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 4
+#define SRK_ABI_VERSION 5
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -191,7 +191,8 @@ int srk_i8_supported(void);
  *                     atomicMax a key of the largest off-diagonal value of every row of the result,
  *                     key = high word of the double + 1, so that (double)(key << 32) bounds the row
  *                     within 2^-20: the input of srk_slice_rows_key_f64, which then needs one pass.
- * mode SRK_X2_COUNTS: out_counts[j, r] = min(D[j,r], 65535) as uint16 (ns must be 1, V = a 0/1
+ * mode SRK_X2_COUNTS: out_counts[j, r] = min(D[j,r], 65535) as uint16, or D[j,r] as uint32 when
+ *                     counts_bits == 32 (needed once two rows can share 65535 neighbours) (ns must be 1, V = a 0/1
  *                     matrix as a single plane): `np.dot((G>0).astype(int), (G>0).T.astype(int))`
  *                     of SimRank.py:315, also the A A^T term above.                              */
 #define SRK_X2_MID 0
@@ -210,13 +211,14 @@ typedef struct srk_x2_args {
   uint8_t* out_planes; int64_t ld_outp; int64_t out_plane_stride;    /* MID */
   srk_rowbound out_rowbound;                                         /* MID: bound of U row j */
   const double* g_a; const double* g_v;                              /* FINAL: row factors of A8 / V rows */
-  const uint16_t* counts; int64_t ld_counts;                         /* FINAL (indexed like out_f64) */
+  const void* counts; int64_t ld_counts;                             /* FINAL (indexed like out_f64) */
   int add_counts, use_evidence;
+  int counts_bits;                                                   /* 16 (default when 0) or 32: element type of counts / out_counts */
   double* out_f64; int64_t ld_out; int64_t diag_offset;              /* FINAL */
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;        /* FINAL, TRANSPOSED: see above */
   uint32_t* rowmax_hi;                                               /* FINAL, DIRECT/SYMMETRIC: see below */
   srk_epilogue epi;                                                  /* FINAL */
-  uint16_t* out_counts; int64_t ld_out_counts;                       /* COUNTS */
+  void* out_counts; int64_t ld_out_counts;                           /* COUNTS */
 } srk_x2_args;
 int srk_x2_half(const srk_x2_args* args, void* stream);
 

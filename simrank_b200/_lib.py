@@ -11,7 +11,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 SRK_I8_MID, SRK_I8_FINAL, SRK_I8_COUNTS = 0, 1, 2
 SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
@@ -68,7 +68,7 @@ class X2Args(C.Structure):
                 ("out_rowbound", RowBound),
                 ("g_a", C.c_void_p), ("g_v", C.c_void_p),
                 ("counts", C.c_void_p), ("ld_counts", C.c_int64),
-                ("add_counts", C.c_int), ("use_evidence", C.c_int),
+                ("add_counts", C.c_int), ("use_evidence", C.c_int), ("counts_bits", C.c_int),
                 ("out_f64", C.c_void_p), ("ld_out", C.c_int64), ("diag_offset", C.c_int64),
                 ("mirror_out", C.c_void_p), ("ld_mirror", C.c_int64), ("mirror_col0", C.c_int64),
                 ("rowmax_hi", C.c_void_p),

@@ -205,7 +205,7 @@ __device__ __forceinline__ int pow2_exponent(double b) {
   const long long bits = __double_as_longlong(b);
   int e = (int)((bits >> 52) & 0x7ff) - 1023;
   if (bits & 0xfffffffffffffll) ++e;
-  const int lo = 8 * NS - 46;                             // keeps counts << (8 NS - f) inside 62 bits
+  const int lo = 8 * NS - 40;                             // keeps counts (< 2^22) << (8 NS - f) inside 62 bits
   return e < lo ? lo : (e > 1000 ? 1000 : e);
 }
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
@@ -228,6 +228,10 @@ __device__ __forceinline__ uint32_t mid_quant(unsigned long long D, double alpha
 __device__ __forceinline__ double final_value(unsigned long long D, uint32_t cnt, int sh, double cf, double gj) {
   const unsigned long long T = (D << (sh >> 8)) + ((unsigned long long)cnt << (sh & 0xff));
   return ((double)(long long)T * cf) * gj;
+}
+// common-neighbour counts are held as uint16 (or uint32 when a degree can reach 65535)
+__device__ __forceinline__ uint32_t load_count(const void* base, int64_t idx, int c32) {
+  return c32 ? reinterpret_cast<const uint32_t*>(base)[idx] : (uint32_t)reinterpret_cast<const uint16_t*>(base)[idx];
 }
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 // High word of a non-negative double, rounded up: a 32-bit key that is monotone in the value
@@ -279,14 +283,14 @@ struct Params {
   srk_rowbound out_rowbound;
   // FINAL
   const double* g_a; const double* g_v;
-  const uint16_t* counts; int64_t ld_counts; int add_counts, use_evidence;
+  const void* counts; int64_t ld_counts; int add_counts, use_evidence, counts32;
   double* out_f64; int64_t ld_out; int64_t diag_offset;
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;
   uint32_t* rowmax_hi;
   EpilogueDev epi;
   double* maxdiff; double* maxoff;
   // COUNTS
-  uint16_t* out_counts; int64_t ld_out_counts;
+  void* out_counts; int64_t ld_out_counts;
   // schedule
   int tiles_j, tiles_r, group_j, total_tiles;
   int kblock;
@@ -441,7 +445,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       fast_ok = have_old && !p.epi.prior && !p.epi.evidence &&
                 ((reinterpret_cast<uintptr_t>(p.out_f64) | reinterpret_cast<uintptr_t>(p.epi.s_old)) & 15) == 0 &&
                 ((p.ld_out | p.epi.ld_s_old) & 1) == 0;
-      if (p.counts) fast_ok = fast_ok && (reinterpret_cast<uintptr_t>(p.counts) & 15) == 0 && (p.ld_counts & 7) == 0;
+      if (p.counts) fast_ok = fast_ok && (reinterpret_cast<uintptr_t>(p.counts) & 15) == 0 && (p.ld_counts & (p.counts32 ? 3 : 7)) == 0;
       if (p.mirror_out)
         fast_ok = fast_ok && (reinterpret_cast<uintptr_t>(p.mirror_out) & 15) == 0 && ((p.ld_mirror | p.mirror_col0) & 1) == 0;
     }
@@ -493,8 +497,9 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const char* sp = reinterpret_cast<const char*>(p.epi.s_old + j * p.epi.ld_s_old + r0);
         for (int64_t o = 0; o < cols * 8; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + o));
         if (p.counts) {
-          const char* cp = reinterpret_cast<const char*>(p.counts + j * p.ld_counts + r0);
-          for (int64_t o = 0; o < cols * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o));
+          const int cb = p.counts32 ? 4 : 2;
+          const char* cp = reinterpret_cast<const char*>(p.counts) + (j * p.ld_counts + r0) * cb;
+          for (int64_t o = 0; o < cols * cb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + o));
         }
       }
       mbar_wait(&tmem_full[b], (uint32_t)(t >> 1) & 1u);
@@ -517,6 +522,20 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
         if (MODE == SRK_X2_COUNTS) {
           if (!jvalid) continue;
+          if (p.counts32) {
+            uint32_t* o = reinterpret_cast<uint32_t*>(p.out_counts) + j * p.ld_out_counts + rc;
+            if (rc + 16 <= p.ld_out_counts && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int x = 0; x < 16; x += 4)
+                reinterpret_cast<uint4*>(o)[x >> 2] = make_uint4(rc + x < p.R ? a[0][x] : 0u, rc + x + 1 < p.R ? a[0][x + 1] : 0u,
+                                                                 rc + x + 2 < p.R ? a[0][x + 2] : 0u, rc + x + 3 < p.R ? a[0][x + 3] : 0u);
+            } else {
+#pragma unroll
+              for (int x = 0; x < 16; ++x)
+                if (rc + x < p.R) o[x] = a[0][x];
+            }
+            continue;
+          }
           uint32_t w[8];
 #pragma unroll
           for (int x = 0; x < 16; x += 2) {
@@ -524,7 +543,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const uint32_t hi = (rc + x + 1 < p.R) ? min(a[0][x + 1], 65535u) : 0u;
             w[x >> 1] = lo | (hi << 16);
           }
-          uint16_t* o = p.out_counts + j * p.ld_out_counts + rc;
+          uint16_t* o = reinterpret_cast<uint16_t*>(p.out_counts) + j * p.ld_out_counts + rc;
           if (rc + 16 <= p.ld_out_counts && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
             reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
             reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -575,12 +594,19 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           // rows past the end of A8: nothing to store, but stay for the warp-wide reduction
         } else if (fast && !trans) {
           // 128-bit loads/stores along the row, no predicates
-          uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-          if (p.counts) {
-            const uint4* cp = reinterpret_cast<const uint4*>(p.counts + j * p.ld_counts + rc);
+          uint32_t cv[16];
+#pragma unroll
+          for (int x = 0; x < 16; ++x) cv[x] = 0u;
+          if (p.counts && p.counts32) {
+            const uint4* cp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.counts) + j * p.ld_counts + rc);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { const uint4 t4 = cp[x]; cv[4 * x] = t4.x; cv[4 * x + 1] = t4.y; cv[4 * x + 2] = t4.z; cv[4 * x + 3] = t4.w; }
+          } else if (p.counts) {
+            const uint4* cp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.counts) + j * p.ld_counts + rc);
             const uint4 t0 = cp[0], t1 = cp[1];
-            cw[0] = t0.x; cw[1] = t0.y; cw[2] = t0.z; cw[3] = t0.w;
-            cw[4] = t1.x; cw[5] = t1.y; cw[6] = t1.z; cw[7] = t1.w;
+            const uint32_t cw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+            for (int x = 0; x < 16; ++x) cv[x] = (cw[x >> 1] >> (16 * (x & 1))) & 0xffffu;
           }
           double so[16];
           const double2* sp = reinterpret_cast<const double2*>(p.epi.s_old + j * p.epi.ld_s_old + rc);
@@ -590,7 +616,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
-            const uint32_t cnt = (cw[x >> 1] >> (16 * (x & 1))) & 0xffffu;
+            const uint32_t cnt = cv[x];
             double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
             if (p.use_evidence) val *= evidence_factor(cnt);
             rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
@@ -615,9 +641,8 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
           for (int x = 0; x < 16; ++x) so[x] = sp[x * p.epi.ld_s_old];
           if (p.counts) {
-            const uint16_t* cp = p.counts + rc * p.ld_counts + j;
 #pragma unroll
-            for (int x = 0; x < 16; ++x) cnt[x] = cp[x * p.ld_counts];
+            for (int x = 0; x < 16; ++x) cnt[x] = load_count(p.counts, (rc + x) * p.ld_counts + j, p.counts32);
           } else {
 #pragma unroll
             for (int x = 0; x < 16; ++x) cnt[x] = 0u;
@@ -646,7 +671,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (!live) continue;
             const int64_t idx_o = trans ? r * p.ld_out + j : j * p.ld_out + r;
             uint32_t cnt = 0u;
-            if (p.counts) cnt = trans ? p.counts[r * p.ld_counts + j] : p.counts[j * p.ld_counts + r];
+            if (p.counts) cnt = load_count(p.counts, trans ? r * p.ld_counts + j : j * p.ld_counts + r, p.counts32);
             double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
             if (p.use_evidence) val *= evidence_factor(cnt);
             else if (p.epi.evidence)
@@ -773,6 +798,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.out_rowbound = a.out_rowbound;
   p.g_a = a.g_a; p.g_v = a.g_v;
   p.counts = a.counts; p.ld_counts = a.ld_counts; p.add_counts = a.add_counts; p.use_evidence = a.use_evidence;
+  p.counts32 = a.counts_bits == 32;
   p.out_f64 = a.out_f64; p.ld_out = a.ld_out; p.diag_offset = a.diag_offset;
   p.mirror_out = a.mirror_out; p.ld_mirror = a.ld_mirror; p.mirror_col0 = a.mirror_col0;
   p.rowmax_hi = a.rowmax_hi;
@@ -836,7 +862,8 @@ extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
   if (!srk_i8_supported()) return fail(SRK_ERR_UNSUPPORTED, "%s", "tcgen05 kind::i8 needs an sm_100 device");
   cudaStream_t st = (cudaStream_t)stream;
   if (a->mode == SRK_X2_COUNTS) {
-    SRK_REQUIRE(a->ns == 1 && a->out_counts && a->ld_out_counts >= a->R, "COUNTS needs ns=1 and a uint16 output");
+    SRK_REQUIRE(a->ns == 1 && a->out_counts && a->ld_out_counts >= a->R, "COUNTS needs ns=1 and a count output");
+    SRK_REQUIRE(a->counts_bits == 0 || a->counts_bits == 16 || a->counts_bits == 32, "counts_bits must be 16 or 32");
     return x2::launch<1, SRK_X2_COUNTS>(*a, st);
   }
   SRK_REQUIRE(a->ns == 1 || a->in_plane_stride % 16 == 0, "plane stride must be a multiple of 16");
@@ -858,6 +885,7 @@ extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
                 "unknown layout");
     SRK_REQUIRE(!(a->use_evidence && a->epi.evidence), "evidence given twice (counts and epi.evidence)");
     SRK_REQUIRE(!(a->add_counts || a->use_evidence) || a->counts, "counts missing");
+    SRK_REQUIRE(a->counts_bits == 0 || a->counts_bits == 16 || a->counts_bits == 32, "counts_bits must be 16 or 32");
     if (a->layout == SRK_X2_TRANSPOSED) {
       SRK_REQUIRE(a->ld_out >= a->M, "ld_out smaller than M (transposed layout)");
     } else {

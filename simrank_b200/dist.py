@@ -37,7 +37,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import _ptr, _round_up, _stream, choose_slices
+from .engine import _ptr, _round_up, _stream, choose_slices, count_bits
 from .graph import HostOperator
 
 _NO_DIAGONAL = -(1 << 40)
@@ -219,14 +219,15 @@ class ShardedHalf:
     def _pattern_counts(self) -> torch.Tensor:
         """uint16 ``A A^T`` for the LOCAL rows (rows_q x n_out), see DeviceOperator.pattern_counts."""
         ldc = _round_up(max(self.n_out, 1), 16)
-        cnt = torch.zeros((self.per, ldc), dtype=torch.int16, device=self.device)
+        bits = count_bits(self.op.deg)
+        cnt = torch.zeros((self.per, ldc), dtype=torch.int16 if bits == 16 else torch.int32, device=self.device)
         if self.rows:
             a = _lib.X2Args()
             a.mode, a.ns = _lib.SRK_X2_COUNTS, 1
             a.M, a.R, a.K = self.rows, self.n_out, self.n_in
             a.A8, a.lda = self.a8.data_ptr() + self.row0 * self.lda, self.lda
             a.in_planes, a.ld_in, a.in_plane_stride = self.a8.data_ptr(), self.lda, self.a8.numel()
-            a.out_counts, a.ld_out_counts = cnt.data_ptr(), ldc
+            a.out_counts, a.ld_out_counts, a.counts_bits = cnt.data_ptr(), ldc, bits
             self._launch(a, "srk_x2_half(COUNTS)")
         return cnt
 
@@ -304,7 +305,9 @@ class ShardedHalf:
             b.g_a, b.g_v = self.g.data_ptr() + 8 * col0, self.g.data_ptr() + 8 * (self.row0 + r_lo)
             off = r_lo * self.ld + col0                            # element offset of the block inside S / counts
             ldc = self.counts.stride(0)
-            b.counts, b.ld_counts, b.add_counts = self.counts.data_ptr() + 2 * (r_lo * ldc + col0), ldc, 1
+            esz = self.counts.element_size()
+            b.counts, b.ld_counts, b.add_counts = self.counts.data_ptr() + esz * (r_lo * ldc + col0), ldc, 1
+            b.counts_bits = 8 * esz
             b.use_evidence = 1 if self.evidence_from_pattern else 0
             b.out_f64, b.ld_out = self.S.data_ptr() + 8 * off, self.ld
             e = b.epi

@@ -97,20 +97,26 @@ class DeviceOperator:
             self._a8 = a8
         return self._a8
 
+    def count_bits(self) -> int:
+        """16 unless two rows can have 65535 common neighbours (second-largest degree)."""
+        return count_bits(self.host.deg)
+
     def pattern_counts(self) -> torch.Tensor:
-        """uint16 common-neighbour counts ``A A^T`` of the 0/1 pattern (saturating at 65535), the
-        unit-diagonal term of the tensor-core path: ``A S A^T = A S_off A^T + A A^T``.  Held as an
-        int16 tensor (torch has no arithmetic on uint16; only the bytes matter)."""
+        """Common-neighbour counts ``A A^T`` of the 0/1 pattern, the unit-diagonal term of the
+        tensor-core path: ``A S A^T = A S_off A^T + A A^T``; uint16, or uint32 when a count can reach
+        65535.  Held as an int16/int32 tensor (torch has no arithmetic on unsigned types; only the
+        bytes matter)."""
         if self._cnt16 is None:
+            bits = self.count_bits()
             ld = _round_up(max(self.M, 1), 8)
-            cnt = torch.empty((self.M, ld), dtype=torch.int16, device=self.device)
+            cnt = torch.empty((self.M, ld), dtype=torch.int16 if bits == 16 else torch.int32, device=self.device)
             a8 = self.dense_u8()
             a = _lib.X2Args()
             a.mode, a.ns = _lib.SRK_X2_COUNTS, 1
             a.M, a.R, a.K = self.M, self.M, self.K
             a.A8, a.lda = a8.data_ptr(), self.lda
             a.in_planes, a.ld_in, a.in_plane_stride = a8.data_ptr(), self.lda, a8.numel()
-            a.out_counts, a.ld_out_counts = cnt.data_ptr(), ld
+            a.out_counts, a.ld_out_counts, a.counts_bits = cnt.data_ptr(), ld, bits
             _lib.check(_lib.load().srk_x2_half(C.byref(a), _stream()), "srk_x2_half(COUNTS)")
             self._cnt16 = cnt
         return self._cnt16
@@ -146,6 +152,13 @@ class DeviceOperator:
         return cnt
 
 
+def count_bits(deg: np.ndarray) -> int:
+    """Element width of the common-neighbour counts: |N(i) & N(j)| <= the second-largest degree."""
+    if deg.size < 2:
+        return 16
+    return 16 if int(np.partition(deg, -2)[-2]) < 65535 else 32
+
+
 def choose_mode(op: HostOperator, requested: str | None = None) -> str:
     """'csr' (exact f64 gather path) or 'i8' (tcgen05 fixed-point path)."""
     mode = (requested or os.environ.get("SIMRANK_B200_MODE", "auto")).lower()
@@ -156,9 +169,6 @@ def choose_mode(op: HostOperator, requested: str | None = None) -> str:
     ok = bool(_lib.load().srk_i8_supported()) and bool(np.all(op.g >= 0)) and bool(np.all(np.isfinite(op.g)))
     dense_bytes = op.M * _round_up(op.K, 128)
     density = op.nnz / max(1, op.M * op.K)
-    # the A A^T term of the tensor-core path is held as uint16 counts
-    top2 = np.sort(op.deg)[-2:] if op.M >= 2 else op.deg
-    ok = ok and (op.M < 2 or int(top2[0]) < 65535)
     return "i8" if ok and min(op.M, op.K) >= 1024 and dense_bytes <= (16 << 30) and density >= 1.0 / 1024 else "csr"
 
 
@@ -330,6 +340,7 @@ class _Half:
         b.in_rowbound = bound_U
         b.g_a = b.g_v = self.op.g.data_ptr()
         b.counts, b.ld_counts, b.add_counts = self.counts.data_ptr(), self.counts.stride(0), 1
+        b.counts_bits = 8 * self.counts.element_size()
         b.use_evidence = 1 if self.evidence_from_pattern else 0
         b.out_f64, b.ld_out, b.diag_offset = self.S.data_ptr(), self.ld, 0
         self.rowmax_hi.zero_()                                     # after the slice above read the old keys

@@ -35,6 +35,30 @@ def _unique_pairs(rng, m, n_rows, n_cols, p_rows, p_cols, forbid_diag):
     return have // n_cols, have % n_cols
 
 
+def _distinct_per_row(rng, rows, n_cols, k, p):
+    """[rows, k] column indices, distinct inside each row, drawn ~ p (vectorised: oversample with
+    replacement, keep the first k distinct draws of each row, redraw the few rows that fall short)."""
+    out = np.empty((rows, k), dtype=np.int64)
+    todo = np.arange(rows)
+    width = 2 * k + 8
+    while todo.size:
+        d = rng.choice(n_cols, size=(todo.size, width), p=p)
+        order = np.argsort(d, axis=1, kind="stable")
+        sd = np.take_along_axis(d, order, axis=1)
+        dup_sorted = np.zeros_like(sd, dtype=bool)
+        dup_sorted[:, 1:] = sd[:, 1:] == sd[:, :-1]                # later draws of an already seen value
+        dup = np.empty_like(dup_sorted)
+        np.put_along_axis(dup, order, dup_sorted, axis=1)
+        rank = np.cumsum(~dup, axis=1)                             # 1-based index among the distinct draws
+        ok = rank[:, -1] >= k
+        take = (~dup) & (rank <= k)
+        good = np.nonzero(ok)[0]
+        out[todo[good]] = d[good][take[good]].reshape(good.size, k)
+        todo = todo[~ok]
+        width *= 2
+    return out
+
+
 def directed_edges(n, m, alpha, seed):
     """-> (from_idx, to_idx): m unique directed edges without self-loops."""
     rng = np.random.default_rng(seed)
@@ -54,7 +78,7 @@ def bipartite_edges(n1, n2, m, alpha_items, seed, min_per_user=0):
     p_users = act / act.sum()
     if min_per_user:
         base_u = np.repeat(np.arange(n1), min_per_user)
-        base_i = np.concatenate([rng.choice(n2, size=min_per_user, replace=False, p=p_items) for _ in range(n1)])
+        base_i = _distinct_per_row(rng, n1, n2, min_per_user, p_items).ravel()
         rest = m - base_u.size
         u, i = _unique_pairs(rng, max(rest, 0) + base_u.size, n1, n2, p_users, p_items, forbid_diag=False)
         key = np.concatenate([base_u.astype(np.int64) * n2 + base_i, u.astype(np.int64) * n2 + i])

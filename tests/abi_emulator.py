@@ -54,7 +54,10 @@ def srk_x2_half(a: _lib.X2Args) -> None:
     A = _view(a.A8, C.c_uint8, M, K, a.lda).astype(np.int64)
     D = A @ _read_planes(a).T                                     # [M, R] exact integers
     if a.mode == _lib.SRK_X2_COUNTS:
-        _view(a.out_counts, C.c_uint16, M, R, a.ld_out_counts)[:, :] = np.minimum(D, 65535).astype(np.uint16)
+        if a.counts_bits == 32:
+            _view(a.out_counts, C.c_uint32, M, R, a.ld_out_counts)[:, :] = D.astype(np.uint32)
+        else:
+            _view(a.out_counts, C.c_uint16, M, R, a.ld_out_counts)[:, :] = np.minimum(D, 65535).astype(np.uint16)
         return
     qmax = 256 ** ns
     inb = _bound(a.in_rowbound, R)
@@ -84,7 +87,8 @@ def srk_x2_half(a: _lib.X2Args) -> None:
     dl = np.minimum(np.maximum(-s, 0), 17)
     s = np.maximum(s, 0)
     T = D << dl[None, :]
-    cnt = mat(a.counts, C.c_uint16, a.ld_counts).astype(np.int64) if a.counts else np.zeros((M, R), dtype=np.int64)
+    ctype = C.c_uint32 if a.counts_bits == 32 else C.c_uint16
+    cnt = mat(a.counts, ctype, a.ld_counts).astype(np.int64) if a.counts else np.zeros((M, R), dtype=np.int64)
     if a.add_counts:
         T = T + (cnt << s[None, :])
     g_a, g_v = _f64(a.g_a, M), _f64(a.g_v, R)

@@ -52,6 +52,12 @@ def main():
     l1, l2, S1o, S2o, _, _ = orc.fit_bipartite(df, weighted=True, iterations=4, eps=0.0)
     S1, S2 = M.BipartiteSimRank(mode="i8").fit(df, weighted=True, iterations=4, eps=0.0, verbose=False)
     worst = max(worst, float(np.abs(S1.to_numpy() - S1o).max()), float(np.abs(S2.to_numpy() - S2o).max()))
+    # BASELINE cfg5 at 1/16 scale: BipartiteSimRankPP, n1 != n2 (Evidence_N2 for group 2), weighted
+    df = synth.config_frame("cfg5", scale=1 / 16)
+    l1, l2, S1o, S2o, _, _ = orc.fit_bipartite(df, kind="simrank_pp", weighted=True, iterations=3, eps=0.0)
+    S1, S2 = M.BipartitleSimRankPP(mode="i8").fit(df, weighted=True, iterations=3, eps=0.0, verbose=False)
+    assert list(S1.index) == l1 and list(S2.index) == l2
+    worst = max(worst, float(np.abs(S1.to_numpy() - S1o).max()), float(np.abs(S2.to_numpy() - S2o).max()))
     t = torch.tensor([worst], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -83,6 +83,29 @@ def test_x2_counts_exact(dev, M, R, K):
 
 
 @needs_i8
+def test_x2_counts_uint32(dev):
+    """Counts beyond 65535 need the 32-bit layout (rows sharing more than 65535 neighbours)."""
+    M, R, K = 200, 150, 70016
+    rng = np.random.default_rng(9)
+    A = (rng.random((M, K)) < 0.5).astype(np.uint8)
+    B = (rng.random((R, K)) < 0.5).astype(np.uint8)
+    A[3] = 1
+    B[5] = 1                                              # count 70016 > 65535
+    a8, b8 = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+    ldc = engine._round_up(R, 8)
+    out = torch.full((M, ldc), 7, dtype=torch.int32, device=dev)
+    a = _lib.X2Args()
+    a.mode, a.ns, a.M, a.R, a.K = _lib.SRK_X2_COUNTS, 1, M, R, K
+    a.A8, a.lda = a8.data_ptr(), K
+    a.in_planes, a.ld_in, a.in_plane_stride = b8.data_ptr(), K, R * K
+    a.out_counts, a.ld_out_counts, a.counts_bits = out.data_ptr(), ldc, 32
+    _run(a)
+    want = A.astype(np.int64) @ B.astype(np.int64).T
+    assert want.max() == K
+    np.testing.assert_array_equal(out.cpu().numpy()[:, :R].astype(np.int64), want)
+
+
+@needs_i8
 @pytest.mark.parametrize("ns", [2, 3, 4])
 @pytest.mark.parametrize("M,R,K", [(10, 10, 10), (256, 128, 128), (333, 200, 515), (170, 513, 129), (600, 70, 1300)])
 def test_x2_mid_against_integer_matmul(dev, ns, M, R, K):
@@ -115,7 +138,7 @@ def test_x2_mid_against_integer_matmul(dev, ns, M, R, K):
     assert not pad.any()                                                # chunk padding is written as zeros
 
 
-def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False):
+def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False, bits=16):
     qmax = 256 ** ns
     q = rng.integers(0, qmax, (R, K), dtype=np.int64)
     A = (rng.random((M, K)) < 0.2).astype(np.uint8)
@@ -129,16 +152,16 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False)
     ld = engine._round_up(cols, 16)
     diag_offset = 3 if trans else 0
     S_old = rng.random((rows, cols))
-    cnt = rng.integers(0, 70, (rows, cols)).astype(np.uint16)
-    cnt[0, : min(cols, 5)] = [65535, 54, 53, 1, 0][: min(cols, 5)]
+    cnt = rng.integers(0, 70, (rows, cols)).astype(np.uint16 if bits == 16 else np.uint32)
+    cnt[0, : min(cols, 5)] = [65535 if bits == 16 else 300000, 54, 53, 1, 0][: min(cols, 5)]
     if layout == _lib.SRK_X2_SYMMETRIC:
         S_old = np.triu(S_old) + np.triu(S_old, 1).T
         cnt = np.triu(cnt) + np.triu(cnt, 1).T
     prior = rng.random((rows, cols)) if extras == "prior" else None
     S = torch.zeros((rows, ld), dtype=torch.float64, device=dev)
     S[:, :cols] = torch.from_numpy(S_old)
-    cd = torch.zeros((rows, ld), dtype=torch.int16, device=dev)
-    cd[:, :cols] = torch.from_numpy(cnt.view(np.int16))
+    cd = torch.zeros((rows, ld), dtype=torch.int16 if bits == 16 else torch.int32, device=dev)
+    cd[:, :cols] = torch.from_numpy(cnt.view(np.int16 if bits == 16 else np.int32))
     scal = torch.zeros(2, dtype=torch.float64, device=dev)
     a = _lib.X2Args()
     a.mode, a.ns, a.layout, a.M, a.R, a.K = _lib.SRK_X2_FINAL, ns, layout, M, R, K
@@ -150,7 +173,7 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False)
     a.out_f64, a.ld_out, a.diag_offset = S.data_ptr(), ld, diag_offset
     use_counts = extras in ("counts", "evidence", "prior", "ev8")
     if use_counts:
-        a.counts, a.ld_counts, a.add_counts = cd.data_ptr(), ld, 1
+        a.counts, a.ld_counts, a.add_counts, a.counts_bits = cd.data_ptr(), ld, 1, bits
         a.use_evidence = 1 if extras in ("evidence", "prior") else 0
     e = a.epi
     ev8 = None
@@ -254,6 +277,14 @@ def test_x2_final_bound_ranges(dev, ns, bscale):
     """Bounds of U above 256^NS (left shift of D) and below the clamp (counts << 46)."""
     _final_case(np.random.default_rng(5), ns, 300, 300, 260, _lib.SRK_X2_SYMMETRIC, "counts", dev, bscale=bscale)
     _final_case(np.random.default_rng(6), ns, 300, 200, 260, _lib.SRK_X2_DIRECT, "evidence", dev, bscale=bscale)
+
+
+@needs_i8
+@pytest.mark.parametrize("layout", [_lib.SRK_X2_DIRECT, _lib.SRK_X2_SYMMETRIC, _lib.SRK_X2_TRANSPOSED])
+def test_x2_final_counts_uint32(dev, layout):
+    M = R = 400
+    _final_case(np.random.default_rng(layout), 2, M, R, 260, layout, "evidence", dev, bits=32)
+    _final_case(np.random.default_rng(layout + 5), 3, M, R, 130, layout, "counts", dev, bits=32)
 
 
 @needs_i8
