@@ -166,7 +166,7 @@ int srk_i8_supported(void);
  * graphs whose similarities are small (DESIGN.md "precision").
  *
  * The row bounds of U (out_rowbound of MID = in_rowbound of FINAL) are rounded UP to powers of two
- * by the kernel, 2^f >= bound with f >= 8 NS - 46: the caller passes the same srk_rowbound to both.
+ * by the kernel, 2^f >= bound with f >= 8 NS - 40: the caller passes the same srk_rowbound to both.
  *
  * mode SRK_X2_MID   : U[j, r] = D[j,r] * bound_in(r) / 256^NS  re-quantised with 2^f(j) >= out_rowbound(j)
  *                     into out_planes (row j, column r).  With V = planes of S_off this is

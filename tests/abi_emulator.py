@@ -32,7 +32,7 @@ def pow2_exponent(b, ns):
     """f with 2^f the smallest power of two >= b, clamped to f >= 8 ns - 46; None-like -2^30 for b <= 0."""
     b = np.asarray(b, dtype=np.float64)
     m, e = np.frexp(np.where(b > 0, b, 1.0))
-    f = np.maximum(np.where(m == 0.5, e - 1, e), 8 * ns - 46)
+    f = np.maximum(np.where(m == 0.5, e - 1, e), 8 * ns - 40)
     return np.where(b > 0, f, -(1 << 30)).astype(np.int64)
 
 

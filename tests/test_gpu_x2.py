@@ -50,7 +50,7 @@ def _pow2_exponent(b, ns):
     of the row bounds of U)."""
     m, e = np.frexp(np.asarray(b, dtype=np.float64))          # b = m * 2^e, m in [0.5, 1)
     f = np.where(m == 0.5, e - 1, e)
-    return np.maximum(f, 8 * ns - 46).astype(np.int64)
+    return np.maximum(f, 8 * ns - 40).astype(np.int64)
 
 
 def _run(a):
