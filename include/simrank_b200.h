@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 5
+#define SRK_ABI_VERSION 6
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -219,6 +219,11 @@ typedef struct srk_x2_args {
   uint32_t* rowmax_hi;                                               /* FINAL, DIRECT/SYMMETRIC: see below */
   srk_epilogue epi;                                                  /* FINAL */
   void* out_counts; int64_t ld_out_counts;                           /* COUNTS */
+  /* Optional scratch (device, 4-byte aligned, contents irrelevant, must not be shared by launches
+   * that can overlap): progress counters that keep the CTA pairs of a launch at the same k, so that
+   * they find each other's operand panels in L2.  Used when sync_ws_bytes >= 16 * ceil(tiles /
+   * CTA pairs) (1 MB covers every supported size); NULL = pairs run free (same results, slower). */
+  void* sync_ws; int64_t sync_ws_bytes;
 } srk_x2_args;
 int srk_x2_half(const srk_x2_args* args, void* stream);
 

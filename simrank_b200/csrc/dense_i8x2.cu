@@ -104,28 +104,73 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 // TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes are
 // counted on the leader CTA's barrier (rank bit cleared).
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, uint64_t pol, int c0,
+                                            int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2) {
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, uint64_t pol, int c0,
+                                            int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, uint64_t pol, int c0,
+                                            int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
       : "memory");
+}
+// L2 eviction policies.  The operand panels are re-read by the other CTA pairs of a wave (keep:
+// evict_last); everything the epilogues touch is used exactly once (evict_first), so that 60 MB of
+// result traffic per wave does not push the panels out of the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* a, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* a, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* a, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_stream_f64x2(double2* a, double x, double y, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(a), "d"(x), "d"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream_f64(double* a, double x, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(x), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32x4(uint4* a, uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -168,6 +213,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void red_add_gpu(unsigned int* a) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(a) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* a) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -294,6 +352,10 @@ struct Params {
   // schedule
   int tiles_j, tiles_r, group_j, total_tiles;
   int kblock;
+  // lockstep of the CTA pairs (see "lockstep" in the producer): units of `sync_kb` K-blocks
+  unsigned int* sync; int sync_units_per_tile, sync_kb;
+  unsigned long long* trace;   // SRK_X2_TRACE (diagnostics): [clusters][trace_tiles][4] globaltimer at mainloop start/end, epilogue start/end
+  int trace_tiles;
   int debug;                   // SRK_X2_DEBUG (profiling experiments only): 1 no S_old, 2 no mirror, 4 no direct store
 };
 
@@ -376,24 +438,45 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tw.init(p);
       tw.advance(cluster_id);
       int stage = 0; uint32_t phase = 0;
+      const uint64_t pol = (p.debug & 16) ? policy_evict_normal() : policy_evict_last();
       for (int t = 0; t < my_tiles; ++t) {
         const int j0 = tw.jb * 256 + (int)cta * BMC;
         const int r0 = tw.rb * RT;
         for (int kb = 0; kb < kblocks; ++kb) {
+          if (p.sync && cta == 0 && kb % p.sync_kb == 0) {
+            // Lockstep.  The ~74 pairs of a wave read the same few operand panels; they only find
+            // each other's lines in L2 while they are at about the same k.  Left alone they drift
+            // apart by several tiles (memory-bound pairs run at slightly different speeds and nothing
+            // ever re-aligns them) and every pair streams its panels from DRAM: measured 140 GB per
+            // FINAL launch instead of 35 GB.  So progress is counted in units of sync_kb K-blocks and a
+            // pair starts unit u only after every pair that has a unit u-1 started it.  The wait is
+            // bounded: this is a performance hint, never a correctness dependency.
+            const int unit = t * p.sync_units_per_tile + kb / p.sync_kb;
+            red_add_gpu(p.sync + unit);
+            if (unit > 0) {
+              const int pt = (unit - 1) / p.sync_units_per_tile;               // tile index of the previous unit
+              const int left = p.total_tiles - pt * num_clusters;
+              const unsigned int expect = (unsigned int)(left < num_clusters ? left : num_clusters);
+              if (ld_relaxed_gpu(p.sync + unit - 1) < expect) {
+                const unsigned long long t_in = globaltimer_ns();
+                while (ld_relaxed_gpu(p.sync + unit - 1) < expect && globaltimer_ns() - t_in < 1000000ull) {}
+              }
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * C::kStageBytes;
           uint8_t* sb = sa + BMC * BK;
           if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-          tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, j0);
+          tma_load_2d(sa, &map_a, &full_bar[stage], pol, kb * BK, j0);
 #pragma unroll
           for (int b = 0; b < C::kBoxes; ++b) {
             const int nrow = (int)cta * C::NH + b * C::BR;         // row of the concatenated N operand
             const int plane = nrow / RT, rr = nrow % RT;
             if (p.kblock > 0) {
               const int k = kb * BK;
-              tma_load_4d(sb + b * C::BR * BK, &map_v, &full_bar[stage], k % p.kblock, r0 + rr, k / p.kblock, plane);
+              tma_load_4d(sb + b * C::BR * BK, &map_v, &full_bar[stage], pol, k % p.kblock, r0 + rr, k / p.kblock, plane);
             } else {
-              tma_load_3d(sb + b * C::BR * BK, &map_v, &full_bar[stage], kb * BK, r0 + rr, plane);
+              tma_load_3d(sb + b * C::BR * BK, &map_v, &full_bar[stage], pol, kb * BK, r0 + rr, plane);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -411,6 +494,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         mbar_wait(&tmem_empty[b], ((uint32_t)(t >> 1) & 1u) ^ 1u);    // both CTAs drained this buffer
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(b * kAccStride);
+        if (p.trace && t < p.trace_tiles) p.trace[((size_t)cluster_id * p.trace_tiles + t) * 4] = globaltimer_ns();
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -425,6 +509,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (kb == kblocks - 1) mma_commit_pair(&tmem_full[b]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if (p.trace && t < p.trace_tiles) p.trace[((size_t)cluster_id * p.trace_tiles + t) * 4 + 1] = globaltimer_ns();
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -439,6 +524,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const bool sym = p.layout == SRK_X2_SYMMETRIC;
     const bool trans = p.layout == SRK_X2_TRANSPOSED;
     const bool have_old = p.epi.s_old != nullptr;
+    const uint64_t spol = (p.debug & 8) ? policy_evict_normal() : policy_evict_first();
     // everything the vectorised paths assume about the caller's buffers (uniform over the grid)
     bool fast_ok = false;
     if (MODE == SRK_X2_FINAL) {
@@ -487,7 +573,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (MODE == SRK_X2_MID) fj = pow2_exponent<NS>(row_bound(p.out_rowbound, j));
         if (MODE == SRK_X2_FINAL) rowf = p.g_a[j];
       }
-      if (MODE == SRK_X2_FINAL && !trans && jvalid && have_old && !(sym && j > r0 + RT - 1)) {
+      if (MODE == SRK_X2_FINAL && !trans && jvalid && have_old && !(sym && j > r0 + RT - 1) && !(p.debug & 64)) {
         // The accumulator of this tile is still being computed: pull the rows of S_old and of the
         // counts that its epilogue will read into L2 now, so that the eight dependent
         // load -> compute -> store rounds below see L2 latency instead of DRAM latency.  (An
@@ -505,6 +591,8 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(&tmem_full[b], (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const uint32_t acc = lane_base + (uint32_t)(b * kAccStride);
+      const bool tracing = p.trace && t < p.trace_tiles && cta == 0 && et == 0;
+      if (tracing) p.trace[((size_t)cluster_id * p.trace_tiles + t) * 4 + 2] = globaltimer_ns();
 
       for (int c0 = 0; c0 < RT; c0 += 16) {
         __syncwarp();                                     // reconverge after the divergent tails below
@@ -572,8 +660,8 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
 #pragma unroll
           for (int s = 0; s < NS; ++s)
-            *reinterpret_cast<uint4*>(p.out_planes + s * p.out_plane_stride + j * p.ld_outp + rc) =
-                make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+            st_stream_u32x4(reinterpret_cast<uint4*>(p.out_planes + s * p.out_plane_stride + j * p.ld_outp + rc),
+                            make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]), spol);
           continue;
         }
 
@@ -600,10 +688,10 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (p.counts && p.counts32) {
             const uint4* cp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.counts) + j * p.ld_counts + rc);
 #pragma unroll
-            for (int x = 0; x < 4; ++x) { const uint4 t4 = cp[x]; cv[4 * x] = t4.x; cv[4 * x + 1] = t4.y; cv[4 * x + 2] = t4.z; cv[4 * x + 3] = t4.w; }
+            for (int x = 0; x < 4; ++x) { const uint4 t4 = ld_stream_u32x4(cp + x, spol); cv[4 * x] = t4.x; cv[4 * x + 1] = t4.y; cv[4 * x + 2] = t4.z; cv[4 * x + 3] = t4.w; }
           } else if (p.counts) {
             const uint4* cp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.counts) + j * p.ld_counts + rc);
-            const uint4 t0 = cp[0], t1 = cp[1];
+            const uint4 t0 = ld_stream_u32x4(cp, spol), t1 = ld_stream_u32x4(cp + 1, spol);
             const uint32_t cw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
             for (int x = 0; x < 16; ++x) cv[x] = (cw[x >> 1] >> (16 * (x & 1))) & 0xffffu;
@@ -612,7 +700,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const double2* sp = reinterpret_cast<const double2*>(p.epi.s_old + j * p.epi.ld_s_old + rc);
           if (!(p.debug & 1)) {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) { const double2 d2 = sp[x]; so[2 * x] = d2.x; so[2 * x + 1] = d2.y; }
+            for (int x = 0; x < 8; ++x) { const double2 d2 = ld_stream_f64x2(sp + x, spol); so[2 * x] = d2.x; so[2 * x + 1] = d2.y; }
           }
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
@@ -626,12 +714,12 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           double2* op = reinterpret_cast<double2*>(p.out_f64 + j * p.ld_out + rc);
           if (!(p.debug & 4)) {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) op[x] = make_double2(v[2 * x], v[2 * x + 1]);
+            for (int x = 0; x < 8; ++x) st_stream_f64x2(op + x, v[2 * x], v[2 * x + 1], spol);
           }
           if (sym && !(p.debug & 2)) {
             double* mp = p.out_f64 + rc * p.ld_out + j;   // mirror: 32 lanes write 256 contiguous bytes per x
 #pragma unroll
-            for (int x = 0; x < 16; ++x) { mp[x * p.ld_out] = v[x]; key[x] = hi_key(v[x]); }
+            for (int x = 0; x < 16; ++x) { st_stream_f64(mp + x * p.ld_out, v[x], spol); key[x] = hi_key(v[x]); }
           }
         } else if (fast && trans) {
           // element (row rc + x, column j): every access is coalesced across the lanes
@@ -639,7 +727,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           double so[16];
           const double* sp = p.epi.s_old + rc * p.epi.ld_s_old + j;
 #pragma unroll
-          for (int x = 0; x < 16; ++x) so[x] = sp[x * p.epi.ld_s_old];
+          for (int x = 0; x < 16; ++x) so[x] = ld_stream_f64(sp + x * p.epi.ld_s_old, spol);
           if (p.counts) {
 #pragma unroll
             for (int x = 0; x < 16; ++x) cnt[x] = load_count(p.counts, (rc + x) * p.ld_counts + j, p.counts32);
@@ -654,13 +742,13 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (p.use_evidence) val *= evidence_factor(cnt[x]);
             omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
             dmax = umax64(dmax, abs_bits(val - so[x]));
-            op[x * p.ld_out] = val;
+            st_stream_f64(op + x * p.ld_out, val, spol);
             v[x] = val;
           }
           if (p.mirror_out) {                             // (row j, columns rc..) of the owner of row j
             double2* mp = reinterpret_cast<double2*>(p.mirror_out + j * p.ld_mirror + p.mirror_col0 + rc);
 #pragma unroll
-            for (int x = 0; x < 8; ++x) mp[x] = make_double2(v[2 * x], v[2 * x + 1]);
+            for (int x = 0; x < 8; ++x) st_stream_f64x2(mp + x, v[2 * x], v[2 * x + 1], spol);
           }
         } else if (!(sym && jd > rc + 15)) {              // (strictly below the diagonal: mirrored from above)
           // ---- general path: chunks that touch the diagonal or an edge, priors, uint8 evidence
@@ -695,12 +783,13 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (trans && p.mirror_out && r != jd) p.mirror_out[j * p.ld_mirror + p.mirror_col0 + r] = val;
           }
         }
-        if (sym && p.rowmax_hi) {                         // warp-uniform
+        if (sym && p.rowmax_hi && !(p.debug & 32)) {      // warp-uniform
           __syncwarp();
           const uint32_t cm = column_max16(key, lane);
           if (!(lane & 1) && cm > 1u) atomicMax(p.rowmax_hi + rc + column_of_lane(lane), cm);
         }
       }
+      if (tracing) p.trace[((size_t)cluster_id * p.trace_tiles + t) * 4 + 3] = globaltimer_ns();
       if (MODE == SRK_X2_FINAL && rmax) {
         omax = umax64(omax, rmax);
         if (p.rowmax_hi) atomicMax(p.rowmax_hi + j, (uint32_t)(rmax >> 32) + 1u);
@@ -835,6 +924,38 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   if (p.total_tiles < clusters) clusters = p.total_tiles;
   if (clusters < 1) return SRK_OK;
   cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+  {
+    // lockstep workspace: one counter per (tile index, quarter of the K loop)
+    const int kblocks = (int)((a.K + BK - 1) / BK);
+    const int per_tile = kblocks >= 64 ? 4 : 1;
+    const int64_t tiles_per_cluster = (p.total_tiles + clusters - 1) / clusters;
+    const int64_t need = tiles_per_cluster * per_tile * 4;
+    const bool off = (p.debug & 128) != 0;
+    if (a.sync_ws && a.sync_ws_bytes >= need && clusters > 1 && kblocks >= 16 && !off) {
+      p.sync = reinterpret_cast<unsigned int*>(a.sync_ws);
+      p.sync_units_per_tile = per_tile;
+      p.sync_kb = (kblocks + per_tile - 1) / per_tile;
+      SRK_CUDA_OK(cudaMemsetAsync(a.sync_ws, 0, (size_t)need, st));
+    }
+  }
+  if (const char* tp = getenv("SRK_X2_TRACE")) {
+    // diagnostics only: per-tile mainloop start/end times of every CTA pair, dumped after a blocking launch
+    static int launch_no = 0;
+    p.trace_tiles = (p.total_tiles + clusters - 1) / clusters;
+    const size_t words = (size_t)clusters * p.trace_tiles * 4;
+    SRK_CUDA_OK(cudaMalloc(&p.trace, words * 8));
+    SRK_CUDA_OK(cudaMemsetAsync(p.trace, 0, words * 8, st));
+    SRK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_a, map_v, p));
+    SRK_CUDA_OK(cudaStreamSynchronize(st));
+    unsigned long long* h = (unsigned long long*)malloc(words * 8);
+    SRK_CUDA_OK(cudaMemcpy(h, p.trace, words * 8, cudaMemcpyDeviceToHost));
+    char name[512];
+    snprintf(name, sizeof(name), "%s.%03d.m%d.ns%d.c%d.t%d.bin", tp, launch_no++, MODE, NS, clusters, p.trace_tiles);
+    if (FILE* f = fopen(name, "wb")) { fwrite(h, 8, words, f); fclose(f); }
+    free(h);
+    cudaFree(p.trace);
+    return SRK_OK;
+  }
   SRK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_a, map_v, p));
   return SRK_OK;
 }

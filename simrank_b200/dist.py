@@ -37,7 +37,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import _ptr, _round_up, _stream, choose_slices, count_bits
+from .engine import _ptr, _round_up, _stream, attach_sync_ws, choose_slices, count_bits
 from .graph import HostOperator
 
 _NO_DIAGONAL = -(1 << 40)
@@ -205,6 +205,7 @@ class ShardedHalf:
         return a8
 
     def _launch(self, args: _lib.X2Args, name: str):
+        attach_sync_ws(args, self.device)
         _lib.check(_lib.load().srk_x2_half(C.byref(args), _stream()), name)
 
     def _launch_slice(self, ns: int):

@@ -49,6 +49,19 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_SYNC_WS = {}
+
+
+def attach_sync_ws(args: "_lib.X2Args", device) -> None:
+    """Give a paired-SM launch its lockstep scratch (srk_x2_args.sync_ws): one 1 MB buffer per
+    (device, stream) -- launches on one stream never overlap."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
+    ws = _SYNC_WS.get(key)
+    if ws is None:
+        ws = _SYNC_WS[key] = torch.zeros(1 << 18, dtype=torch.int32, device=device)
+    args.sync_ws, args.sync_ws_bytes = ws.data_ptr(), ws.numel() * 4
+
+
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -117,6 +130,7 @@ class DeviceOperator:
             a.A8, a.lda = a8.data_ptr(), self.lda
             a.in_planes, a.ld_in, a.in_plane_stride = a8.data_ptr(), self.lda, a8.numel()
             a.out_counts, a.ld_out_counts, a.counts_bits = cnt.data_ptr(), ld, bits
+            attach_sync_ws(a, self.device)
             _lib.check(_lib.load().srk_x2_half(C.byref(a), _stream()), "srk_x2_half(COUNTS)")
             self._cnt16 = cnt
         return self._cnt16
@@ -328,6 +342,7 @@ class _Half:
         a.in_rowbound = _lib.RowBound.of(src.bound_vec.data_ptr(), 1.0, 0.0)
         a.out_planes, a.ld_outp, a.out_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
         a.out_rowbound = bound_U
+        attach_sync_ws(a, self.S.device)
         _lib.check(self._timed("x2_half_mid", lambda: lib.srk_x2_half(C.byref(a), _stream())), "srk_x2_half(MID)")
 
         b = _lib.X2Args()
@@ -346,6 +361,7 @@ class _Half:
         self.rowmax_hi.zero_()                                     # after the slice above read the old keys
         b.rowmax_hi = self.rowmax_hi.data_ptr()
         b.epi = self._epilogue()
+        attach_sync_ws(b, self.S.device)
         _lib.check(self._timed("x2_half_final", lambda: lib.srk_x2_half(C.byref(b), _stream())),
                    "srk_x2_half(FINAL)")
         self.version += 1
