@@ -141,11 +141,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ uint64_t policy_evict_normal() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* a, uint64_t pol) {
   double2 v;
   asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
@@ -280,12 +275,41 @@ __device__ __forceinline__ uint32_t mid_quant(unsigned long long D, double alpha
   return q;
 }
 
-// FINAL: x = coef * g_a[j] * g_v[r] * (D * 2^(f_r - 8 NS) + count).  With sh = s | dl << 8, where
-// s = max(8 NS - f_r, 0) and dl = max(f_r - 8 NS, 0), and cf = coef * g_v[r] * 2^-s this is
-// ((D << dl) + (count << s)) * cf * g_a[j]: integer combine, one conversion, two multiplies.
-__device__ __forceinline__ double final_value(unsigned long long D, uint32_t cnt, int sh, double cf, double gj) {
-  const unsigned long long T = (D << (sh >> 8)) + ((unsigned long long)cnt << (sh & 0xff));
-  return ((double)(long long)T * cf) * gj;
+// FINAL: x = coef * g_a[j] * g_v[r] * (D * 2^(f_r - 8 NS) + count).  With s = max(8 NS - f_r, 0),
+// dl = max(f_r - 8 NS, 0), T = (D << dl) + (count << s) (an exact integer < 2^62) and the two
+// positive scale factors cf = coef * g_v[r] * 2^-s and gj = g_a[j] this is x = T * cf * gj.
+//
+// The product is formed with INTEGER instructions.  FP64-pipe instructions (DMUL, DADD, I2F.F64)
+// issued while the tensor pipe is saturated take ~90 cycles each (ncu: 40 % of the epilogue's
+// stall samples were math-pipe throttle with 4 of them per element) and made the FINAL epilogue
+// longer than the mainloop it has to hide behind.  Every factor is held as a 64-bit mantissa with
+// bit 63 set plus a binary exponent, x = m / 2^63 * 2^e; two mul.hi.u64 give the top 64 bits of
+// T * cf * gj (relative truncation error < 2^-60), which are rounded to the 53-bit mantissa of the
+// result: within 0.51 ulp of the exactly rounded product, where the FP64 chain rounded twice.
+__device__ __forceinline__ void split_f64(double x, unsigned long long& m, int& e) {
+  const long long bits = __double_as_longlong(x);
+  const int ex = (int)((bits >> 52) & 0x7ff);
+  const bool ok = bits > 0 && ex != 0 && ex != 0x7ff;          // positive, normal, finite; else 0
+  m = ok ? (((unsigned long long)bits & 0xfffffffffffffull) | (1ull << 52)) << 11 : 0ull;
+  e = ex - 1023;
+}
+// sh = s | dl << 8 | (e_cf + 2048) << 16
+__device__ __forceinline__ int pack_shift(int s, int dl, int e_cf) { return s | (dl << 8) | ((e_cf + 2048) << 16); }
+__device__ __forceinline__ double final_value(unsigned long long D, uint32_t cnt, int sh, unsigned long long m_cf,
+                                              unsigned long long m_gj, int e_gj) {
+  const unsigned long long T = (D << ((sh >> 8) & 0xff)) + ((unsigned long long)cnt << (sh & 0xff));
+  // c = cf * gj = mc / 2^63 * 2^ec
+  unsigned long long mc = __umul64hi(m_cf, m_gj);               // in [2^62, 2^64) or 0
+  int ec = (sh >> 16) - 2048 + e_gj;
+  if ((long long)mc < 0) ++ec; else mc <<= 1;
+  const int z = __clzll((long long)T) & 63;
+  unsigned long long pr = __umul64hi(T << z, mc);               // T * c = pr * 2^(1 - z + ec), pr in [2^62, 2^64)
+  int E = 63 - z + ec;
+  if ((long long)pr < 0) ++E; else pr <<= 1;
+  const int biased = E + 1023;
+  unsigned long long bits = ((unsigned long long)(unsigned)(biased - 1) << 52) + (pr >> 11) + ((pr >> 10) & 1ull);
+  if (T == 0ull || mc == 0ull || biased <= 0) bits = 0ull;      // zero operands, underflow
+  return __longlong_as_double((long long)bits);
 }
 // common-neighbour counts are held as uint16 (or uint32 when a degree can reach 65535)
 __device__ __forceinline__ uint32_t load_count(const void* base, int64_t idx, int c32) {
@@ -323,13 +347,22 @@ __device__ __forceinline__ uint32_t column_max16(const uint32_t (&k)[16], int la
   return max(d, __shfl_xor_sync(0xffffffffu, d, 1));
 }
 __device__ __forceinline__ int column_of_lane(int lane) { return (lane >> 1) & 15; }   // h16*8 + h8*4 + h4*2 + h2
-// bit pattern of |x|, taken with an integer AND (asm: the compiler would turn the C++ form back
-// into a DADD with an |x| modifier, and FP64-pipe instructions are what this epilogue rations)
-__device__ __forceinline__ unsigned long long abs_bits(double x) {
-  unsigned lo, hi;
-  asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "d"(x));
-  asm volatile("and.b32 %0, %0, 0x7fffffff;" : "+r"(hi));
-  return ((unsigned long long)hi << 32) | lo;
+// Bit pattern of |a - b| for two non-negative doubles, formed with integer instructions (see
+// final_value for why): the mantissas are aligned at bit 62, subtracted and renormalised; the
+// result is within one ulp of the exact difference (truncated, never above it).  Inf/NaN -> 0,
+// the reference's `abs(a - b) > eps` is False for NaN as well.
+__device__ __forceinline__ unsigned long long absdiff_bits(double a, double b) {
+  const unsigned long long A = (unsigned long long)__double_as_longlong(a), B = (unsigned long long)__double_as_longlong(b);
+  const unsigned long long hi = A > B ? A : B, lo = A > B ? B : A;
+  const int eh = (int)(hi >> 52), el = (int)(lo >> 52);
+  const int sh = eh - el;
+  const unsigned long long mh = ((hi & 0xfffffffffffffull) | (1ull << 52)) << 10;
+  const unsigned long long ml = (el > 0 && sh < 63) ? (((lo & 0xfffffffffffffull) | (1ull << 52)) << 10) >> sh : 0ull;
+  const unsigned long long d = mh - ml;
+  const int z = __clzll((long long)d) & 63;
+  const int be = eh + 1 - z;
+  const unsigned long long bits = ((unsigned long long)(unsigned)(be - 1) << 52) + ((d << z) >> 11);
+  return (eh == 0 || eh >= 0x7ff || d == 0ull || be <= 0) ? 0ull : bits;
 }
 
 struct Params {
@@ -356,7 +389,6 @@ struct Params {
   unsigned int* sync; int sync_units_per_tile, sync_kb;
   unsigned long long* trace;   // SRK_X2_TRACE (diagnostics): [clusters][trace_tiles][4] globaltimer at mainloop start/end, epilogue start/end
   int trace_tiles;
-  int debug;                   // SRK_X2_DEBUG (profiling experiments only): 1 no S_old, 2 no mirror, 4 no direct store
 };
 
 // Walks the pair tiles in the order: bands of `group_j` row blocks; inside a band the column
@@ -438,7 +470,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tw.init(p);
       tw.advance(cluster_id);
       int stage = 0; uint32_t phase = 0;
-      const uint64_t pol = (p.debug & 16) ? policy_evict_normal() : policy_evict_last();
+      const uint64_t pol = policy_evict_last();
       for (int t = 0; t < my_tiles; ++t) {
         const int j0 = tw.jb * 256 + (int)cta * BMC;
         const int r0 = tw.rb * RT;
@@ -524,7 +556,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const bool sym = p.layout == SRK_X2_SYMMETRIC;
     const bool trans = p.layout == SRK_X2_TRANSPOSED;
     const bool have_old = p.epi.s_old != nullptr;
-    const uint64_t spol = (p.debug & 8) ? policy_evict_normal() : policy_evict_first();
+    const uint64_t spol = policy_evict_first();
     // everything the vectorised paths assume about the caller's buffers (uniform over the grid)
     bool fast_ok = false;
     if (MODE == SRK_X2_FINAL) {
@@ -544,6 +576,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       // per-column factors of this tile (double-buffered; one named barrier per tile)
       double* cf = colfac + (size_t)b * RT;                                 // [2][RT] doubles
       int* shv = reinterpret_cast<int*>(colfac + 2 * RT) + (size_t)b * RT;  // [2][RT] ints
+      const unsigned long long* mcf = reinterpret_cast<const unsigned long long*>(cf);   // FINAL: mantissas
       if (MODE != SRK_X2_COUNTS) {
         for (int c = et; c < RT; c += 128) {
           const int64_t r = r0 + c;
@@ -557,8 +590,11 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               const int fr = pow2_exponent<NS>(bin);
               int s = fr == kNoBound ? 0 : 8 * NS - fr, dl = 0;
               if (s < 0) { dl = -s > 17 ? 17 : -s; s = 0; }
-              sh = s | (dl << 8);
-              f = p.epi.coef * p.g_v[r] * pow2(-s);
+              unsigned long long m_cf;
+              int e_cf;
+              split_f64(p.epi.coef * p.g_v[r] * pow2(-s), m_cf, e_cf);
+              sh = pack_shift(s, dl, e_cf);
+              f = __longlong_as_double((long long)m_cf);        // FINAL keeps the mantissa bits in the slot
             }
           }
           cf[c] = f;
@@ -567,13 +603,14 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         epi_bar_sync();
       }
       unsigned long long rmax = 0ull;                     // FINAL, row-major layouts: max of row j inside this tile
-      double rowf = 0.0;                                  // FINAL: g_a[j]
+      unsigned long long m_gj = 0ull;                     // FINAL: g_a[j] = m_gj / 2^63 * 2^e_gj
+      int e_gj = 0;
       int fj = kNoBound;                                  // MID: exponent of the power-of-two bound of row j
       if (jvalid) {
         if (MODE == SRK_X2_MID) fj = pow2_exponent<NS>(row_bound(p.out_rowbound, j));
-        if (MODE == SRK_X2_FINAL) rowf = p.g_a[j];
+        if (MODE == SRK_X2_FINAL) split_f64(p.g_a[j], m_gj, e_gj);
       }
-      if (MODE == SRK_X2_FINAL && !trans && jvalid && have_old && !(sym && j > r0 + RT - 1) && !(p.debug & 64)) {
+      if (MODE == SRK_X2_FINAL && !trans && jvalid && have_old && !(sym && j > r0 + RT - 1)) {
         // The accumulator of this tile is still being computed: pull the rows of S_old and of the
         // counts that its epilogue will read into L2 now, so that the eight dependent
         // load -> compute -> store rounds below see L2 latency instead of DRAM latency.  (An
@@ -672,16 +709,21 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
         for (int x = 0; x < 16; ++x) key[x] = 0u;
         const int64_t jd = j - p.diag_offset;             // V row that sits on the diagonal with j
-        // Chunks whose 16 elements are all in range, off the diagonal and (symmetric layout) above it
-        // take the vectorised paths; a warp diverges only where its rows meet the diagonal or an
-        // edge, so every tile costs about the same and the CTA pairs stay in step (which is what
-        // keeps their operand panels shared in L2).
-        const bool fast = fast_ok && rc + 16 <= p.R && (jd < rc || (!sym && jd > rc + 15));
+        // Chunks whose 16 elements are all in range take the vectorised paths.  In the row-major
+        // layouts that includes the chunk that holds the diagonal element of row j: its loads are the
+        // same 128-bit loads, only the stores are predicated (symmetric layout: elements left of the
+        // diagonal belong to the mirror image of another tile).  A tile that crosses the diagonal so
+        // costs about as much as any other -- with the pairs in lockstep one slow epilogue per wave
+        // would otherwise set the pace of every wave.
+        const bool in_range = fast_ok && rc + 16 <= p.R;
+        const bool fast_t = in_range && trans && (jd < rc || jd > rc + 15);
+        const bool fast_n = in_range && !trans && !(sym && jd > rc + 15);
         double v[16];
         if (!jvalid) {
           // rows past the end of A8: nothing to store, but stay for the warp-wide reduction
-        } else if (fast && !trans) {
-          // 128-bit loads/stores along the row, no predicates
+        } else if (fast_n) {
+          const int xd = jd < rc ? -1 : (jd > rc + 15 ? 16 : (int)(jd - rc));   // diagonal position, -1 / 16 = none
+          const int x_lo = sym ? xd : -1;                 // symmetric layout: elements x >= xd are this tile's
           uint32_t cv[16];
 #pragma unroll
           for (int x = 0; x < 16; ++x) cv[x] = 0u;
@@ -698,30 +740,35 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
           double so[16];
           const double2* sp = reinterpret_cast<const double2*>(p.epi.s_old + j * p.epi.ld_s_old + rc);
-          if (!(p.debug & 1)) {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) { const double2 d2 = ld_stream_f64x2(sp + x, spol); so[2 * x] = d2.x; so[2 * x + 1] = d2.y; }
-          }
+          for (int x = 0; x < 8; ++x) { const double2 d2 = ld_stream_f64x2(sp + x, spol); so[2 * x] = d2.x; so[2 * x + 1] = d2.y; }
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
             const uint32_t cnt = cv[x];
-            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
+            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], mcf[c0 + x], m_gj, e_gj);
             if (p.use_evidence) val *= evidence_factor(cnt);
-            rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
-            if (!(p.debug & 1)) dmax = umax64(dmax, abs_bits(val - so[x]));
+            if (x == xd) val = 1.0;
+            else if (x > x_lo) rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
+            if (x >= x_lo) dmax = umax64(dmax, absdiff_bits(val, so[x]));
             v[x] = val;
           }
-          double2* op = reinterpret_cast<double2*>(p.out_f64 + j * p.ld_out + rc);
-          if (!(p.debug & 4)) {
+          if (x_lo <= 0) {                                // every element of the chunk is stored
+            double2* op = reinterpret_cast<double2*>(p.out_f64 + j * p.ld_out + rc);
 #pragma unroll
             for (int x = 0; x < 8; ++x) st_stream_f64x2(op + x, v[2 * x], v[2 * x + 1], spol);
+          } else {
+            double* op = p.out_f64 + j * p.ld_out + rc;
+#pragma unroll
+            for (int x = 0; x < 16; ++x)
+              if (x >= x_lo) st_stream_f64(op + x, v[x], spol);
           }
-          if (sym && !(p.debug & 2)) {
+          if (sym) {
             double* mp = p.out_f64 + rc * p.ld_out + j;   // mirror: 32 lanes write 256 contiguous bytes per x
 #pragma unroll
-            for (int x = 0; x < 16; ++x) { st_stream_f64(mp + x * p.ld_out, v[x], spol); key[x] = hi_key(v[x]); }
+            for (int x = 0; x < 16; ++x)
+              if (x > x_lo) { st_stream_f64(mp + x * p.ld_out, v[x], spol); key[x] = hi_key(v[x]); }
           }
-        } else if (fast && trans) {
+        } else if (fast_t) {
           // element (row rc + x, column j): every access is coalesced across the lanes
           uint32_t cnt[16];
           double so[16];
@@ -738,10 +785,10 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           double* op = p.out_f64 + rc * p.ld_out + j;
 #pragma unroll
           for (int x = 0; x < 16; ++x) {
-            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt[x] : 0u, shv[c0 + x], cf[c0 + x], rowf);
+            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt[x] : 0u, shv[c0 + x], mcf[c0 + x], m_gj, e_gj);
             if (p.use_evidence) val *= evidence_factor(cnt[x]);
             omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
-            dmax = umax64(dmax, abs_bits(val - so[x]));
+            dmax = umax64(dmax, absdiff_bits(val, so[x]));
             st_stream_f64(op + x * p.ld_out, val, spol);
             v[x] = val;
           }
@@ -760,7 +807,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const int64_t idx_o = trans ? r * p.ld_out + j : j * p.ld_out + r;
             uint32_t cnt = 0u;
             if (p.counts) cnt = load_count(p.counts, trans ? r * p.ld_counts + j : j * p.ld_counts + r, p.counts32);
-            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], cf[c0 + x], rowf);
+            double val = final_value(combine<NS>(a, x), p.add_counts ? cnt : 0u, shv[c0 + x], mcf[c0 + x], m_gj, e_gj);
             if (p.use_evidence) val *= evidence_factor(cnt);
             else if (p.epi.evidence)
               val *= evidence_factor(trans ? p.epi.evidence[r * p.epi.ld_evidence + j] : p.epi.evidence[j * p.epi.ld_evidence + r]);
@@ -783,7 +830,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (trans && p.mirror_out && r != jd) p.mirror_out[j * p.ld_mirror + p.mirror_col0 + r] = val;
           }
         }
-        if (sym && p.rowmax_hi && !(p.debug & 32)) {      // warp-uniform
+        if (sym && p.rowmax_hi) {                         // warp-uniform
           __syncwarp();
           const uint32_t cm = column_max16(key, lane);
           if (!(lane & 1) && cm > 1u) atomicMax(p.rowmax_hi + rc + column_of_lane(lane), cm);
@@ -899,7 +946,6 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.group_j = 8;
   p.total_tiles = count_tiles(p.tiles_j, p.tiles_r, C::RT, p.layout == SRK_X2_SYMMETRIC);
   p.kblock = (int)a.in_kblock;
-  { const char* e = getenv("SRK_X2_DEBUG"); p.debug = e ? atoi(e) : 0; }
 
   auto kern = i8x2_kernel<NS, MODE>;
   SRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -930,7 +976,8 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
     const int per_tile = kblocks >= 64 ? 4 : 1;
     const int64_t tiles_per_cluster = (p.total_tiles + clusters - 1) / clusters;
     const int64_t need = tiles_per_cluster * per_tile * 4;
-    const bool off = (p.debug & 128) != 0;
+    const char* env = getenv("SRK_X2_LOCKSTEP");                       // "0": let the pairs run free (A/B profiling)
+    const bool off = env && env[0] == '0';
     if (a.sync_ws && a.sync_ws_bytes >= need && clusters > 1 && kblocks >= 16 && !off) {
       p.sync = reinterpret_cast<unsigned int*>(a.sync_ws);
       p.sync_units_per_tile = per_tile;

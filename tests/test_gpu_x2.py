@@ -235,7 +235,8 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False,
     if layout == _lib.SRK_X2_SYMMETRIC:
         assert np.array_equal(got, got.T)
     md, mo = scal.tolist()
-    assert md == np.abs(got - S_old).max()
+    want_md = np.abs(got - S_old).max()                                 # integer subtraction: truncated, < 1 ulp below
+    assert want_md * (1 - 2.0 ** -51) <= md <= want_md
     off = got.copy()
     dmask = (jj == rr + diag_offset).T if trans else (jj == rr + diag_offset)
     off[dmask] = 0.0
