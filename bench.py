@@ -64,6 +64,16 @@ def peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="B200_PROFILING.md fallback")
 
 
+def ncu_traffic(kernel, ns, n, world):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of ``kernel`` from the
+    committed `ncu --set full` capture of this very workload (profiles/ncu_traffic.json, written by
+    scripts/ncu_summary.py); None when no capture matches."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(kernel, {}).get(f"ns{ns}_n{n}_g{world}")
+
+
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
 
@@ -205,7 +215,7 @@ def run_engine(args):
         ach = flops_half / (kernels[dom]["ms"] * 1e-3) / 1e12
         sym = args.mode == "i8" and world == 1 and dom.endswith("final")
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor_sustained"], "traffic": None,
+                "frac": ach / pk["tensor_sustained"], "traffic": ncu_traffic(dom, used[-1], n, world),
                 "peak_kind": f"dense bf16 sustained, {pk['source']}; burst {pk['tensor_burst']}",
                 "executed_int8_tops": ach * used[-1] * (0.5 if sym else 1.0),
                 "note": ("achieved = algorithmic 2n^3 flop of one half-product / mean launch time inside the timed "
@@ -216,7 +226,7 @@ def run_engine(args):
         by = (3 if dom.endswith("final") else 2) * n * n * 8.0 / world
         ach = by / (kernels[dom]["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": ach / pk["hbm"], "traffic": None, "peak_kind": pk["source"],
+                "frac": ach / pk["hbm"], "traffic": ncu_traffic(dom, 0, n, world), "peak_kind": pk["source"],
                 "note": "algorithmic bytes: first half 2 n^2 s, second half 3 n^2 s (s = 8)"}
 
     line = {"metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 6
+#define SRK_ABI_VERSION 7
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -187,7 +187,8 @@ int srk_i8_supported(void);
  *                                       memory of the GPU that owns row j (a peer-mapped pointer over
  *                                       NVLink), so no rank computes both (q,p) and (p,q).
  *                     The diagonal is the element with j == r + diag_offset.
- *                     rowmax_hi (optional, caller-zeroed, one uint32 per output row): receives with
+ *                     rowmax_hi (optional, caller-zeroed, one uint32 per output row -- row j in the row-major
+                     layouts, row r in the transposed one): receives with
  *                     atomicMax a key of the largest off-diagonal value of every row of the result,
  *                     key = high word of the double + 1, so that (double)(key << 32) bounds the row
  *                     within 2^-20: the input of srk_slice_rows_key_f64, which then needs one pass.
@@ -216,7 +217,7 @@ typedef struct srk_x2_args {
   int counts_bits;                                                   /* 16 (default when 0) or 32: element type of counts / out_counts */
   double* out_f64; int64_t ld_out; int64_t diag_offset;              /* FINAL */
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;        /* FINAL, TRANSPOSED: see above */
-  uint32_t* rowmax_hi;                                               /* FINAL, DIRECT/SYMMETRIC: see below */
+  uint32_t* rowmax_hi;                                               /* FINAL: see above */
   srk_epilogue epi;                                                  /* FINAL */
   void* out_counts; int64_t ld_out_counts;                           /* COUNTS */
   /* Optional scratch (device, 4-byte aligned, contents irrelevant, must not be shared by launches
@@ -224,6 +225,9 @@ typedef struct srk_x2_args {
    * they find each other's operand panels in L2.  Used when sync_ws_bytes >= 16 * ceil(tiles /
    * CTA pairs) (1 MB covers every supported size); NULL = pairs run free (same results, slower). */
   void* sync_ws; int64_t sync_ws_bytes;
+  /* FINAL, TRANSPOSED with mirror_out: like rowmax_hi for the rows of the MIRRORED block, one uint32
+   * per A8 row j, updated with atomicMax in the memory of the GPU that owns those rows.        */
+  uint32_t* mirror_rowmax_hi;
 } srk_x2_args;
 int srk_x2_half(const srk_x2_args* args, void* stream);
 

@@ -11,7 +11,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 SRK_I8_MID, SRK_I8_FINAL, SRK_I8_COUNTS = 0, 1, 2
 SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
@@ -74,7 +74,8 @@ class X2Args(C.Structure):
                 ("rowmax_hi", C.c_void_p),
                 ("epi", Epilogue),
                 ("out_counts", C.c_void_p), ("ld_out_counts", C.c_int64),
-                ("sync_ws", C.c_void_p), ("sync_ws_bytes", C.c_int64)]
+                ("sync_ws", C.c_void_p), ("sync_ws_bytes", C.c_int64),
+                ("mirror_rowmax_hi", C.c_void_p)]
 
 
 _P, _I64, _INT, _DBL = C.c_void_p, C.c_int64, C.c_int, C.c_double

@@ -52,9 +52,11 @@ struct Cfg {
   static constexpr int kBoxes = NH / BR;
   static constexpr int kStageBytes = BMC * BK + NH * BK;
   static constexpr int kColfacBytes = 2 * 2 * RT * 8;               // 2 buffers x 2 vectors
-  static constexpr int kStagesRaw = (kSmemLimit - 1024 - 256 - kColfacBytes) / kStageBytes;
+  static constexpr int kMirrorRow = 18;                             // doubles per staged row (16 + pad: 144 B)
+  static constexpr int kMirrorBytes = 4 * 32 * kMirrorRow * 8;      // one 32 x 16 tile per epilogue warp
+  static constexpr int kStagesRaw = (kSmemLimit - 1024 - 256 - kColfacBytes - kMirrorBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kColfacBytes + 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kColfacBytes + 256 + kMirrorBytes;
   static_assert(N % 32 == 0 && N <= 256, "invalid UMMA N for cta_group::2 kind::i8");
   static_assert(NH % BR == 0 && RT % BR == 0, "box rows must divide the CTA half and the plane block");
   static_assert(kStages >= 3, "not enough shared memory for a pipeline");
@@ -378,6 +380,7 @@ struct Params {
   double* out_f64; int64_t ld_out; int64_t diag_offset;
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;
   uint32_t* rowmax_hi;
+  uint32_t* mirror_rowmax_hi;
   EpilogueDev epi;
   double* maxdiff; double* maxoff;
   // COUNTS
@@ -440,6 +443,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* tmem_full = empty_bar + kStages;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  double* mirror_stage = reinterpret_cast<double*>(smem + kStages * C::kStageBytes + C::kColfacBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();
@@ -708,6 +712,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint32_t key[16];
 #pragma unroll
         for (int x = 0; x < 16; ++x) key[x] = 0u;
+        bool staged = false;                              // this lane's mirror values are in the warp's staging tile
         const int64_t jd = j - p.diag_offset;             // V row that sits on the diagonal with j
         // Chunks whose 16 elements are all in range take the vectorised paths.  In the row-major
         // layouts that includes the chunk that holds the diagonal element of row j: its loads are the
@@ -787,15 +792,21 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           for (int x = 0; x < 16; ++x) {
             double val = final_value(combine<NS>(a, x), p.add_counts ? cnt[x] : 0u, shv[c0 + x], mcf[c0 + x], m_gj, e_gj);
             if (p.use_evidence) val *= evidence_factor(cnt[x]);
-            omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
+            rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
             dmax = umax64(dmax, absdiff_bits(val, so[x]));
             st_stream_f64(op + x * p.ld_out, val, spol);
+            key[x] = hi_key(val);
             v[x] = val;
           }
-          if (p.mirror_out) {                             // (row j, columns rc..) of the owner of row j
-            double2* mp = reinterpret_cast<double2*>(p.mirror_out + j * p.ld_mirror + p.mirror_col0 + rc);
+          if (p.mirror_out) {
+            // (row j, columns rc..rc+15) of the GPU that owns row j: 128 contiguous bytes per lane.
+            // Stored lane by lane that is 32 x 16 B pieces per instruction; over NVLink every piece is
+            // its own write packet.  The warp stages the 32 x 16 tile in shared memory instead and
+            // writes it out as whole 128-byte lines, four rows per instruction (below).
+            double2* sm = reinterpret_cast<double2*>(mirror_stage + (ew * 32 + lane) * C::kMirrorRow);
 #pragma unroll
-            for (int x = 0; x < 8; ++x) st_stream_f64x2(mp + x, v[2 * x], v[2 * x + 1], spol);
+            for (int x = 0; x < 8; ++x) sm[x] = make_double2(v[2 * x], v[2 * x + 1]);
+            staged = true;
           }
         } else if (!(sym && jd > rc + 15)) {              // (strictly below the diagonal: mirrored from above)
           // ---- general path: chunks that touch the diagonal or an edge, priors, uint8 evidence
@@ -816,9 +827,8 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     p.epi.lambda * (trans ? p.epi.prior[r * p.epi.ld_prior + j] : p.epi.prior[j * p.epi.ld_prior + r]);
             if (r == jd) val = 1.0;
             else if (val > 0.0) {
-              if (trans) omax = umax64(omax, (unsigned long long)__double_as_longlong(val));
-              else rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
-              if (sym) key[x] = hi_key(val);              // r > jd here: this value is mirrored to row r
+              rmax = umax64(rmax, (unsigned long long)__double_as_longlong(val));
+              if (sym || trans) key[x] = hi_key(val);     // symmetric: r > jd here, the value is mirrored to row r
             }
             if (have_old) {
               const double so = trans ? p.epi.s_old[r * p.epi.ld_s_old + j] : p.epi.s_old[j * p.epi.ld_s_old + r];
@@ -830,16 +840,35 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (trans && p.mirror_out && r != jd) p.mirror_out[j * p.ld_mirror + p.mirror_col0 + r] = val;
           }
         }
-        if (sym && p.rowmax_hi) {                         // warp-uniform
+        if ((sym || trans) && p.rowmax_hi) {              // warp-uniform
+          // symmetric: keys of the values mirrored into rows rc + x; transposed: rows rc + x of the output
           __syncwarp();
           const uint32_t cm = column_max16(key, lane);
           if (!(lane & 1) && cm > 1u) atomicMax(p.rowmax_hi + rc + column_of_lane(lane), cm);
+        }
+        if (trans && p.mirror_out) {                      // warp-uniform
+          const unsigned smask = __ballot_sync(0xffffffffu, staged);
+          if (smask) {
+            const int64_t jw = jc0 + ew * 32;             // A8 row of lane 0
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = 4 * i + (lane >> 3), piece = lane & 7;
+              if ((smask >> row) & 1u) {
+                const double2 d = *reinterpret_cast<const double2*>(mirror_stage + (ew * 32 + row) * C::kMirrorRow + 2 * piece);
+                st_stream_f64x2(reinterpret_cast<double2*>(p.mirror_out + (jw + row) * p.ld_mirror + p.mirror_col0 + rc) + piece,
+                                d.x, d.y, spol);
+              }
+            }
+            __syncwarp();                                 // the tile is rewritten by the next chunk
+          }
         }
       }
       if (tracing) p.trace[((size_t)cluster_id * p.trace_tiles + t) * 4 + 3] = globaltimer_ns();
       if (MODE == SRK_X2_FINAL && rmax) {
         omax = umax64(omax, rmax);
-        if (p.rowmax_hi) atomicMax(p.rowmax_hi + j, (uint32_t)(rmax >> 32) + 1u);
+        // row j of the result (row-major layouts) / of the mirrored block (transposed layout)
+        uint32_t* rk = trans ? (p.mirror_out ? p.mirror_rowmax_hi : nullptr) : p.rowmax_hi;
+        if (rk) atomicMax(rk + j, (uint32_t)(rmax >> 32) + 1u);
       }
       tw.advance(num_clusters);
     }
@@ -938,6 +967,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.out_f64 = a.out_f64; p.ld_out = a.ld_out; p.diag_offset = a.diag_offset;
   p.mirror_out = a.mirror_out; p.ld_mirror = a.ld_mirror; p.mirror_col0 = a.mirror_col0;
   p.rowmax_hi = a.rowmax_hi;
+  p.mirror_rowmax_hi = a.mirror_rowmax_hi;
   p.epi = to_dev(a.epi);
   p.maxdiff = a.epi.maxdiff; p.maxoff = a.epi.maxoff;
   p.out_counts = a.out_counts; p.ld_out_counts = a.ld_out_counts;
@@ -1059,7 +1089,7 @@ extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
     } else {
       SRK_REQUIRE(a->ld_out >= a->R, "ld_out smaller than R");
     }
-    SRK_REQUIRE(!a->rowmax_hi || a->layout != SRK_X2_TRANSPOSED, "rowmax_hi needs a row-major layout");
+    SRK_REQUIRE(!a->mirror_rowmax_hi || a->mirror_out, "mirror_rowmax_hi without mirror_out");
     SRK_REQUIRE(!a->mirror_out || (a->layout == SRK_X2_TRANSPOSED && a->ld_mirror >= a->mirror_col0 + a->R),
                 "mirror_out needs the transposed layout and ld_mirror >= mirror_col0 + R");
     if (a->layout == SRK_X2_SYMMETRIC)

@@ -172,6 +172,9 @@ class ShardedHalf:
         self._init_identity()
         self.U, self.U_ptrs = self.ex.alloc((self.ns_alloc, self.per, self.ldu), torch.uint8, dev)
         self.planes = None
+        # keys of the row maxima of the local rows of S, collected by the FINAL epilogues of every rank
+        # that writes into them (peer mode; the staged fallback takes the maxima in the slicer)
+        self.rowmax, self.rowmax_ptrs = self.ex.alloc((self.per,), torch.int32, dev) if self.ex.peer else (None, None)
         self.bound_vec = torch.zeros(self.per, dtype=torch.float64, device=dev)
         self.scal = torch.zeros(2, dtype=torch.float64, device=dev)
         self.maxoff = 0.0
@@ -209,6 +212,11 @@ class ShardedHalf:
         _lib.check(_lib.load().srk_x2_half(C.byref(args), _stream()), name)
 
     def _launch_slice(self, ns: int):
+        if self.rowmax is not None:                               # one pass: the maxima are known
+            _lib.check(_lib.load().srk_slice_rows_key_f64(
+                _ptr(self.S), self.ld, self.rows, self.n_out, self.row0, ns, _ptr(self.rowmax), _ptr(self.planes),
+                self.ldp, self.planes.stride(0), _ptr(self.bound_vec), _stream()), "srk_slice_rows_key_f64")
+            return
         _lib.check(_lib.load().srk_slice_rows_max_f64(
             _ptr(self.S), self.ld, self.rows, self.n_out, self.row0, ns, _ptr(self.planes), self.ldp,
             self.planes.stride(0), _ptr(self.bound_vec), _stream()), "srk_slice_rows_max_f64")
@@ -249,7 +257,7 @@ class ShardedHalf:
             self._sliced = (-1, 0)
         if self._sliced != (self.version, ns):
             if self.rows:
-                self._timed("slice_rows_max", lambda: self._launch_slice(ns))
+                self._timed("slice_rows_key" if self.rowmax is not None else "slice_rows_max", lambda: self._launch_slice(ns))
             self._sliced = (self.version, ns)
         return self.planes
 
@@ -321,6 +329,8 @@ class ShardedHalf:
             if self.prior is not None:
                 e.prior = self.prior.data_ptr() + 8 * (r_lo * self.prior.stride(0) + col0)
                 e.ld_prior, e.lambda_ = self.prior.stride(0), self.lbd
+            if self.rowmax is not None:
+                b.rowmax_hi = self.rowmax.data_ptr() + 4 * r_lo    # own block: r_lo == j_lo == 0
             if own:
                 b.layout, b.diag_offset = _lib.SRK_X2_SYMMETRIC, 0
             else:
@@ -331,6 +341,7 @@ class ShardedHalf:
                     if self.ex.peer:                               # rows j of rank p's S, my columns
                         b.mirror_out = self.S_ptrs[p] + 8 * (j_lo * self.ld)
                         b.ld_mirror, b.mirror_col0 = self.ld, self.row0 + r_lo
+                        b.mirror_rowmax_hi = self.rowmax_ptrs[p] + 4 * j_lo
                     else:
                         b.mirror_out = self.mirror_send[p].data_ptr() + 8 * (j_lo * self.per)
                         b.ld_mirror, b.mirror_col0 = self.per, r_lo
@@ -364,6 +375,8 @@ class ShardedHalf:
         guard = 1.0 + 2.0 ** -14
         bound_mul = src.maxoff * guard                             # U[j, :] <= deg_j * max(S_off)
         self._timed("x2_half_mid", lambda: self._mid(src, ns, bound_mul))
+        if self.rowmax is not None:
+            self.rowmax.zero_()          # after the slice inside _mid read the old keys, before the barrier
         self._timed("exchange", lambda: self._exchange_U(src, ns))
         self._timed("x2_half_final", lambda: self._final(ns, bound_mul))
         self._timed("mirror_exchange", self._exchange_mirrors)

@@ -53,7 +53,15 @@ def _pow2_exponent(b, ns):
     return np.maximum(f, 8 * ns - 40).astype(np.int64)
 
 
+def _exact_matmul(A, q):
+    """A (0/1) @ q.T as exact int64: through BLAS in float64 while every sum stays below 2^53."""
+    if q.size and float(q.max()) * A.shape[1] < 2.0 ** 52:
+        return np.rint(A.astype(np.float64) @ q.T.astype(np.float64)).astype(np.int64)
+    return A.astype(np.int64) @ q.T
+
+
 def _run(a):
+    engine.attach_sync_ws(a, torch.device("cuda", torch.cuda.current_device()))   # lockstep scratch (used from K >= 2048)
     _lib.check(_lib.load().srk_x2_half(C.byref(a), engine._stream()), "srk_x2_half")
     torch.cuda.synchronize()
 
@@ -127,7 +135,7 @@ def test_x2_mid_against_integer_matmul(dev, ns, M, R, K):
     a.out_planes, a.ld_outp, a.out_plane_stride = out.data_ptr(), ldr, M * ldr
     a.out_rowbound = _lib.RowBound.of(out_vec.data_ptr(), 30.0, 1.0)
     _run(a)
-    D = (A.astype(np.int64) @ q.T).astype(np.float64)                  # [M, R] exact
+    D = _exact_matmul(A, q).astype(np.float64)                          # [M, R] exact
     inb = in_vec.cpu().numpy() * 0.9
     outb = out_vec.cpu().numpy() * 30.0 + 1.0
     fj = _pow2_exponent(outb, ns)
@@ -192,18 +200,18 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False,
         pr = torch.from_numpy(prior).to(dev)
         keep.append(pr)
         e.prior, e.ld_prior, e.lambda_ = pr.data_ptr(), cols, 0.25
-    rk = None
-    if not trans:                                                       # keys of the row maxima
-        rk = torch.zeros(rows, dtype=torch.int32, device=dev)
-        a.rowmax_hi = rk.data_ptr()
-    mir = None
+    rk = torch.zeros(rows, dtype=torch.int32, device=dev)               # keys of the row maxima of the output
+    a.rowmax_hi = rk.data_ptr()
+    mir = mrk = None
     if mirror:                                                          # the block as its owner stores it
         ldm = engine._round_up(R + 6, 2)
         mir = torch.full((M, ldm), -3.0, dtype=torch.float64, device=dev)
         a.mirror_out, a.ld_mirror, a.mirror_col0 = mir.data_ptr(), ldm, 6
+        mrk = torch.zeros(M, dtype=torch.int32, device=dev)             # ... and of the mirrored block
+        a.mirror_rowmax_hi = mrk.data_ptr()
     _run(a)
     # ---- numpy restatement, in the (j, r) frame of the kernel
-    D = A.astype(np.int64) @ q.T                                        # [M, R] exact
+    D = _exact_matmul(A, q)                                             # [M, R] exact
     inb = (in_vec.cpu().numpy() * 2.0 + 1.0) * bscale
     s = 8 * ns - _pow2_exponent(inb, ns)                                # bounds of U are powers of two
     dl = np.maximum(-s, 0)
@@ -241,10 +249,10 @@ def _final_case(rng, ns, M, R, K, layout, extras, dev, bscale=1.0, mirror=False,
     dmask = (jj == rr + diag_offset).T if trans else (jj == rr + diag_offset)
     off[dmask] = 0.0
     assert mo == off.max()
-    if rk is not None:
-        m = off.max(axis=1)
-        want_key = np.where(m > 0, (m.view(np.int64) >> 32) + 1, 0)
-        np.testing.assert_array_equal(rk.cpu().numpy().astype(np.int64), want_key)
+    for keys, m in ((rk, off.max(axis=1)), (mrk, off.max(axis=0))):
+        if keys is not None:
+            want_key = np.where(m > 0, (m.view(np.int64) >> 32) + 1, 0)
+            np.testing.assert_array_equal(keys.cpu().numpy().astype(np.int64), want_key)
     assert not S[:, cols:].cpu().numpy().any()                          # nothing written past the matrix
 
 
@@ -324,7 +332,7 @@ def test_x2_kblocked_operand(dev):
     a.out_planes, a.ld_outp, a.out_plane_stride = out.data_ptr(), ldr, M * ldr
     a.out_rowbound = _lib.RowBound.of(None, 0.0, float(K))
     _run(a)
-    D = (A.astype(np.int64) @ q.T).astype(np.float64)
+    D = _exact_matmul(A, q).astype(np.float64)
     fj = int(_pow2_exponent(float(K), ns))
     want = np.clip(np.rint(D * 2.0 ** -fj), 0, qmax - 1).astype(np.int64)
     got = _join(out.cpu().numpy(), ns)[:, :R]
@@ -337,6 +345,17 @@ def test_x2_many_tiles_per_pair(dev):
     shared-memory ring wrap-around and the symmetric tile walk across several bands."""
     _final_case(np.random.default_rng(77), 2, 5000, 5000, 384, _lib.SRK_X2_SYMMETRIC, "counts", dev)
     _final_case(np.random.default_rng(78), 3, 4100, 3000, 256, _lib.SRK_X2_DIRECT, "none", dev)
+
+
+@needs_i8
+def test_x2_lockstep_long_k(dev):
+    """K >= 2048 with the scratch attached: the CTA pairs throttle each other through the progress
+    counters (four units per tile); results must not depend on it, the launch must not hang, and a
+    second launch must find the counters reset."""
+    for _ in range(2):
+        _final_case(np.random.default_rng(91), 2, 2304, 2304, 8192, _lib.SRK_X2_SYMMETRIC, "counts", dev)
+    _final_case(np.random.default_rng(92), 3, 1100, 2100, 4096, _lib.SRK_X2_TRANSPOSED, "evidence", dev, mirror=True)
+    test_x2_mid_against_integer_matmul(dev, 2, 2600, 1300, 2176)
 
 
 @pytest.mark.parametrize("ns", [1, 2, 3, 4])
