@@ -222,7 +222,7 @@ typedef struct srk_x2_args {
   void* out_counts; int64_t ld_out_counts;                           /* COUNTS */
   /* Optional scratch (device, 4-byte aligned, contents irrelevant, must not be shared by launches
    * that can overlap): progress counters that keep the CTA pairs of a launch at the same k, so that
-   * they find each other's operand panels in L2.  Used when sync_ws_bytes >= 16 * ceil(tiles /
+   * they find each other's operand panels in L2.  Used when sync_ws_bytes >= 32 * ceil(tiles /
    * CTA pairs) (1 MB covers every supported size); NULL = pairs run free (same results, slower). */
   void* sync_ws; int64_t sync_ws_bytes;
   /* FINAL, TRANSPOSED with mirror_out: like rowmax_hi for the rows of the MIRRORED block, one uint32

@@ -1,9 +1,9 @@
 #!/bin/bash
-# A/B of the lockstep throttle of the paired-SM kernel: SRK_X2_LOCKSTEP=0 lets the CTA pairs run free.
+# A/B of the lockstep throttle of the paired-SM kernel: SRK_X2_LOCKSTEP=0 lets the CTA pairs run
+# free, "units,lag" changes the granularity (default 4,1).  usage: gpu_exp.sh [settings...]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-echo "== x2 unit tests"; timeout -k 5 200 python -m pytest tests/test_gpu_x2.py -x -q 2>&1 | tail -3
-for d in ${@:-1 0}; do
+for d in ${@:-4,1 0}; do
   echo "== SRK_X2_LOCKSTEP=$d"
   SRK_X2_LOCKSTEP=$d timeout -k 5 200 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
 import json,sys

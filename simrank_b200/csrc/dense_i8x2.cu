@@ -389,7 +389,7 @@ struct Params {
   int tiles_j, tiles_r, group_j, total_tiles;
   int kblock;
   // lockstep of the CTA pairs (see "lockstep" in the producer): units of `sync_kb` K-blocks
-  unsigned int* sync; int sync_units_per_tile, sync_kb;
+  unsigned int* sync; int sync_units_per_tile, sync_kb, sync_lag;
   unsigned long long* trace;   // SRK_X2_TRACE (diagnostics): [clusters][trace_tiles][4] globaltimer at mainloop start/end, epilogue start/end
   int trace_tiles;
 };
@@ -485,17 +485,18 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             // apart by several tiles (memory-bound pairs run at slightly different speeds and nothing
             // ever re-aligns them) and every pair streams its panels from DRAM: measured 140 GB per
             // FINAL launch instead of 35 GB.  So progress is counted in units of sync_kb K-blocks and a
-            // pair starts unit u only after every pair that has a unit u-1 started it.  The wait is
+            // pair starts unit u only after every pair that has a unit u-lag started it.  The wait is
             // bounded: this is a performance hint, never a correctness dependency.
             const int unit = t * p.sync_units_per_tile + kb / p.sync_kb;
             red_add_gpu(p.sync + unit);
-            if (unit > 0) {
-              const int pt = (unit - 1) / p.sync_units_per_tile;               // tile index of the previous unit
+            if (unit >= p.sync_lag) {
+              const int prev = unit - p.sync_lag;
+              const int pt = prev / p.sync_units_per_tile;                     // tile index of that unit
               const int left = p.total_tiles - pt * num_clusters;
               const unsigned int expect = (unsigned int)(left < num_clusters ? left : num_clusters);
-              if (ld_relaxed_gpu(p.sync + unit - 1) < expect) {
+              if (ld_relaxed_gpu(p.sync + prev) < expect) {
                 const unsigned long long t_in = globaltimer_ns();
-                while (ld_relaxed_gpu(p.sync + unit - 1) < expect && globaltimer_ns() - t_in < 1000000ull) {}
+                while (ld_relaxed_gpu(p.sync + prev) < expect && globaltimer_ns() - t_in < 1000000ull) {}
               }
             }
           }
@@ -1001,16 +1002,21 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   if (clusters < 1) return SRK_OK;
   cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
   {
-    // lockstep workspace: one counter per (tile index, quarter of the K loop)
+    // lockstep workspace: one counter per (tile index, eighth of the K loop)
     const int kblocks = (int)((a.K + BK - 1) / BK);
-    const int per_tile = kblocks >= 64 ? 4 : 1;
-    const int64_t tiles_per_cluster = (p.total_tiles + clusters - 1) / clusters;
-    const int64_t need = tiles_per_cluster * per_tile * 4;
     const char* env = getenv("SRK_X2_LOCKSTEP");                       // "0": let the pairs run free (A/B profiling)
     const bool off = env && env[0] == '0';
+    int per_tile = kblocks >= 128 ? 8 : (kblocks >= 64 ? 4 : 1), lag = 1;     // 4..8 units per tile measured equal within 2 %
+    if (env && env[0] != '0' && kblocks >= 64) sscanf(env, "%d,%d", &per_tile, &lag);   // A/B profiling: "units,lag"
+    if (per_tile < 1 || per_tile > kblocks) per_tile = 1;
+    if (lag < 1) lag = 1;
+    const int64_t tiles_per_cluster = (p.total_tiles + clusters - 1) / clusters;
+    const int64_t need = tiles_per_cluster * per_tile * 4;
+
     if (a.sync_ws && a.sync_ws_bytes >= need && clusters > 1 && kblocks >= 16 && !off) {
       p.sync = reinterpret_cast<unsigned int*>(a.sync_ws);
       p.sync_units_per_tile = per_tile;
+      p.sync_lag = lag;
       p.sync_kb = (kblocks + per_tile - 1) / per_tile;
       SRK_CUDA_OK(cudaMemsetAsync(a.sync_ws, 0, (size_t)need, st));
     }

@@ -167,14 +167,23 @@ class ShardedHalf:
         self.ns_alloc = 3 if ns in (None, "auto") else int(ns)
         self.ex = exchange if exchange is not None else make_exchange(device, group)
         dev = device
-        # S and the row panel of U are written by other ranks in peer mode
-        self.S, self.S_ptrs = self.ex.alloc((self.per, self.ld), torch.float64, dev)
+        # S, the row panel of U and the row-maximum keys are written by other ranks in peer mode: one
+        # peer-mapped arena per matrix (a symmetric-memory rendezvous costs ~0.1 s whatever its size)
+        s_bytes = self.per * self.ld * 8
+        u_bytes = self.ns_alloc * self.per * self.ldu
+        k_bytes = _round_up(self.per * 4, 256)
+        arena, ptrs = self.ex.alloc((_round_up(s_bytes, 256) + _round_up(u_bytes, 256) + k_bytes,), torch.uint8, dev)
+        o_u, o_k = _round_up(s_bytes, 256), _round_up(s_bytes, 256) + _round_up(u_bytes, 256)
+        self.S = arena[:s_bytes].view(torch.float64).view(self.per, self.ld)
+        self.U = arena[o_u:o_u + u_bytes].view(self.ns_alloc, self.per, self.ldu)
+        self.S_ptrs = ptrs and [q for q in ptrs]
+        self.U_ptrs = ptrs and [q + o_u for q in ptrs]
         self._init_identity()
-        self.U, self.U_ptrs = self.ex.alloc((self.ns_alloc, self.per, self.ldu), torch.uint8, dev)
         self.planes = None
         # keys of the row maxima of the local rows of S, collected by the FINAL epilogues of every rank
         # that writes into them (peer mode; the staged fallback takes the maxima in the slicer)
-        self.rowmax, self.rowmax_ptrs = self.ex.alloc((self.per,), torch.int32, dev) if self.ex.peer else (None, None)
+        self.rowmax = arena[o_k:o_k + self.per * 4].view(torch.int32) if self.ex.peer else None
+        self.rowmax_ptrs = ptrs and [q + o_k for q in ptrs]
         self.bound_vec = torch.zeros(self.per, dtype=torch.float64, device=dev)
         self.scal = torch.zeros(2, dtype=torch.float64, device=dev)
         self.maxoff = 0.0
