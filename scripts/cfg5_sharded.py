@@ -20,8 +20,33 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from simrank_b200 import synth  # noqa: E402
+from simrank_b200 import drivers, synth  # noqa: E402
 from SimRank import SimRank as M  # noqa: E402
+
+
+def record_launches():
+    """Make every solver built from here on collect CUDA events per launch; -> list of solvers."""
+    made, orig = [], drivers.bipartite_solver
+
+    def wrapped(*a, **k):
+        s = orig(*a, **k)
+        for h in (s.h1, s.h2):
+            h.events = []
+        made.append(s)
+        return s
+
+    drivers.bipartite_solver = wrapped
+    return made
+
+
+def launch_times(solver):
+    out = {}
+    for name, h in (("S1", solver.h1), ("S2", solver.h2)):
+        per = {}
+        for nm, a, b in h.events:
+            per.setdefault(nm, []).append(round(a.elapsed_time(b), 2))
+        out[name] = {"ms": per, "slices": list(h.slices_used)}
+    return out
 
 
 def load_edges(scale):
@@ -45,6 +70,7 @@ def main():
     t0 = time.perf_counter()
     df = load_edges(scale)
     t_data = time.perf_counter() - t0
+    made = record_launches()
     obj = M.BipartitleSimRankPP(mode="i8", gather="local", result="device")
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -56,7 +82,7 @@ def main():
     out = {"scale": scale, "K": K, "world": world, "edges": len(df), "n1": len(res.labels[0]), "n2": len(res.labels[1]),
            "seconds_data": round(t_data, 2), "seconds_fit": round(t_fit, 3), "stages_s": obj.fit_timings_,
            "iterate_s_per_iteration": obj.fit_timings_["iterate"] / K, "mode": obj.fit_info_.mode,
-           "last_maxdiff": list(obj.fit_info_.last)}
+           "last_maxdiff": list(obj.fit_info_.last_maxdiff), "launches": launch_times(made[0])}
     ok = True
     for name, S, a, b in (("S1", S1, a1, b1), ("S2", S2, a2, b2)):
         if b > a:
