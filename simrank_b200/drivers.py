@@ -198,7 +198,7 @@ def collect(solver, labels, gather: str = "all") -> Result:
     row blocks (``gather="local"``: rank r returns rows ``plan.start(r):plan.stop(r)`` of each
     matrix, nothing crosses NVLink or PCIe twice)."""
     halves = getattr(solver, "halves", None)
-    pair = hasattr(solver, "S1")
+    pair = hasattr(type(solver), "S1")          # on the class: the property getter all-gathers the matrix
     if halves is None or gather == "all":
         return Result([solver.S1, solver.S2] if pair else [solver.S], labels)
     if gather != "local":
