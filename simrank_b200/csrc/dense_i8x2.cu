@@ -143,6 +143,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* a, uint64_t pol) {
   double2 v;
   asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
@@ -390,6 +395,7 @@ struct Params {
   int kblock;
   // lockstep of the CTA pairs (see "lockstep" in the producer): units of `sync_kb` K-blocks
   unsigned int* sync; int sync_units_per_tile, sync_kb, sync_lag;
+  int flags;                   // SRK_X2_FLAGS (A/B profiling): 1 = operand loads, 2 = epilogue streams with the default L2 policy
   unsigned long long* trace;   // SRK_X2_TRACE (diagnostics): [clusters][trace_tiles][4] globaltimer at mainloop start/end, epilogue start/end
   int trace_tiles;
 };
@@ -474,30 +480,42 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tw.init(p);
       tw.advance(cluster_id);
       int stage = 0; uint32_t phase = 0;
-      const uint64_t pol = policy_evict_last();
+      const uint64_t pol = (p.flags & 1) ? policy_evict_normal() : policy_evict_last();
+      unsigned int peek = 0u;                              // lockstep: counter of unit peek_unit, read ahead
+      int peek_unit = -1;
       for (int t = 0; t < my_tiles; ++t) {
         const int j0 = tw.jb * 256 + (int)cta * BMC;
         const int r0 = tw.rb * RT;
+        int sync_next = 0, peek_next = p.sync_kb >> 1, unit_in_tile = 0;   // K-blocks of the next boundary / look-ahead
         for (int kb = 0; kb < kblocks; ++kb) {
-          if (p.sync && cta == 0 && kb % p.sync_kb == 0) {
+          if (p.sync && cta == 0) {
             // Lockstep.  The ~74 pairs of a wave read the same few operand panels; they only find
             // each other's lines in L2 while they are at about the same k.  Left alone they drift
             // apart by several tiles (memory-bound pairs run at slightly different speeds and nothing
             // ever re-aligns them) and every pair streams its panels from DRAM: measured 140 GB per
             // FINAL launch instead of 35 GB.  So progress is counted in units of sync_kb K-blocks and a
-            // pair starts unit u only after every pair that has a unit u-lag started it.  The wait is
+            // pair starts unit u only after every pair that has a unit u-lag started it.  The counter
+            // is read half a unit ahead (the load is in flight while the next K-blocks are issued), so
+            // in step the boundary costs nothing; only a pair that runs ahead polls.  The wait is
             // bounded: this is a performance hint, never a correctness dependency.
-            const int unit = t * p.sync_units_per_tile + kb / p.sync_kb;
-            red_add_gpu(p.sync + unit);
-            if (unit >= p.sync_lag) {
+            if (kb == sync_next) {
+              const int unit = t * p.sync_units_per_tile + unit_in_tile;
+              sync_next += p.sync_kb;
+              red_add_gpu(p.sync + unit);
               const int prev = unit - p.sync_lag;
-              const int pt = prev / p.sync_units_per_tile;                     // tile index of that unit
-              const int left = p.total_tiles - pt * num_clusters;
-              const unsigned int expect = (unsigned int)(left < num_clusters ? left : num_clusters);
-              if (ld_relaxed_gpu(p.sync + prev) < expect) {
-                const unsigned long long t_in = globaltimer_ns();
-                while (ld_relaxed_gpu(p.sync + prev) < expect && globaltimer_ns() - t_in < 1000000ull) {}
+              if (prev >= 0) {
+                const int left = p.total_tiles - (prev / p.sync_units_per_tile) * num_clusters;
+                const unsigned int expect = (unsigned int)(left < num_clusters ? left : num_clusters);
+                if (!(peek_unit == prev && peek >= expect) && ld_relaxed_gpu(p.sync + prev) < expect) {
+                  const unsigned long long t_in = globaltimer_ns();
+                  while (ld_relaxed_gpu(p.sync + prev) < expect && globaltimer_ns() - t_in < 1000000ull) {}
+                }
               }
+            } else if (kb == peek_next) {
+              peek_next += p.sync_kb;
+              peek_unit = t * p.sync_units_per_tile + unit_in_tile + 1 - p.sync_lag;
+              ++unit_in_tile;
+              if (peek_unit >= 0) peek = ld_relaxed_gpu(p.sync + peek_unit);
             }
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -561,7 +579,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const bool sym = p.layout == SRK_X2_SYMMETRIC;
     const bool trans = p.layout == SRK_X2_TRANSPOSED;
     const bool have_old = p.epi.s_old != nullptr;
-    const uint64_t spol = policy_evict_first();
+    const uint64_t spol = (p.flags & 2) ? policy_evict_normal() : policy_evict_first();
     // everything the vectorised paths assume about the caller's buffers (uniform over the grid)
     bool fast_ok = false;
     if (MODE == SRK_X2_FINAL) {
@@ -977,6 +995,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.group_j = 8;
   p.total_tiles = count_tiles(p.tiles_j, p.tiles_r, C::RT, p.layout == SRK_X2_SYMMETRIC);
   p.kblock = (int)a.in_kblock;
+  { const char* e = getenv("SRK_X2_FLAGS"); p.flags = e ? atoi(e) : 0; }
 
   auto kern = i8x2_kernel<NS, MODE>;
   SRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -1006,9 +1025,9 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
     const int kblocks = (int)((a.K + BK - 1) / BK);
     const char* env = getenv("SRK_X2_LOCKSTEP");                       // "0": let the pairs run free (A/B profiling)
     const bool off = env && env[0] == '0';
-    int per_tile = kblocks >= 128 ? 8 : (kblocks >= 64 ? 4 : 1), lag = 1;     // 4..8 units per tile measured equal within 2 %
+    int per_tile = kblocks >= 256 ? 8 : (kblocks >= 32 ? kblocks / 32 : 1), lag = 1;   // units of >= 32 K-blocks
     if (env && env[0] != '0' && kblocks >= 64) sscanf(env, "%d,%d", &per_tile, &lag);   // A/B profiling: "units,lag"
-    if (per_tile < 1 || per_tile > kblocks) per_tile = 1;
+    if (per_tile < 1 || per_tile > kblocks / 2) per_tile = 1;          // a unit spans >= 2 K-blocks (boundary + look-ahead)
     if (lag < 1) lag = 1;
     const int64_t tiles_per_cluster = (p.total_tiles + clusters - 1) / clusters;
     const int64_t need = tiles_per_cluster * per_tile * 4;
