@@ -243,6 +243,11 @@ def run_engine(args):
 
     clk = clocks.summary()
     if world > 1:
+        # the per-kernel times above are rank 0's; the spread over the ranks shows who waits for whom
+        every = [None] * world
+        dist.all_gather_object(every, {k: v["ms"] for k, v in kernels.items()})
+        line["kernels_rank_spread_ms"] = {k: [round(min(e.get(k, 0.0) for e in every), 3),
+                                              round(max(e.get(k, 0.0) for e in every), 3)] for k in kernels}
         gathered = [None] * world
         dist.all_gather_object(gathered, clk)
         mhz = [g["sm_mhz"] for g in gathered if g["sm_mhz"]]

@@ -65,6 +65,8 @@ def stall_page(rep, top=12):
             for h in stalls:
                 agg[h] += int(r[ix[h]])
         hot = sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:top]
+        if any(o["kernel"] == rows[s][1] and o["samples"] == total for o in out):
+            continue                      # the source page lists every function twice
         out.append({"kernel": rows[s][1], "samples": total,
                     "stall_share": {k: round(v / total, 4) for k, v in agg.most_common(8)},
                     "hottest": [{"sass": r[1].strip(), "samples": int(r[ix["# Samples"]]),

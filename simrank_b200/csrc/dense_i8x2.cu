@@ -439,7 +439,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_v, const Params p) {
   using C = Cfg<NS>;
   constexpr int RT = C::RT, N = C::N, kStages = C::kStages;
-  constexpr double kQ = (double)(1ull << (8 * NS));
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -654,6 +653,17 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const bool tracing = p.trace && t < p.trace_tiles && cta == 0 && et == 0;
       if (tracing) p.trace[((size_t)cluster_id * p.trace_tiles + t) * 4 + 2] = globaltimer_ns();
 
+      // MID keeps the packed planes of its whole row (RT bytes per plane) in registers until the tile is
+      // done, then the warp writes them out as whole lines (below); that needs a fully unrolled loop.
+      uint4 wq[MODE == SRK_X2_MID ? NS : 1][RT / 16];
+      if (MODE == SRK_X2_MID) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int c = 0; c < RT / 16; ++c) wq[s][c] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      constexpr int kChunkUnroll = MODE == SRK_X2_MID ? RT / 16 : 1;
+#pragma unroll kChunkUnroll
       for (int c0 = 0; c0 < RT; c0 += 16) {
         __syncwarp();                                     // reconverge after the divergent tails below
         uint32_t a[NS][16];
@@ -704,13 +714,12 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
 
         if (MODE == SRK_X2_MID) {
-          if (!jvalid) continue;
           uint32_t w[NS][4];
 #pragma unroll
           for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int x = 0; x < 4; ++x) w[s][x] = 0u;
-          if (fj != kNoBound) {
+          if (jvalid && fj != kNoBound) {
 #pragma unroll
             for (int x = 0; x < 16; ++x) {
               const uint32_t q = mid_quant<NS>(combine<NS>(a, x), cf[c0 + x], fj);
@@ -719,9 +728,7 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
           }
 #pragma unroll
-          for (int s = 0; s < NS; ++s)
-            st_stream_u32x4(reinterpret_cast<uint4*>(p.out_planes + s * p.out_plane_stride + j * p.ld_outp + rc),
-                            make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]), spol);
+          for (int s = 0; s < NS; ++s) wq[MODE == SRK_X2_MID ? s : 0][c0 / 16] = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
           continue;
         }
 
@@ -879,6 +886,31 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               }
             }
             __syncwarp();                                 // the tile is rewritten by the next chunk
+          }
+        }
+      }
+      if (MODE == SRK_X2_MID) {
+        // Row j of the tile is RT contiguous bytes per plane, but held by ONE lane: stored from there
+        // every instruction scatters 32 x 16 B over 32 lines (and, when the row panel of U lives on
+        // another GPU, over 32 NVLink write packets: 2 ms per iteration at 2 GPUs).  Each plane goes
+        // through the warp's staging tile and leaves as whole rows, 32 / (RT / 16) rows per instruction.
+        constexpr int kPieces = RT / 16, kRows = 32 / kPieces;
+        uint8_t* stg = reinterpret_cast<uint8_t*>(mirror_stage) + ew * (32 * C::kMirrorRow * 8);
+        const int64_t jw = jc0 + ew * 32;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < kPieces; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * (C::kMirrorRow * 8) + c * 16) = wq[MODE == SRK_X2_MID ? s : 0][c];
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < kPieces; ++i) {
+            const int row = i * kRows + lane / kPieces, piece = lane % kPieces;
+            const int64_t jj = jw + row, rcol = r0 + piece * 16;
+            if (jj < p.M && rcol < p.R)
+              st_stream_u32x4(reinterpret_cast<uint4*>(p.out_planes + s * p.out_plane_stride + jj * p.ld_outp + rcol),
+                              *reinterpret_cast<const uint4*>(stg + row * (C::kMirrorRow * 8) + piece * 16), spol);
           }
         }
       }
