@@ -4,6 +4,8 @@
 // graph is too sparse/large for a dense operand (BASELINE cfg5).  It is bound by HBM for the
 // streamed operands (S read once per column panel, result written once) and by L2 for the row
 // gather; see DESIGN.md "K3".
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace srk {
@@ -25,10 +27,11 @@ char* error_buffer() {
 //   phase 2  the TI x TC tile is transposed through shared memory and written as 256 B rows of
 //            OUT, where the SimRank epilogue (C, evidence, prior, diagonal, max|dS|) is fused.
 constexpr int TI = 32;
-constexpr int TC = 128;
 constexpr int CSR_THREADS = 256;
 
-template <bool kFinal>
+// TC = columns of X per CTA = width of the panel all CTAs of a grid column gather from: the panel
+// (rows of X x TC x 8 B, held once per L2 die) has to survive next to the result streams.
+template <bool kFinal, int TC>
 __global__ void __launch_bounds__(CSR_THREADS)
 csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const double* __restrict__ g, int64_t row_begin, int64_t row_end,
@@ -43,7 +46,10 @@ csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
 
   for (int il = warp; il < TI; il += CSR_THREADS / 32) {
     const int64_t i = i0 + il;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int TQ = TC / 32;
+    double acc[TQ];
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) acc[q] = 0.0;
     if (i < row_end) {
       const int64_t beg = indptr[i], end = indptr[i + 1];
       for (int64_t e = beg; e < end; e += 32) {
@@ -51,12 +57,12 @@ csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
         const int my = (lane < cnt) ? indices[e + lane] : 0;
         int t = 0;
         for (; t + 4 <= cnt; t += 4) {          // 4 neighbours in flight, summed in list order
-          double v[4][4];
+          double v[4][TQ];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const double* row = X + (int64_t)__shfl_sync(0xffffffffu, my, t + u) * ldx + c0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < TQ; ++q) {
               const int64_t c = lane + 32 * q;
               v[u][q] = (c0 + c < L) ? __ldg(row + c) : 0.0;
             }
@@ -64,12 +70,12 @@ csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] += v[u][q];
+            for (int q = 0; q < TQ; ++q) acc[q] += v[u][q];
         }
         for (; t < cnt; ++t) {
           const double* row = X + (int64_t)__shfl_sync(0xffffffffu, my, t) * ldx + c0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < TQ; ++q) {
             const int64_t c = lane + 32 * q;
             acc[q] += (c0 + c < L) ? __ldg(row + c) : 0.0;
           }
@@ -77,10 +83,10 @@ csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
       }
       const double gi = g[i];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] *= gi;
+      for (int q = 0; q < TQ; ++q) acc[q] *= gi;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tile[lane + 32 * q][il] = acc[q];
+    for (int q = 0; q < TQ; ++q) tile[lane + 32 * q][il] = acc[q];
   }
   __syncthreads();
 
@@ -431,19 +437,24 @@ extern "C" int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, c
   SRK_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= M, "row range");
   SRK_REQUIRE(L >= 0 && ldx >= L && ldo >= row_end, "leading dimensions");
   if (row_end == row_begin || L == 0) return SRK_OK;
-  const int64_t gx = (row_end - row_begin + TI - 1) / TI, gy = (L + TC - 1) / TC;
+  // Panel width.  The first half only streams its result next to the gathered panel of X: 128
+  // columns (rows of X x 1 KB, held once per L2 die).  The second half also streams S_old; with 128
+  // columns its panel fell out of L2 and the gather came from DRAM (93 ms against 35 ms for the same
+  // gather volume at n = 32768), with 64 columns it stays (42 ms).  SRK_CSR_TC=64|128 forces one
+  // width for A/B profiling.
+  int tc = final_epi ? 64 : 128;
+  if (const char* e = getenv("SRK_CSR_TC")) tc = atoi(e) == 128 ? 128 : 64;
+  const int64_t gx = (row_end - row_begin + TI - 1) / TI, gy = (L + tc - 1) / tc;
   SRK_REQUIRE(gy <= 65535, "too many column panels");
   dim3 grid((unsigned)gx, (unsigned)gy);
   cudaStream_t st = (cudaStream_t)stream;
-  if (final_epi) {
-    csr_half_kernel<true><<<grid, CSR_THREADS, 0, st>>>(indptr, indices, g, row_begin, row_end, X, ldx,
-                                                        L, OUT, ldo, to_dev(*final_epi),
-                                                        final_epi->maxdiff, final_epi->maxoff);
-  } else {
-    EpilogueDev none = {};
-    csr_half_kernel<false><<<grid, CSR_THREADS, 0, st>>>(indptr, indices, g, row_begin, row_end, X, ldx,
-                                                         L, OUT, ldo, none, nullptr, nullptr);
-  }
+  EpilogueDev ed = {};
+  double *md = nullptr, *mo = nullptr;
+  if (final_epi) { ed = to_dev(*final_epi); md = final_epi->maxdiff; mo = final_epi->maxoff; }
+#define SRK_CSR_LAUNCH(F, T) csr_half_kernel<F, T><<<grid, CSR_THREADS, 0, st>>>(indptr, indices, g, row_begin, row_end, X, ldx, L, OUT, ldo, ed, md, mo)
+  if (final_epi) { if (tc == 128) SRK_CSR_LAUNCH(true, 128); else SRK_CSR_LAUNCH(true, 64); }
+  else { if (tc == 128) SRK_CSR_LAUNCH(false, 128); else SRK_CSR_LAUNCH(false, 64); }
+#undef SRK_CSR_LAUNCH
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }

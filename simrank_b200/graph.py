@@ -67,13 +67,14 @@ def _inverse_or_zero(x: np.ndarray) -> np.ndarray:
 
 
 def _csr(rows: np.ndarray, cols: np.ndarray, M: int, K: int):
-    if rows.size and M * K < (1 << 62):
-        key = rows.astype(np.int64) * K + cols.astype(np.int64)
-        key.sort()                                   # values only: rows and columns are recovered from the key
+    if rows.size:
+        # one sort of packed (row, column) keys; both halves come back with shifts
+        key = (rows.astype(np.int64) << 32) | cols.astype(np.int64)
+        key.sort()
         if key.size > 1 and np.any(key[1:] == key[:-1]):
             raise ValueError(_DUPLICATE_MSG)
-        rows = key // K
-        cols = key - rows * K
+        rows = key >> 32
+        cols = key & 0xFFFFFFFF
     indptr = np.zeros(M + 1, dtype=np.int64)
     np.cumsum(np.bincount(rows, minlength=M), out=indptr[1:])
     return indptr, cols.astype(np.int32)
@@ -93,13 +94,18 @@ def build_directed(data: pd.DataFrame, weighted: bool, from_node_column: str, to
     nodes = list(node_set)
     n = len(nodes)
     labels = pd.Index(nodes)
-    if weighted:
-        inn = data.groupby(to_node_column)[weight_column].sum()
-    else:
-        inn = data.groupby(to_node_column)[from_node_column].count()
-    g = _inverse_or_zero(_per_node(inn, labels))
     rows = labels.get_indexer(data[to_node_column])
     cols = labels.get_indexer(data[from_node_column])
+    if weighted:
+        inn = _per_node(data.groupby(to_node_column)[weight_column].sum(), labels)
+    elif data[from_node_column].isna().any() or data[to_node_column].isna().any():
+        inn = _per_node(data.groupby(to_node_column)[from_node_column].count(), labels)
+    else:
+        # `groupby(to)[from].count()` without missing values is the number of rows per `to` label;
+        # nodes that never occur as `to` have no group: NaN after the join (SimRank.py:48), g = 0
+        inn = np.bincount(rows, minlength=n).astype(np.float64)
+        inn[inn == 0] = np.nan
+    g = _inverse_or_zero(inn)
     indptr, indices = _csr(rows, cols, n, n)
     return node_set, nodes, HostOperator(n, n, indptr, indices, g)
 
