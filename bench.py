@@ -64,6 +64,15 @@ def peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="B200_PROFILING.md fallback")
 
 
+def ncu_pipe_active(kernel, ns, n, world):
+    """Fraction of cycles the tensor pipe was active in that capture (ncu
+    sm__pipe_tensor_cycles_active_realtime), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("_tensor_pipe_active", {}).get(kernel, {}).get(f"ns{ns}_n{n}_g{world}")
+
+
 def ncu_traffic(kernel, ns, n, world):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of ``kernel`` from the
     committed `ncu --set full` capture of this very workload (profiles/ncu_traffic.json, written by
@@ -218,6 +227,7 @@ def run_engine(args):
                 "frac": ach / pk["tensor_sustained"], "traffic": ncu_traffic(dom, used[-1], n, world),
                 "peak_kind": f"dense bf16 sustained, {pk['source']}; burst {pk['tensor_burst']}",
                 "executed_int8_tops": ach * used[-1] * (0.5 if sym else 1.0),
+                "tensor_pipe_active_ncu": ncu_pipe_active(dom, used[-1], n, world),
                 "note": ("achieved = algorithmic 2n^3 flop of one half-product / mean launch time inside the timed "
                          f"steps; the kernel executes {used} u8 x u8 -> s32 tcgen05 products per algorithmic one"
                          + ("; this launch computes only the upper triangle of the symmetric result" if sym else ""))}

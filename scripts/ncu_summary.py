@@ -101,6 +101,12 @@ if __name__ == "__main__":
             cur = {}
         for (name, ns), b in traffic_entries(kernels).items():
             cur.setdefault(name, {})[f"ns{ns}_{tag}"] = b
+        pipe = "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"
+        names = {"i8x2_kernel<2, 0>": "x2_half_mid", "i8x2_kernel<2, 1>": "x2_half_final"}
+        for k in kernels:
+            for pat, name in names.items():
+                if pat in k["kernel"] and pipe in k:
+                    cur.setdefault("_tensor_pipe_active", {}).setdefault(name, {})[f"ns2_{tag}"] = float(k[pipe][0]) / 100.0
         cur["_source"] = cur.get("_source", {})
         cur["_source"][tag] = dst
         json.dump(cur, open(path, "w"), indent=1, sort_keys=True)

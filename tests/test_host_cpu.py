@@ -100,6 +100,19 @@ def test_zero_weight_sum_and_missing_in_edges():
     assert op.dead.sum() >= 2
 
 
+def test_missing_labels_keep_pandas_count_semantics():
+    """`groupby(to)[from].count()` skips missing `from` values (SimRank.py:47); the fast in-degree
+    count is only taken when no label is missing."""
+    df = pd.DataFrame({"from": [1.0, np.nan, 3.0, 1.0, 2.0], "to": [2.0, 2.0, 2.0, 4.0, 3.0]})
+    _, nodes, op = graph.build_directed(df, False, "from", "to", "weight")
+    g = dict(zip(nodes, op.g))
+    assert g[2.0] == 0.5 and g[4.0] == 1.0 and g[3.0] == 1.0 and g[1.0] == 0.0   # node 2: three rows, two counted
+    big = synth.directed_frame(3000, 40000, 0.7, 11)                    # no missing labels: bincount path
+    _, G = orc.directed_graph(big, False)
+    _, _, op = graph.build_directed(big, False, "from", "to", "weight")
+    np.testing.assert_array_equal(op.to_dense(), G)
+
+
 def test_duplicate_pairs_raise_pivot_error():
     df = pd.DataFrame({"from": [1, 1], "to": [2, 2]})
     with pytest.raises(ValueError, match="Index contains duplicate entries, cannot reshape"):
