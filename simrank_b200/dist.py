@@ -414,9 +414,17 @@ def _rank_world(group=None):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
-def _check_mode(mode):
+def _check_mode(mode, *ops):
+    """The row-sharded solver runs the tensor-core path only.  It needs what that path needs on one
+    GPU (engine.choose_mode): finite, non-negative row scales -- the fixed-point planes hold
+    non-negative similarities.  Anything else must fail loudly, not produce numbers."""
     if mode not in (None, "auto", "i8"):
-        raise NotImplementedError("the row-sharded solver runs the tensor-core (i8) path")
+        raise NotImplementedError("the row-sharded solver runs the tensor-core (i8) path; mode='csr' is single-GPU")
+    for op in ops:
+        g = np.asarray(op.g)
+        if not (np.all(np.isfinite(g)) and np.all(g >= 0)):
+            raise NotImplementedError("row-sharded fit needs finite, non-negative 1/inNeighbors (negative weight "
+                                      "sums take the float64 CSR path, which is single-GPU)")
 
 
 class ShardedDirectedSolver:
@@ -426,7 +434,7 @@ class ShardedDirectedSolver:
 
     def __init__(self, op: HostOperator, C_, evidence=None, prior=None, lbd=0.0, mode="i8", ns=None, device=None,
                  group=None, evidence_from_pattern=False):
-        _check_mode(mode)
+        _check_mode(mode, op)
         rank, world = _rank_world(group)
         self.mode = "i8"
         self.half = self.half_cls(op, C_, rank, world, device, ns, evidence, prior, lbd, group,
@@ -450,7 +458,7 @@ class ShardedBipartiteSolver:
     def __init__(self, op12: HostOperator, op21: HostOperator, C1, C2, evidence1=None, evidence2=None, prior1=None,
                  prior2=None, lbd1=0.0, lbd2=0.0, mode="i8", ns=None, device=None, group=None,
                  evidence1_from_pattern=False, evidence2_from_pattern=False):
-        _check_mode(mode)
+        _check_mode(mode, op12, op21)
         rank, world = _rank_world(group)
         self.mode = "i8"
         self.h1 = self.half_cls(op12, C1, rank, world, device, ns, evidence1, prior1, lbd1, group,

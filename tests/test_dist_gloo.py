@@ -125,6 +125,15 @@ def test_sharded_solver_matches_oracle(world, case):
     assert sum(r[3] for r in results) == n              # the row blocks tile the matrix
 
 
+def test_sharded_solver_refuses_what_the_fixed_point_path_cannot_hold():
+    op = graph.operator_from_edges([0, 1, 2], [1, 2, 0], 3, 3, g=np.array([0.5, -0.25, 1.0]))
+    with pytest.raises(NotImplementedError, match="non-negative"):
+        sdist._check_mode(None, op)
+    with pytest.raises(NotImplementedError, match="single-GPU"):
+        sdist._check_mode("csr", op)
+    sdist._check_mode("i8", graph.operator_from_edges([0, 1], [1, 0], 2, 2))
+
+
 def test_shard_plan_and_block_assignment():
     p = sdist.ShardPlan(700, 3)
     assert p.per == 240 and [p.count(r) for r in range(3)] == [240, 240, 220]
