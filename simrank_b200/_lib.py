@@ -120,7 +120,12 @@ def load():
     return lib
 
 
+LAUNCHES = 0      # successful library calls so far; every one of them enqueues exactly one kernel
+
+
 def check(rc: int, what: str = ""):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = load().srk_last_error().decode("utf-8", "replace")
         raise EngineError(f"{what or 'libsimrank_b200'} failed ({rc}): {msg}")
