@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 7
+#define SRK_ABI_VERSION 8
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -46,7 +46,9 @@ int srk_device_cc(void);
  *   v = coef * x                      coef carries C (SimRank.py:139) or C1/C2 (:298,:301)
  *   v = v * (1 - 0.5^evidence[r,c])   if evidence != NULL  (SimRank.py:316 with :361/:420/:423)
  *   v = (1-lambda)*v + lambda*prior[r,c]   if prior != NULL (SimRank.py:453,:488,:491)
- *   v = 1 if r == c                   np.fill_diagonal(new_S, 1)  (SimRank.py:140,...)
+ *   v = 1 if r + diag_offset == c     np.fill_diagonal(new_S, 1)  (SimRank.py:140,...); diag_offset is the
+ *                                     global index of output row 0 (row-sharded CSR calls; the
+ *                                     tensor-core calls carry their own diag_offset and ignore this one)
  *   *maxdiff = max(*maxdiff, |v - s_old[r,c]|)   if s_old != NULL: the reduction behind
  *                                     _converged (SimRank.py:74): converged <=> maxdiff <= eps
  *   *maxoff  = max(*maxoff, v) over r != c        if maxoff != NULL (range tracking for the
@@ -64,15 +66,21 @@ typedef struct srk_epilogue {
   int64_t ld_s_old;
   double* maxdiff;           /* device scalar or NULL */
   double* maxoff;            /* device scalar or NULL */
+  int64_t diag_offset;       /* srk_csr_half_f64 only: see above */
 } srk_epilogue;
 
 /* ----------------------------------------------------------------------------- CSR path (f64)
  * One half-product  OUT[c, i] = g[i] * sum_{m in N(i)} X[m, c]   (i < M, c < L), i.e.
  * OUT = (G X)^T, written transposed through shared memory so that two calls give
  * (G (G X)^T)^T = G X^T G^T  -- the chain `G.dot(S).dot(G.T)` of SimRank.py:139 (S symmetric).
- * row_begin/row_end restrict i to a row shard (multi-GPU); OUT always has L rows.
+ * row_begin/row_end restrict i to a row shard (multi-GPU); OUT always has L rows and only its
+ * columns [row_begin, row_end) are touched (ldo >= row_end - row_begin: a buffer that holds just
+ * those columns is passed as its address minus row_begin elements).
  * final_epi == NULL  -> plain store (first half, T);
- * final_epi != NULL  -> second half with the fused epilogue above (r = c index, c = i).     */
+ * final_epi != NULL  -> second half with the fused epilogue above (r = c index, c = i).
+ * Row-sharded use (one rank owns the output rows [row0, row0 + L) of S_new): X = the column panel
+ * T[:, row0 .. row0 + L) as an [K x L] matrix, OUT / s_old / evidence / prior = the rank's row
+ * blocks, final_epi->diag_offset = row0.                                                       */
 int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double* g,
                      int64_t M, int64_t row_begin, int64_t row_end,
                      const double* X, int64_t ldx, int64_t L,

@@ -11,7 +11,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 SRK_I8_MID, SRK_I8_FINAL, SRK_I8_COUNTS = 0, 1, 2
 SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
@@ -28,7 +28,8 @@ class Epilogue(C.Structure):
                 ("prior", C.c_void_p), ("ld_prior", C.c_int64),
                 ("lambda_", C.c_double),
                 ("s_old", C.c_void_p), ("ld_s_old", C.c_int64),
-                ("maxdiff", C.c_void_p), ("maxoff", C.c_void_p)]
+                ("maxdiff", C.c_void_p), ("maxoff", C.c_void_p),
+                ("diag_offset", C.c_int64)]
 
 
 class RowBound(C.Structure):

@@ -61,6 +61,7 @@ struct EpilogueDev {
   const uint8_t* evidence; int64_t ld_evidence;
   const double* prior; int64_t ld_prior;
   const double* s_old; int64_t ld_s_old;
+  int64_t diag_offset;         // CSR half-product: global index of output row 0
 };
 
 inline EpilogueDev to_dev(const srk_epilogue& e) {
@@ -69,6 +70,7 @@ inline EpilogueDev to_dev(const srk_epilogue& e) {
   d.evidence = e.evidence; d.ld_evidence = e.ld_evidence;
   d.prior = e.prior; d.ld_prior = e.ld_prior;
   d.s_old = e.s_old; d.ld_s_old = e.ld_s_old;
+  d.diag_offset = e.diag_offset;
   return d;
 }
 

@@ -102,7 +102,7 @@ csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
       // loads/stores keep them from pushing the gathered panel of X out of L2
       if (epi.evidence) v *= evidence_factor(__ldcs(epi.evidence + r * epi.ld_evidence + i));
       if (epi.prior) v = (1.0 - epi.lambda) * v + epi.lambda * __ldcs(epi.prior + r * epi.ld_prior + i);
-      if (r == i) v = 1.0; else if (v > omax) omax = v;
+      if (r + epi.diag_offset == i) v = 1.0; else if (v > omax) omax = v;
       if (epi.s_old) {
         const double d = fabs(v - __ldcs(epi.s_old + r * epi.ld_s_old + i));
         if (d > dmax) dmax = d;                  // NaN compares false: ignored like SimRank.py:74
@@ -435,7 +435,9 @@ extern "C" int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, c
                                 const srk_epilogue* final_epi, void* stream) {
   SRK_REQUIRE(indptr && indices && g && X && OUT, "null pointer");
   SRK_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= M, "row range");
-  SRK_REQUIRE(L >= 0 && ldx >= L && ldo >= row_end, "leading dimensions");
+  // OUT is addressed as OUT[c * ldo + i] for i in [row_begin, row_end) only: a caller that stores just
+  // those columns passes the address of (virtual) column 0, i.e. its buffer minus row_begin elements
+  SRK_REQUIRE(L >= 0 && ldx >= L && ldo >= row_end - row_begin, "leading dimensions");
   if (row_end == row_begin || L == 0) return SRK_OK;
   // Panel width.  The first half only streams its result next to the gathered panel of X: 128
   // columns (rows of X x 1 KB, held once per L2 die).  The second half also streams S_old; with 128

@@ -410,35 +410,145 @@ class ShardedHalf:
         return full[: self.n_out]
 
 
+class ShardedCsrHalf:
+    """Rank-local state of one similarity matrix in the float64 CSR mode (exact arithmetic; graphs the
+    fixed-point path cannot hold: negative weight sums, or when float64 results are asked for).
+
+    S_out is row-sharded like in ShardedHalf.  One update ``S_out <- epilogue(coef * G S_in G^T)`` on
+    rank q, with T = (G S_in)^T (n_in x n_out):
+
+      1. first half   T[rows_in_q, :]: ``srk_csr_half_f64`` on X = (local rows of S_in)^T -- S_in is
+                      symmetric, so the local ROW block transposed is the COLUMN block the gather needs.
+                      One launch per destination rank p over the graph rows of p's block, stored
+                      straight into the send block for p.
+      2. exchange     block transpose: rank p receives T[rows_in_q, rows_out_p] from every q
+                      (``all_to_all_single``) and so holds the column panel
+                      T[:, rows_out_p] as an [n_in x rows_out_p] matrix.
+      3. second half  ``srk_csr_half_f64`` with the fused epilogue on that panel: S_out[rows_out_p, :],
+                      ``diag_offset`` = first global row of the block.
+      4. the 2-double MAX all-reduce of ShardedHalf.finish.
+    """
+
+    def __init__(self, op: HostOperator, coef, rank, world, device, evidence=None, prior=None, lbd=0.0, group=None):
+        self.op, self.coef, self.rank, self.world, self.device, self.group = op, float(coef), rank, world, device, group
+        self.n_out, self.n_in = op.M, op.K
+        self.plan = ShardPlan(self.n_out, world)
+        self.row0, self.rows, self.per = self.plan.start(rank), self.plan.count(rank), max(self.plan.per, 16)
+        self.ld = _round_up(max(self.n_out, 1), 16)
+        self.evidence, self.prior, self.lbd = evidence, prior, float(lbd)          # LOCAL rows
+        self.events = None
+        self.slices_used = []
+        self.S = torch.zeros((self.per, self.ld), dtype=torch.float64, device=device)
+        self._init_identity()
+        self.scal = torch.zeros(2, dtype=torch.float64, device=device)
+        self.maxoff = 0.0
+        self.indptr = torch.from_numpy(op.indptr).to(device)
+        self.indices = torch.from_numpy(np.ascontiguousarray(op.indices)).to(device)
+        self.g = torch.from_numpy(np.ascontiguousarray(op.g, dtype=np.float64)).to(device)
+        self._send = self._recv = None
+
+    # ---- device hooks (replaced by numpy stand-ins in the CPU tests) ------------------------
+    def _init_identity(self):
+        if self.rows:
+            _lib.check(_lib.load().srk_set_identity_f64(_ptr(self.S), self.ld, self.rows, self.n_out, self.row0,
+                                                        _stream()), "srk_set_identity_f64")
+
+    def _launch_csr(self, row_begin, row_end, x_ptr, ldx, L, out_ptr, ldo, epi):
+        import ctypes as C_
+        _lib.check(_lib.load().srk_csr_half_f64(_ptr(self.indptr), _ptr(self.indices), _ptr(self.g), self.n_out,
+                                                row_begin, row_end, C_.c_void_p(x_ptr), ldx, L, C_.c_void_p(out_ptr),
+                                                ldo, C_.byref(epi) if epi is not None else None, _stream()),
+                   "srk_csr_half_f64")
+
+    def _reduce_scalars(self):
+        dist.all_reduce(self.scal, op=dist.ReduceOp.MAX, group=self.group)
+
+    _timed = ShardedHalf._timed
+
+    # ---- one update ----------------------------------------------------------------------------
+    def update(self, src: "ShardedCsrHalf") -> None:
+        self.scal.zero_()
+        P, per_in, per_out = self.world, src.per, self.per
+        if self._send is None or self._send.shape != (P, per_in, per_out):
+            self._send = torch.zeros((P, per_in, per_out), dtype=torch.float64, device=self.device)
+            self._recv = torch.zeros((P, per_in, per_out), dtype=torch.float64, device=self.device)
+
+        def first():
+            if src.rows == 0:
+                return
+            # column block of the symmetric S_in = its local row block, transposed (a copy, no arithmetic)
+            xt = src.S[: src.rows, : self.n_in].t().contiguous()                  # [n_in, rows_in_q]
+            for p in range(P):
+                lo, hi = self.plan.start(p), self.plan.stop(p)
+                if hi > lo:        # OUT[c, i] lands at send[p][c, i - lo]: shift the base by -lo columns
+                    self._launch_csr(lo, hi, xt.data_ptr(), src.rows, src.rows,
+                                     self._send[p].data_ptr() - 8 * lo, per_out, None)
+        self._timed("csr_half_first", first)
+        self._timed("exchange", lambda: dist.all_to_all_single(self._recv, self._send, group=self.group))
+
+        def second():
+            if self.rows == 0:
+                return
+            e = _lib.Epilogue()
+            e.coef = self.coef
+            if self.evidence is not None:
+                e.evidence, e.ld_evidence = self.evidence.data_ptr(), self.evidence.stride(0)
+            if self.prior is not None:
+                e.prior, e.ld_prior, e.lambda_ = self.prior.data_ptr(), self.prior.stride(0), self.lbd
+            e.s_old, e.ld_s_old = self.S.data_ptr(), self.ld
+            e.maxdiff, e.maxoff = self.scal.data_ptr(), self.scal.data_ptr() + 8
+            e.diag_offset = self.row0
+            # block q of the receive buffer holds rows start_in(q).. of the panel: [P * per_in, per_out]
+            self._launch_csr(0, self.n_out, self._recv.data_ptr(), per_out, self.rows, self.S.data_ptr(), self.ld, e)
+        self._timed("csr_half_final", second)
+
+    def finish(self) -> float:
+        self._reduce_scalars()
+        maxdiff, maxoff = self.scal.tolist()
+        self.maxoff = maxoff
+        return maxdiff
+
+    local_result = ShardedHalf.local_result
+    gathered_result = ShardedHalf.gathered_result
+
+
 def _rank_world(group=None):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
-def _check_mode(mode, *ops):
-    """The row-sharded solver runs the tensor-core path only.  It needs what that path needs on one
-    GPU (engine.choose_mode): finite, non-negative row scales -- the fixed-point planes hold
-    non-negative similarities.  Anything else must fail loudly, not produce numbers."""
-    if mode not in (None, "auto", "i8"):
-        raise NotImplementedError("the row-sharded solver runs the tensor-core (i8) path; mode='csr' is single-GPU")
-    for op in ops:
-        g = np.asarray(op.g)
-        if not (np.all(np.isfinite(g)) and np.all(g >= 0)):
-            raise NotImplementedError("row-sharded fit needs finite, non-negative 1/inNeighbors (negative weight "
-                                      "sums take the float64 CSR path, which is single-GPU)")
+def _sharded_mode(mode, *ops) -> str:
+    """'i8' (tensor-core planes, peer-memory exchange) or 'csr' (float64, all-to-all exchange).  The
+    fixed-point planes hold non-negative similarities, so the tensor-core path needs finite,
+    non-negative row scales (as engine.choose_mode demands on one GPU): asked for explicitly on
+    anything else it fails loudly, left to 'auto' such a graph takes the CSR path."""
+    mode = (mode or "auto").lower()
+    if mode not in ("auto", "i8", "csr"):
+        raise ValueError(f"unknown mode {mode!r} for the row-sharded solver")
+    ok = all(bool(np.all(np.isfinite(np.asarray(op.g))) and np.all(np.asarray(op.g) >= 0)) for op in ops)
+    if mode == "i8" and not ok:
+        raise ValueError("mode='i8' needs finite, non-negative 1/inNeighbors; use mode='csr' (float64)")
+    if mode == "auto":
+        return "i8" if ok else "csr"
+    return mode
 
 
 class ShardedDirectedSolver:
     """Row-sharded ``S <- [E o] C * W S W^T; diag <- 1`` (SimRank.py:139, :361)."""
 
     half_cls = ShardedHalf
+    csr_half_cls = ShardedCsrHalf
 
     def __init__(self, op: HostOperator, C_, evidence=None, prior=None, lbd=0.0, mode="i8", ns=None, device=None,
                  group=None, evidence_from_pattern=False):
-        _check_mode(mode, op)
         rank, world = _rank_world(group)
-        self.mode = "i8"
-        self.half = self.half_cls(op, C_, rank, world, device, ns, evidence, prior, lbd, group,
-                                  evidence_from_pattern)
+        self.mode = _sharded_mode(mode, op)
+        if self.mode == "csr":
+            if evidence_from_pattern:
+                raise ValueError("the CSR path takes evidence counts, not the pattern flag")
+            self.half = self.csr_half_cls(op, C_, rank, world, device, evidence, prior, lbd, group)
+        else:
+            self.half = self.half_cls(op, C_, rank, world, device, ns, evidence, prior, lbd, group,
+                                      evidence_from_pattern)
         self.halves = [self.half]
 
     def step(self) -> float:
@@ -454,13 +564,20 @@ class ShardedBipartiteSolver:
     """Row-sharded Gauss-Seidel alternation of SimRank.py:297-302."""
 
     half_cls = ShardedHalf
+    csr_half_cls = ShardedCsrHalf
 
     def __init__(self, op12: HostOperator, op21: HostOperator, C1, C2, evidence1=None, evidence2=None, prior1=None,
                  prior2=None, lbd1=0.0, lbd2=0.0, mode="i8", ns=None, device=None, group=None,
                  evidence1_from_pattern=False, evidence2_from_pattern=False):
-        _check_mode(mode, op12, op21)
         rank, world = _rank_world(group)
-        self.mode = "i8"
+        self.mode = _sharded_mode(mode, op12, op21)
+        if self.mode == "csr":
+            if evidence1_from_pattern or evidence2_from_pattern:
+                raise ValueError("the CSR path takes evidence counts, not the pattern flag")
+            self.h1 = self.csr_half_cls(op12, C1, rank, world, device, evidence1, prior1, lbd1, group)
+            self.h2 = self.csr_half_cls(op21, C2, rank, world, device, evidence2, prior2, lbd2, group)
+            self.halves = [self.h1, self.h2]
+            return
         self.h1 = self.half_cls(op12, C1, rank, world, device, ns, evidence1, prior1, lbd1, group,
                                 evidence1_from_pattern)
         self.h2 = self.half_cls(op21, C2, rank, world, device, ns, evidence2, prior2, lbd2, group,

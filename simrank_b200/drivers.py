@@ -96,6 +96,20 @@ def _mode_with_prior(mode, *priors):
     return mode
 
 
+def _require_symmetric_prior(*priors):
+    """The row-sharded solvers read column blocks of S as transposed row blocks, which is only the
+    same thing while S stays symmetric: it does for every class of the reference unless an Apriori
+    prior is not symmetric itself (SimRank.py:453)."""
+    for p in priors:
+        if p is None:
+            continue
+        a = np.asarray(p, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] != a.shape[1] or float(np.abs(a - a.T).max(initial=0.0)) > 1e-12 * max(
+                1.0, float(np.abs(a).max(initial=0.0))):
+            raise NotImplementedError("a row-sharded fit needs a symmetric prior matrix; run a non-symmetric "
+                                      "AprioriSim on one GPU")
+
+
 def _world():
     """(rank, world) of the default process group, (0, 1) when torch.distributed is not in use."""
     import torch.distributed as dist
@@ -128,9 +142,11 @@ def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mod
     rank, world = _world()
     if world > 1:                      # one process per GPU: S row-sharded, tensor-core path
         from . import dist as _sd
-        ev, from_pattern = _evidence_args(evidence, op, "i8")
+        _require_symmetric_prior(prior)
+        smode = _sd._sharded_mode(_mode_with_prior(mode, prior), op)
+        ev, from_pattern = _evidence_args(evidence, op, smode)
         return _sd.ShardedDirectedSolver(op, C, _local_rows(ev, op.M, rank, world),
-                                         _local_rows(pr, op.M, rank, world), lbd, _mode_with_prior(mode, prior),
+                                         _local_rows(pr, op.M, rank, world), lbd, smode,
                                          slices, dop.device, evidence_from_pattern=from_pattern)
     mode = _eng.choose_mode(op, _mode_with_prior(mode, prior))
     ev, from_pattern = _evidence_args(evidence, op, mode)
@@ -146,12 +162,14 @@ def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=N
     rank, world = _world()
     if world > 1:
         from . import dist as _sd
-        e1, pat1 = _evidence_args(evidence1, op12, "i8")
-        e2, pat2 = _evidence_args(evidence2, op21, "i8")
+        _require_symmetric_prior(prior1, prior2)
+        smode = _sd._sharded_mode(_mode_with_prior(mode, prior1, prior2), op12, op21)
+        e1, pat1 = _evidence_args(evidence1, op12, smode)
+        e2, pat2 = _evidence_args(evidence2, op21, smode)
         return _sd.ShardedBipartiteSolver(op12, op21, C1, C2, _local_rows(e1, op12.M, rank, world),
                                           _local_rows(e2, op21.M, rank, world), _local_rows(p1, op12.M, rank, world),
                                           _local_rows(p2, op21.M, rank, world), lbd1, lbd2,
-                                          _mode_with_prior(mode, prior1, prior2), slices, d12.device,
+                                          smode, slices, d12.device,
                                           evidence1_from_pattern=pat1, evidence2_from_pattern=pat2)
     mode = _mode_with_prior(mode, prior1, prior2)
     m1, m2 = _eng.choose_mode(op12, mode), _eng.choose_mode(op21, mode)

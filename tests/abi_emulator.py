@@ -1,5 +1,5 @@
-"""Host-memory emulator of ``srk_x2_half`` and ``srk_slice_rows_max_f64`` (include/simrank_b200.h)
-in numpy.  TEST ONLY.
+"""Host-memory emulator of ``srk_x2_half``, ``srk_slice_rows_max_f64`` and ``srk_csr_half_f64``
+(include/simrank_b200.h) in numpy.  TEST ONLY.
 
 It interprets the very structs the product passes to the CUDA library, but on CPU tensors, so the
 multi-rank host logic (shard offsets, block assignment of the symmetric update, staging layouts,
@@ -139,3 +139,40 @@ def srk_slice_rows_max_f64(V_ptr, ldv, R, K, zero_diag_offset, ns, planes_ptr, l
         out = _view(planes_ptr + s * plane_stride, C.c_uint8, R, ldp, ldp)
         out[:, :K] = ((q >> (8 * (ns - 1 - s))) & 0xFF).astype(np.uint8)
         out[:, K:] = 0
+
+
+def srk_csr_half_f64(indptr, indices, g, M, row_begin, row_end, X_ptr, ldx, L, OUT_ptr, ldo, epi, K):
+    """OUT[c, i] = g[i] * sum_{m in N(i)} X[m, c] for i in [row_begin, row_end), c < L, then the fused
+    epilogue when ``epi`` is given.  ``indptr/indices/g`` are host arrays, X has K rows.  Only the
+    columns [row_begin, row_end) of OUT are touched (the caller may pass a shifted base)."""
+    if row_end <= row_begin or L == 0:
+        return
+    X = _view(X_ptr, C.c_double, K, L, ldx)
+    acc = np.zeros((row_end - row_begin, L))
+    for i in range(row_begin, row_end):
+        nb = indices[indptr[i]:indptr[i + 1]]
+        acc[i - row_begin] = g[i] * X[nb, :].sum(axis=0) if nb.size else 0.0
+    val = acc.T                                                    # [L, rows]: (r = c index, column i)
+    cols = np.arange(row_begin, row_end)
+
+    def block(ptr, ctype, ld):                                    # rows 0..L, columns row_begin..row_end of a caller matrix
+        return _view(ptr + row_begin * C.sizeof(ctype), ctype, L, row_end - row_begin, ld)
+
+    if epi is not None:
+        val = epi.coef * val
+        if epi.evidence:
+            val = val * (1 - 0.5 ** np.minimum(block(epi.evidence, C.c_uint8, epi.ld_evidence).astype(np.float64), 60.0))
+        if epi.prior:
+            val = (1 - epi.lambda_) * val + epi.lambda_ * block(epi.prior, C.c_double, epi.ld_prior)
+        diag = (np.arange(L)[:, None] + epi.diag_offset) == cols[None, :]
+        val = np.where(diag, 1.0, val)
+        if epi.maxoff:
+            m = _f64(epi.maxoff, 1)
+            m[0] = max(m[0], val[~diag].max(initial=0.0))
+        if epi.s_old and epi.maxdiff:
+            d = np.abs(val - block(epi.s_old, C.c_double, epi.ld_s_old))
+            d = d[~np.isnan(d)]
+            if d.size:
+                m = _f64(epi.maxdiff, 1)
+                m[0] = max(m[0], d.max())
+    block(OUT_ptr, C.c_double, ldo)[:, :] = val

@@ -45,12 +45,30 @@ class CpuHalf(sdist.ShardedHalf):
         return fn()
 
 
+class CpuCsrHalf(sdist.ShardedCsrHalf):
+    """ShardedCsrHalf with host tensors and the emulated CSR half-product."""
+
+    def _init_identity(self):
+        for i in range(self.rows):
+            self.S[i, self.row0 + i] = 1.0
+
+    def _launch_csr(self, row_begin, row_end, x_ptr, ldx, L, out_ptr, ldo, epi):
+        assert ldx >= L and ldo >= row_end - row_begin            # the library's own argument check
+        abi_emulator.srk_csr_half_f64(self.op.indptr, self.op.indices, np.asarray(self.op.g, dtype=np.float64),
+                                      self.n_out, row_begin, row_end, x_ptr, ldx, L, out_ptr, ldo, epi, self.n_in)
+
+    def _timed(self, name, fn):
+        return fn()
+
+
 class CpuDirected(sdist.ShardedDirectedSolver):
     half_cls = CpuHalf
+    csr_half_cls = CpuCsrHalf
 
 
 class CpuBipartite(sdist.ShardedBipartiteSolver):
     half_cls = CpuHalf
+    csr_half_cls = CpuCsrHalf
 
 
 def _free_port():
@@ -80,6 +98,51 @@ def _worker(rank, world, port, case, out):
                 np.fill_diagonal(Sb, 1)
                 ref_diffs.append(float(np.abs(Sb - Sa).max()))
             out.put((rank, err, float(np.abs(np.array(diffs) - np.array(ref_diffs)).max()), sol.half.rows))
+        elif case == "directed_csr":
+            # negative weight sums: rows of G with a negative scale (SimRank.py:45,49) -- float64 CSR path
+            frm, to = synth.directed_edges(210, 1800, 0.8, 12)
+            gsc = np.random.default_rng(3).random(210) * 0.2 - 0.05
+            op = graph.operator_from_edges(to, frm, 210, 210, gsc)
+            prior = np.random.default_rng(4).random((210, 210))
+            prior = 0.5 * (prior + prior.T)          # sharded fits need a symmetric prior (drivers._require_symmetric_prior)
+            plan = sdist.ShardPlan(210, world)
+            sol = CpuDirected(op, 0.8, prior=torch.from_numpy(prior[plan.start(rank):plan.stop(rank)].copy()), lbd=0.25,
+                              mode=None, device=dev)
+            assert sol.mode == "csr"
+            diffs = [sol.step() for _ in range(4)]
+            G = op.to_dense()
+            Sa, Sb, ref_diffs = np.zeros((210, 210)), np.eye(210), []
+            for _ in range(4):
+                Sa, Sb = Sb, 0.75 * (0.8 * G @ Sb @ G.T) + 0.25 * prior
+                np.fill_diagonal(Sb, 1)
+                ref_diffs.append(float(np.abs(Sb - Sa).max()))
+            err = float(np.abs(sol.S.numpy() - Sb).max())
+            out.put((rank, err, float(np.abs(np.array(diffs) - np.array(ref_diffs)).max()), sol.half.rows))
+        elif case == "bipartite_csr":
+            u, i = synth.bipartite_edges(130, 77, 1500, 1.0, 5)
+            g1 = np.random.default_rng(1).random(130) * 0.05 - 0.01     # some negative row scales
+            g2 = np.random.default_rng(2).random(77) * 0.05 + 0.01
+            op12 = graph.operator_from_edges(u, i, 130, 77, g1)
+            op21 = graph.operator_from_edges(i, u, 77, 130, g2)
+            A12 = (op12.to_dense() != 0).astype(np.int64)
+            cnt = np.minimum(A12 @ A12.T, 255).astype(np.uint8)
+            plan1 = sdist.ShardPlan(130, world)
+            ev = torch.zeros((plan1.count(rank), 144), dtype=torch.uint8)
+            ev[:, :130] = torch.from_numpy(cnt[plan1.start(rank):plan1.stop(rank)].copy())
+            sol = CpuBipartite(op12, op21, 0.8, 0.7, evidence1=ev, mode="auto", device=dev)
+            assert sol.mode == "csr"
+            for _ in range(3):
+                sol.step()
+            S1, S2 = sol.S1.numpy(), sol.S2.numpy()
+            E1 = 1 - 0.5 ** cnt.astype(np.float64)
+            W1, W2 = op12.to_dense(), op21.to_dense()
+            s1, s2 = np.eye(130), np.eye(77)
+            for _ in range(3):
+                s1 = E1 * (0.8 * (W1 @ s2 @ W1.T))
+                np.fill_diagonal(s1, 1)
+                s2 = 0.7 * (W2 @ s1 @ W2.T)
+                np.fill_diagonal(s2, 1)
+            out.put((rank, float(max(np.abs(S1 - s1).max(), np.abs(S2 - s2).max())), 0.0, sol.h1.rows))
         else:
             u, i = synth.bipartite_edges(130, 77, 1500, 1.0, 5)
             g1 = np.random.default_rng(1).random(130) * 0.05 + 0.01      # weighted-style row scales
@@ -104,8 +167,9 @@ def _worker(rank, world, port, case, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3, 4])
-@pytest.mark.parametrize("case", ["directed", "bipartite"])
+@pytest.mark.parametrize("world,case", [(2, "directed"), (3, "directed"), (4, "directed"), (2, "bipartite"),
+                                        (3, "bipartite"), (4, "bipartite"), (2, "directed_csr"),
+                                        (3, "bipartite_csr"), (4, "bipartite_csr")])
 def test_sharded_solver_matches_oracle(world, case):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
@@ -121,17 +185,27 @@ def test_sharded_solver_matches_oracle(world, case):
     for rank, err, derr, rows in results:
         assert err <= 1e-6, (rank, err)                 # fixed-point planes: north-star bound
         assert derr <= 1e-6
-    n = 300 if case == "directed" else 130
+    n = {"directed": 300, "directed_csr": 210}.get(case, 130)
     assert sum(r[3] for r in results) == n              # the row blocks tile the matrix
 
 
 def test_sharded_solver_refuses_what_the_fixed_point_path_cannot_hold():
     op = graph.operator_from_edges([0, 1, 2], [1, 2, 0], 3, 3, g=np.array([0.5, -0.25, 1.0]))
-    with pytest.raises(NotImplementedError, match="non-negative"):
-        sdist._check_mode(None, op)
-    with pytest.raises(NotImplementedError, match="single-GPU"):
-        sdist._check_mode("csr", op)
-    sdist._check_mode("i8", graph.operator_from_edges([0, 1], [1, 0], 2, 2))
+    with pytest.raises(ValueError, match="non-negative"):
+        sdist._sharded_mode("i8", op)
+    assert sdist._sharded_mode(None, op) == "csr"                  # auto: the float64 path takes it
+    ok = graph.operator_from_edges([0, 1], [1, 0], 2, 2)
+    assert sdist._sharded_mode(None, ok) == "i8" and sdist._sharded_mode("csr", ok) == "csr"
+    with pytest.raises(ValueError, match="unknown mode"):
+        sdist._sharded_mode("i8v1", ok)
+
+
+def test_sharded_fit_needs_a_symmetric_prior():
+    from simrank_b200 import drivers
+    p = np.random.default_rng(0).random((5, 5))
+    with pytest.raises(NotImplementedError, match="symmetric prior"):
+        drivers._require_symmetric_prior(p)
+    drivers._require_symmetric_prior(None, p + p.T)
 
 
 def test_shard_plan_and_block_assignment():

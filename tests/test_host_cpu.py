@@ -28,9 +28,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes as C
-    assert C.sizeof(_lib.Epilogue) == 10 * 8
+    assert C.sizeof(_lib.Epilogue) == 11 * 8
     assert C.sizeof(_lib.RowBound) == 24
-    assert C.sizeof(_lib.I8Args) == 8 + 3 * 8 + 5 * 8 + 24 + 2 * 8 + 8 + 8 + 2 * 8 + 2 * 8 + 3 * 8 + 24 + 80
+    assert C.sizeof(_lib.I8Args) == 8 + 3 * 8 + 5 * 8 + 24 + 2 * 8 + 8 + 8 + 2 * 8 + 2 * 8 + 3 * 8 + 24 + 88
 
 
 def test_struct_layouts_match_c_compiler(tmp_path):
