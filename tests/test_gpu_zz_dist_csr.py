@@ -20,3 +20,70 @@ def test_row_sharded_csr_classes_match_oracle():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DIST_CSR_OK" in res.stdout
+
+
+def test_csr_half_row_block_calls_single_gpu():
+    """The two call shapes of the row-sharded CSR solver on ONE GPU: a first half restricted to the
+    graph rows of a destination block that stores into a buffer holding just those columns (shifted
+    base), and a second half on a column panel of T with ``diag_offset`` = first row of the block."""
+    import ctypes as C
+
+    import numpy as np
+
+    from simrank_b200 import _lib, engine, graph
+
+    dev = engine.require_cuda()
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    n, K = 203, 150
+    mask = rng.random((n, K)) < 0.1
+    rows, cols = np.nonzero(mask)
+    op = graph.operator_from_edges(rows, cols, n, K, rng.random(n) * 0.2 - 0.03)     # some negative scales
+    dop = engine.DeviceOperator(op, dev)
+    G = op.to_dense()
+    p = lambda t: engine._ptr(t)                                                      # noqa: E731
+
+    # ---- first half, destination block = graph rows [lo, hi)
+    lo, hi, Lx, per = 64, 134, 37, 80
+    Xh = rng.random((K, Lx))
+    X = torch.from_numpy(Xh).to(dev)
+    buf = torch.full((Lx, per), -7.0, dtype=torch.float64, device=dev)
+    _lib.check(lib.srk_csr_half_f64(p(dop.indptr), p(dop.indices), p(dop.g), n, lo, hi, p(X), Lx, Lx,
+                                    C.c_void_p(buf.data_ptr() - 8 * lo), per, None, engine._stream()))
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy()
+    np.testing.assert_allclose(got[:, : hi - lo], (G @ Xh).T[:, lo:hi], rtol=1e-13, atol=1e-300)
+    assert np.all(got[:, hi - lo:] == -7.0)                                          # nothing else touched
+
+    # ---- second half on the column panel T[:, r0 : r0 + L) of a square problem
+    op2 = graph.operator_from_edges(*np.nonzero(rng.random((n, n)) < 0.1), n, n, rng.random(n) * 0.2 + 0.01)
+    d2 = engine.DeviceOperator(op2, dev)
+    G2 = op2.to_dense()
+    r0, L = 48, 70
+    Th, S_old = rng.random((n, n)), rng.random((n, n))
+    cnt = rng.integers(0, 70, (n, n)).astype(np.uint8)
+    ld = engine._round_up(n, 16)
+    S_blk = torch.zeros((L, ld), dtype=torch.float64, device=dev)
+    S_blk[:, :n] = torch.from_numpy(S_old[r0:r0 + L])
+    ev = torch.zeros((L, ld), dtype=torch.uint8, device=dev)
+    ev[:, :n] = torch.from_numpy(cnt[r0:r0 + L])
+    panel = torch.from_numpy(np.ascontiguousarray(Th[:, r0:r0 + L])).to(dev)
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    e = _lib.Epilogue()
+    e.coef = 0.8
+    e.evidence, e.ld_evidence = ev.data_ptr(), ld
+    e.s_old, e.ld_s_old = S_blk.data_ptr(), ld
+    e.maxdiff, e.maxoff = scal.data_ptr(), scal.data_ptr() + 8
+    e.diag_offset = r0
+    _lib.check(lib.srk_csr_half_f64(p(d2.indptr), p(d2.indices), p(d2.g), n, 0, n, p(panel), L, L, p(S_blk), ld,
+                                    C.byref(e), engine._stream()))
+    torch.cuda.synchronize()
+    want = (1 - 0.5 ** cnt.astype(np.int64)) * 0.8 * (G2 @ Th).T
+    np.fill_diagonal(want, 1.0)
+    got = S_blk[:, :n].cpu().numpy()
+    np.testing.assert_allclose(got, want[r0:r0 + L], rtol=1e-12, atol=1e-300)
+    md, mo = scal.tolist()
+    assert md == np.abs(got - S_old[r0:r0 + L]).max()
+    off = got.copy()
+    off[np.arange(L), r0 + np.arange(L)] = 0.0
+    assert mo == off.max()
