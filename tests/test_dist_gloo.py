@@ -98,6 +98,42 @@ def _worker(rank, world, port, case, out):
                 np.fill_diagonal(Sb, 1)
                 ref_diffs.append(float(np.abs(Sb - Sa).max()))
             out.put((rank, err, float(np.abs(np.array(diffs) - np.array(ref_diffs)).max()), sol.half.rows))
+        elif case == "drivers":
+            # the routing layer the drop-in classes call (simrank_b200.drivers) with the device pieces
+            # replaced: operator -> device is a stub, the solvers use the emulated kernels
+            import types
+            from simrank_b200 import drivers
+            drivers._device_op = lambda op, device=None: types.SimpleNamespace(device=dev)
+            sdist.ShardedDirectedSolver.half_cls, sdist.ShardedDirectedSolver.csr_half_cls = CpuHalf, CpuCsrHalf
+            sdist.ShardedBipartiteSolver.half_cls, sdist.ShardedBipartiteSolver.csr_half_cls = CpuHalf, CpuCsrHalf
+            frm, to = synth.directed_edges(260, 2600, 0.8, 13)
+            op = graph.operator_from_edges(to, frm, 260, 260)
+            G = op.to_dense()
+            worst = 0.0
+            for mode, want_mode in ((None, "i8"), ("i8", "i8"), ("csr", "csr")):
+                sol = drivers.directed_solver(op, 0.8, mode=mode, device=dev)
+                assert sol.mode == want_mode
+                applied, conv, last = drivers.run_loop(sol.step, 3, 0.0, False)
+                res = drivers.collect(sol, [list(range(260))], "local")
+                (a, b), = res.rows
+                So, _, _ = orc.simrank(G, 0.8, 3, 0.0)
+                worst = max(worst, float(np.abs(res.mats[0].numpy() - So[a:b]).max()))
+                full = drivers.collect(sol, [list(range(260))], "all")
+                worst = max(worst, float(np.abs(full.mats[0].numpy() - So).max()))
+            # SimRank++ with the evidence of the operator's own pattern, bipartite, through the same layer
+            u, i = synth.bipartite_edges(120, 70, 1400, 1.0, 6)
+            op12, op21 = graph.operator_from_edges(u, i, 120, 70), graph.operator_from_edges(i, u, 70, 120)
+            ev1, ev2 = drivers.EvidenceMatrix(op12, dev), drivers.EvidenceMatrix(op21, dev)
+            sol = drivers.bipartite_solver(op12, op21, 0.8, 0.8, evidence1=ev1, evidence2=ev2, device=dev)
+            assert sol.mode == "i8" and sol.h1.evidence_from_pattern and sol.h2.evidence_from_pattern
+            drivers.run_loop(sol.step, 3, 0.0, True)
+            W1, W2 = op12.to_dense(), op21.to_dense()
+            s1o, s2o, _, _ = orc.bipartite_simrank_pp(W1, W2, orc.evidence(W1), orc.evidence(W2), 0.8, 0.8, 3, 0.0)
+            res = drivers.collect(sol, [list(range(120)), list(range(70))], "all")
+            worst = max(worst, float(np.abs(res.mats[0].numpy() - s1o).max()), float(np.abs(res.mats[1].numpy() - s2o).max()))
+            with pytest.raises(NotImplementedError, match="symmetric prior"):
+                drivers.directed_solver(op, 0.8, prior=np.triu(np.ones((260, 260))), lbd=0.5, device=dev)
+            out.put((rank, worst, 0.0, sol.h1.rows))
         elif case == "directed_csr":
             # negative weight sums: rows of G with a negative scale (SimRank.py:45,49) -- float64 CSR path
             frm, to = synth.directed_edges(210, 1800, 0.8, 12)
@@ -169,7 +205,7 @@ def _worker(rank, world, port, case, out):
 
 @pytest.mark.parametrize("world,case", [(2, "directed"), (3, "directed"), (4, "directed"), (2, "bipartite"),
                                         (3, "bipartite"), (4, "bipartite"), (2, "directed_csr"),
-                                        (3, "bipartite_csr"), (4, "bipartite_csr")])
+                                        (3, "bipartite_csr"), (4, "bipartite_csr"), (2, "drivers")])
 def test_sharded_solver_matches_oracle(world, case):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
@@ -185,7 +221,7 @@ def test_sharded_solver_matches_oracle(world, case):
     for rank, err, derr, rows in results:
         assert err <= 1e-6, (rank, err)                 # fixed-point planes: north-star bound
         assert derr <= 1e-6
-    n = {"directed": 300, "directed_csr": 210}.get(case, 130)
+    n = {"directed": 300, "directed_csr": 210, "drivers": 120}.get(case, 130)
     assert sum(r[3] for r in results) == n              # the row blocks tile the matrix
 
 
