@@ -87,3 +87,24 @@ def test_csr_half_row_block_calls_single_gpu():
     off = got.copy()
     off[np.arange(L), r0 + np.arange(L)] = 0.0
     assert mo == off.max()
+
+
+@pytest.mark.parametrize("mode,tol", [("csr", 1e-13), ("i8", 1e-9)])
+def test_relabelling_the_nodes_permutes_the_result(mode, tol):
+    """Permutation equivariance (SURVEY.md section 4 iii): the similarity of two nodes does not depend
+    on their labels, on the node order the labels induce, or on where their rows fall in a tile."""
+    import numpy as np
+
+    from simrank_b200 import synth
+    from SimRank import SimRank as M
+
+    df = synth.directed_frame(1300, 26000, 0.8, 41)
+    labels = np.unique(np.concatenate([df["from"].to_numpy(), df["to"].to_numpy()]))
+    relabel = dict(zip(labels.tolist(), (np.random.default_rng(5).permutation(labels.size) * 7 + 3).tolist()))
+    df2 = df.assign(**{"from": df["from"].map(relabel), "to": df["to"].map(relabel)})
+    df2 = df2.sample(frac=1.0, random_state=3).reset_index(drop=True)               # and another edge order
+    S1 = M.SimRank(mode=mode).fit(df, iterations=4, eps=0.0, verbose=False)
+    S2 = M.SimRank(mode=mode).fit(df2, iterations=4, eps=0.0, verbose=False)
+    mapped = [relabel[x] for x in S1.index]
+    diff = np.abs(S1.to_numpy() - S2.loc[mapped, mapped].to_numpy()).max()
+    assert diff <= tol, diff
