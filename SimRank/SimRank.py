@@ -69,7 +69,10 @@ class _Base(object):
         if verbose:
             print('Start iterating...')
         on_it = (lambda it: update_progress(it / iterations)) if verbose else None
-        applied, conv, last = _drv.run_loop(solver.step, iterations, eps, pair, on_it)
+        halves = [h for h in (getattr(solver, "half", None), getattr(solver, "h1", None), getattr(solver, "h2", None))
+                  if h is not None]
+        initial = tuple(0.0 if h.n_out == 0 else 1.0 for h in halves)      # empty matrix: nothing differs
+        applied, conv, last = _drv.run_loop(solver.step, iterations, eps, pair, on_it, initial)
         if conv and verbose:
             sys.stdout.write(_converged_message(applied))
             sys.stdout.flush()

@@ -138,6 +138,8 @@ class DeviceOperator:
     def row_spread(self, vals: torch.Tensor | None = None) -> torch.Tensor:
         """exp(-var) of the nonzeros of each row (SimRank.py:326-332)."""
         out = torch.empty(self.M, dtype=torch.float64, device=self.device)
+        if self.M == 0:
+            return out
         _lib.check(_lib.load().srk_csr_row_spread(_ptr(self.indptr), _ptr(vals), _ptr(self.g), self.M, _ptr(out),
                                                   _stream()), "srk_csr_row_spread")
         return out
@@ -225,8 +227,9 @@ class _Half:
         self.ld = _round_up(max(self.n_out, 1), 16)
         self.S = torch.empty((self.n_out, self.ld), dtype=torch.float64, device=dev)
         lib = _lib.load()
-        _lib.check(lib.srk_set_identity_f64(_ptr(self.S), self.ld, self.n_out, self.n_out, 0, _stream()),
-                   "srk_set_identity_f64")
+        if self.n_out:                                            # an empty graph has an empty S (null data pointer)
+            _lib.check(lib.srk_set_identity_f64(_ptr(self.S), self.ld, self.n_out, self.n_out, 0, _stream()),
+                       "srk_set_identity_f64")
         self.evidence, self.prior, self.lbd = evidence, prior, float(lbd)
         self.scal = torch.zeros(2, dtype=torch.float64, device=dev)        # [maxdiff, maxoff]
         self.events = None          # set to a list to collect (name, start, end) CUDA events per launch
@@ -472,10 +475,12 @@ class BipartiteSolver:
         return self.h2.result()
 
 
-def run_loop(step, iterations: int, eps: float, pair: bool, on_iteration=None):
+def run_loop(step, iterations: int, eps: float, pair: bool, on_iteration=None, initial=None):
     """The reference's loop skeleton (SimRank.py:129-140 / 288-302): test convergence BEFORE each
-    update, using max|dS| of the previous update (``|I - 0|`` = 1 before the first)."""
-    last = (1.0, 1.0) if pair else (1.0,)
+    update, using max|dS| of the previous update (``|I - 0|`` = 1 before the first; ``initial``
+    overrides that: an empty matrix has no entry that differs, so an empty graph is converged at
+    iteration 0 as in the reference)."""
+    last = tuple(initial) if initial is not None else ((1.0, 1.0) if pair else (1.0,))
     applied, conv = 0, False
     for it in range(iterations):
         if all(not (d > eps) for d in last):

@@ -108,3 +108,23 @@ def test_relabelling_the_nodes_permutes_the_result(mode, tol):
     mapped = [relabel[x] for x in S1.index]
     diff = np.abs(S1.to_numpy() - S2.loc[mapped, mapped].to_numpy()).max()
     assert diff <= tol, diff
+
+
+def test_empty_edge_list_returns_empty_frames():
+    """An edge list without rows: the reference builds 0 x 0 matrices, finds nothing that differs
+    (`_converged` of two empty arrays) and returns empty DataFrames at iteration 0."""
+    import pandas as pd
+
+    from SimRank import SimRank as M
+
+    df = pd.DataFrame({"from": pd.Series([], dtype="int64"), "to": pd.Series([], dtype="int64"),
+                       "weight": pd.Series([], dtype="float64")})
+    for cls in (M.SimRank, M.SimRankPP):
+        obj = cls()
+        S = obj.fit(df, weighted=True, verbose=False)
+        assert S.shape == (0, 0) and obj.Nodes == set()
+        assert (obj.fit_info_.applied, obj.fit_info_.converged) == (0, True)
+    bi = df.rename(columns={"from": "user", "to": "item"})
+    obj = M.BipartiteSimRank()
+    S1, S2 = obj.fit(bi, verbose=False)
+    assert S1.shape == (0, 0) and S2.shape == (0, 0) and obj.fit_info_.converged

@@ -180,6 +180,8 @@ def test_run_loop_semantics():
     assert (applied, conv) == (3, True)                 # check happens BEFORE each update
     applied, conv, _ = run_loop(lambda: 0.5, 4, 1e-4, False)
     assert (applied, conv) == (4, False)                # last pair never checked (SimRank.py:129)
+    applied, conv, _ = run_loop(lambda: 1 / 0, 5, 1e-4, True, None, (0.0, 0.0))       # empty graph: no update at all
+    assert (applied, conv) == (0, True)
     applied, conv, _ = run_loop(lambda: 0.5, 0, 1e-4, False)
     assert (applied, conv) == (0, False)
     applied, conv, _ = run_loop(lambda: 0.5, 5, 1.0, False)
