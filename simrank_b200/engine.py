@@ -148,6 +148,8 @@ class DeviceOperator:
         """uint8 common-neighbour counts (clipped at 255) = the integer matmul of SimRank.py:315."""
         ld = _round_up(max(self.M, 1), 16)
         cnt = torch.empty((self.M, ld), dtype=torch.uint8, device=self.device)
+        if self.M == 0:
+            return cnt
         lib = _lib.load()
         # rows with G>0 False (g <= 0) must count as empty: only the CSR kernel knows `dead`
         has_dead = bool((self.host.dead.astype(bool) & (self.host.deg > 0)).any())
