@@ -33,8 +33,12 @@ class _Base(object):
     device : CUDA device (default: current)
     slices : uint8 planes per matrix in i8 mode: 2, 3, 4 or None/'auto' = the fewest planes whose
              guaranteed error bound stays below 5e-7 (simrank_b200.engine.choose_slices)
-    gather : under torch.distributed (one process per GPU, S row-sharded): 'all' returns the whole
-             matrix on every rank, 'local' returns each rank's own row block (all columns)
+    sharded: None (default) | True | False.  With torch.distributed initialised and more than one
+             rank, ``fit`` is a COLLECTIVE: every rank must call it with the same arguments, and S is
+             row-sharded over the ranks' GPUs (one process per GPU).  ``sharded=False`` keeps the fit
+             on the calling rank's own GPU; ``sharded=True`` insists on a process group.
+    gather : row-sharded fits only: 'all' returns the whole matrix on every rank, 'local' returns
+             each rank's own row block (all columns)
     result : 'frame' (the reference's DataFrames) or 'device' (fit returns the device-resident
              simrank_b200.drivers.Result; nothing is copied to the host until asked)
     label_order : bipartite only -- 'sorted' labels the result rows with the labels they belong
@@ -42,8 +46,9 @@ class _Base(object):
     """
 
     def _engine_options(self, mode=None, device=None, slices=None, label_order="sorted", gather="all",
-                        result="frame"):
+                        result="frame", sharded=None):
         self._mode, self._device, self._slices, self._label_order = mode, device, slices, label_order
+        self._sharded = sharded
         if result not in ("frame", "device"):
             raise ValueError("result must be 'frame' or 'device'")
         self._gather, self._result_kind = gather, result
@@ -76,7 +81,9 @@ class _Base(object):
         if conv and verbose:
             sys.stdout.write(_converged_message(applied))
             sys.stdout.flush()
-        self.fit_info_ = _drv.FitInfo(applied, conv, last, solver.mode)
+        self.fit_info_ = _drv.FitInfo(applied, conv, last, solver.mode,
+                                      tuple(tuple(getattr(h, "slices_used", ())) for h in halves),
+                                      tuple(float(getattr(h, "err", 0.0)) for h in halves))
         return applied, conv
 
     def _finish(self, solver, labels):
@@ -135,7 +142,8 @@ class SimRank(_Base):
         self._tick()
         self._create_graph(data, weighted, from_node_column, to_node_column, weight_column)
         self._tick("graph")
-        solver = _drv.directed_solver(self._graph_op, C, mode=self._mode, device=self._device, slices=self._slices)
+        solver = _drv.directed_solver(self._graph_op, C, mode=self._mode, device=self._device, slices=self._slices,
+                                      sharded=self._sharded)
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
         self._tick("iterate")
@@ -184,7 +192,7 @@ class SimRankPP(SimRank):
         self._prepare_pp(verbose)
         self._tick("graph")
         solver = _drv.directed_solver(self.Weight, C, evidence=self.Evidence, mode=self._mode,
-                                      device=self._device, slices=self._slices)
+                                      device=self._device, slices=self._slices, sharded=self._sharded)
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
         self._tick("iterate")
@@ -204,7 +212,8 @@ class AprioriSimRank(SimRankPP):
         self._prepare_pp(verbose)
         self._tick("graph")
         solver = _drv.directed_solver(self.Weight, C, evidence=self.Evidence, prior=AprioriSim, lbd=lbd,
-                                      mode=self._mode, device=self._device, slices=self._slices)
+                                      mode=self._mode, device=self._device, slices=self._slices,
+                                      sharded=self._sharded)
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=False)
         self._tick("iterate")
@@ -259,7 +268,7 @@ class BipartiteSimRank(_BipartiteGraphs, _Base):
         self._create_graph(data, weighted, node_group1_column, node_group2_column, weight_column)
         self._tick("graph")
         solver = _drv.bipartite_solver(self._op12, self._op21, C1, C2, mode=self._mode, device=self._device,
-                                       slices=self._slices)
+                                       slices=self._slices, sharded=self._sharded)
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
         self._tick("iterate")
@@ -299,7 +308,7 @@ class BipartiteSimRankPP(_BipartiteGraphs, SimRankPP):
         self._tick("graph")
         solver = _drv.bipartite_solver(self.Weight_N1, self.Weight_N2, C1, C2, evidence1=self.Evidence_N1,
                                        evidence2=self._group2_evidence(), mode=self._mode,
-                                       device=self._device, slices=self._slices)
+                                       device=self._device, slices=self._slices, sharded=self._sharded)
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
         self._tick("iterate")
@@ -323,7 +332,7 @@ class BipartitleAprioriSimRank(BipartiteSimRankPP):
         solver = _drv.bipartite_solver(self.Weight_N1, self.Weight_N2, C1, C2, evidence1=self.Evidence_N1,
                                        evidence2=self._group2_evidence(), prior1=AprioriSim1, prior2=AprioriSim2,
                                        lbd1=lbd1, lbd2=lbd2, mode=self._mode, device=self._device,
-                                       slices=self._slices)
+                                       slices=self._slices, sharded=self._sharded)
         self._tick("setup")
         self._iterate(solver, iterations, eps, verbose, pair=True)
         self._tick("iterate")

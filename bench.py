@@ -19,6 +19,13 @@ import sys
 import threading
 import time
 
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # The reference arm is numpy/OpenBLAS on the host cores.  torchrun exports OMP_NUM_THREADS=1 to its
+    # workers, which would time the reference on ONE core: give rank 0 (the only rank that works in
+    # this arm) the whole host back, before numpy loads its BLAS.
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -36,11 +43,13 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--n", type=int, default=32768, help="nodes (default: the BASELINE cfg4 size)")
     ap.add_argument("--mean-degree", type=int, default=64)
-    ap.add_argument("--mode", default="i8", choices=["i8", "i8v1", "csr"],
-                    help="dense tensor-core chain (graded; i8v1 = first-generation single-CTA kernel) or CSR SpMM")
+    ap.add_argument("--mode", default="i8", choices=["i8", "csr"],
+                    help="dense tensor-core chain (graded) or the float64 CSR SpMM path")
     ap.add_argument("--slices", default="auto", help="uint8 planes per matrix: 2, 3, 4 or auto (error-bound driven)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the float64 re-run that checks the timed solver's result (outside the timed region)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -140,6 +149,11 @@ def run_reference(args):
         return
     import psutil
     from oracle import cpu_baseline
+    try:                                        # the BLAS pool may have been created with one thread already
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        pass
     op, _, name = workload(args)
     res = cpu_baseline.iterations_per_second(op.indptr, op.indices, op.g, op.M, target_seconds=args.cpu_seconds,
                                              steps=args.steps, warmup=args.warmup,
@@ -219,7 +233,7 @@ def run_engine(args):
     flops_half = 2.0 * n * n * n / world                        # algorithmic: one n x n x n product, row-sharded
     kernels = {k: {"ms": statistics.mean(v), "launches": len(v)} for k, v in per.items()}
     used = sorted(set(x for h in halves for x in getattr(h, "slices_used", [])[-args.steps:])) or [args.slices or 3]
-    if args.mode in ("i8", "i8v1"):
+    if args.mode == "i8":
         gemms = {k: v for k, v in kernels.items() if "half" in k}
         dom = max(gemms, key=lambda k: gemms[k]["ms"])
         ach = flops_half / (kernels[dom]["ms"] * 1e-3) / 1e12
@@ -251,6 +265,9 @@ def run_engine(args):
             "algorithmic_tflops": 4.0 * n ** 3 / (ms * 1e-3) / 1e12,
             "roofline": roof, "kernels": kernels, "gpu_launches": launches,
             "last_maxdiff": last if not isinstance(last, tuple) else list(last)}
+
+    if not args.no_parity:
+        line["parity"] = run_parity(args, solver, halves, op, dev, world, args.warmup + args.steps)
 
     clk = clocks.summary()
     if world > 1:
@@ -286,6 +303,60 @@ def run_engine(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+PARITY_TOL = 1e-6          # north_star: max-abs 1e-6 against the float64 reference after K iterations
+
+
+def run_parity(args, solver, halves, op, dev, world, iterations):
+    """Check the matrix the timed solver ended with -- OUTSIDE the timed region.  Every rank re-runs
+    the same ``iterations`` updates from S = I on its own GPU with the single-GPU float64 CSR path
+    (the exact-arithmetic mode of this engine, itself held to 1e-12 against the numpy oracle by
+    tests/test_gpu_parity.py) and compares ALL rows it owns (the whole matrix at N = 1).  Also checks
+    the unit diagonal.  Raises (non-zero exit) when the deviation exceeds PARITY_TOL."""
+    import torch
+    import torch.distributed as dist
+    from simrank_b200 import engine
+    h = halves[0]
+    rows, row0 = (h.rows, h.row0) if world > 1 else (op.M, 0)
+    mine = h.S[:rows, :op.M]
+    ref = engine.DirectedSolver(engine.DeviceOperator(op, dev), 0.8, mode="csr")
+    for _ in range(iterations):
+        ref.step()
+    want = ref.S[row0:row0 + rows]
+    worst = float((mine - want).abs().max().item()) if rows else 0.0
+    diag_ok = bool((mine[torch.arange(rows, device=dev), row0 + torch.arange(rows, device=dev)] == 1.0).all().item()) \
+        if rows else True
+    top_ok = None
+    if rows:                                   # node-index parity: top-10 of 64 sampled rows, off-diagonal
+        pick = torch.linspace(0, rows - 1, min(rows, 64), device=dev).long()
+        a, b = mine[pick].clone(), want[pick].clone()
+        a[torch.arange(len(pick), device=dev), row0 + pick] = -1.0
+        b[torch.arange(len(pick), device=dev), row0 + pick] = -1.0
+        ia, va = engine.topk_rows(a.contiguous(), 10)
+        ib, vb = engine.topk_rows(b.contiguous(), 10)
+        # an index may only differ where the float64 values themselves are closer than the tolerance
+        # (near-ties): the float64 value of the node picked at rank p must be within 2 tol of the p-th best
+        same = ia == ib
+        gap_ok = (vb - torch.gather(b, 1, ia.long())).abs() <= 2 * PARITY_TOL
+        top_ok = bool((same | gap_ok).all().item())
+        top_same = float(same.double().mean().item())
+    del ref
+    torch.cuda.empty_cache()
+    out = {"max_abs": worst, "rows_checked": rows, "tol": PARITY_TOL, "iterations": iterations,
+           "unit_diagonal": diag_ok, "against": "single-GPU float64 CSR path of this engine, same graph, same iterations",
+           "topk10_consistent": top_ok, "topk10_identical_frac": top_same if rows else None}
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, out)
+        out = {"max_abs": max(e["max_abs"] for e in every), "rows_checked": sum(e["rows_checked"] for e in every),
+               "tol": PARITY_TOL, "iterations": iterations, "unit_diagonal": all(e["unit_diagonal"] for e in every),
+               "against": out["against"] + " (every rank checks the rows it owns)",
+               "topk10_consistent": all(e["topk10_consistent"] is not False for e in every),
+               "per_rank_max_abs": [e["max_abs"] for e in every]}
+    if not (out["max_abs"] <= PARITY_TOL and out["unit_diagonal"]):
+        raise SystemExit(f"PARITY FAILED: {json.dumps(out)}")
+    return out
 
 
 def run_e2e(args, edges, n, world, rank):

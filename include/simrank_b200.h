@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 8
+#define SRK_ABI_VERSION 9
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -124,39 +124,6 @@ int srk_slice_rows_f64(const double* V, int64_t ldv, int64_t R, int64_t K,
                        const srk_rowbound* rowbound, int64_t zero_diag_offset, int ns,
                        uint8_t* planes, int64_t ldp, int64_t plane_stride, void* stream);
 
-/* Workspace-free tensor-core half-product (tcgen05.mma kind::i8, TMEM accumulators, TMA feed):
- *   D[r, j] = sum_k V[r,k] * A8[j,k]      r < R (planes), j < N (dense 0/1 matrix, K columns)
- * mode SRK_I8_MID   : U[j, r] = (D[r,j] + unit_diag * A8[j, r + diag_offset]) is re-quantised
- *                     into `out_planes` (row j, column r: TRANSPOSED store) with bound
- *                     out_rowbound[j]; this is the first half `G.dot(S)` of SimRank.py:139.
- * mode SRK_I8_FINAL : S_new[r, j] = epilogue(g_row[r] * g_col[j] * D[r,j]) stored as f64 into
- *                     `out_f64` (+ optionally re-quantised into out_planes with out_rowbound[r],
- *                     diagonal forced to 0): the second half `.dot(G.T)` with everything of
- *                     SimRank.py:138-140 and :74 fused.
- * mode SRK_I8_COUNTS: counts[r, j] = min(D[r,j], 255) as uint8 into out_planes (ns must be 1,
- *                     in_rowbound ignored): the evidence product of SimRank.py:315.
- * diag_offset is the global row index of local row 0 (row-sharded operands).                */
-#define SRK_I8_MID 0
-#define SRK_I8_FINAL 1
-#define SRK_I8_COUNTS 2
-typedef struct srk_i8_args {
-  int mode, ns;
-  int64_t R, N, K;
-  const uint8_t* in_planes; int64_t ld_in; int64_t in_plane_stride;
-  /* K-blocked operand (row-sharded multi-GPU exchange buffers): when in_kblock > 0, column k of
-   * V is at in_planes + (k / in_kblock) * in_kblock_stride + s * in_plane_stride + r * ld_in +
-   * k % in_kblock; in_kblock must be a multiple of 128 and K a multiple of in_kblock.          */
-  int64_t in_kblock; int64_t in_kblock_stride;
-  srk_rowbound in_rowbound;             /* bound of V row r */
-  const uint8_t* A8; int64_t lda;       /* [N x K] 0/1 */
-  int64_t diag_offset; int unit_diag;
-  const double* g_row; const double* g_col;          /* FINAL */
-  double* out_f64; int64_t ld_out;                   /* FINAL */
-  uint8_t* out_planes; int64_t ld_outp; int64_t out_plane_stride;
-  srk_rowbound out_rowbound;            /* MID: bound of U row j; FINAL: bound of S_new row r */
-  srk_epilogue epi;                                  /* FINAL */
-} srk_i8_args;
-int srk_i8_half(const srk_i8_args* args, void* stream);
 /* 1 when the tcgen05 path can run on the current device (sm_100), else 0. */
 int srk_i8_supported(void);
 
@@ -200,8 +167,10 @@ int srk_i8_supported(void);
  *                     atomicMax a key of the largest off-diagonal value of every row of the result,
  *                     key = high word of the double + 1, so that (double)(key << 32) bounds the row
  *                     within 2^-20: the input of srk_slice_rows_key_f64, which then needs one pass.
- * mode SRK_X2_COUNTS: out_counts[j, r] = min(D[j,r], 65535) as uint16, or D[j,r] as uint32 when
- *                     counts_bits == 32 (needed once two rows can share 65535 neighbours) (ns must be 1, V = a 0/1
+ * mode SRK_X2_COUNTS: out_counts[j, r] = min(D[j,r], 65535) as uint16, D[j,r] as uint32 when
+ *                     counts_bits == 32 (needed once two rows can share 65535 neighbours), or
+ *                     min(D[j,r], 255) as uint8 when counts_bits == 8 (the srk_epilogue.evidence format:
+ *                     a count >= 54 already gives exactly 1.0) (ns must be 1, V = a 0/1
  *                     matrix as a single plane): `np.dot((G>0).astype(int), (G>0).T.astype(int))`
  *                     of SimRank.py:315, also the A A^T term above.                              */
 #define SRK_X2_MID 0
@@ -215,14 +184,17 @@ typedef struct srk_x2_args {
   int64_t M, R, K;
   const uint8_t* A8; int64_t lda;                                    /* [M x K] 0/1 */
   const uint8_t* in_planes; int64_t ld_in; int64_t in_plane_stride;  /* V: NS planes [R x K] */
-  int64_t in_kblock; int64_t in_kblock_stride;                       /* as in srk_i8_args */
+  /* K-blocked operand (row-sharded multi-GPU exchange buffers): when in_kblock > 0, column k of V is at
+   * in_planes + (k / in_kblock) * in_kblock_stride + s * in_plane_stride + r * ld_in + k % in_kblock;
+   * in_kblock must be a multiple of 128 and K a multiple of in_kblock.                           */
+  int64_t in_kblock; int64_t in_kblock_stride;
   srk_rowbound in_rowbound;                                          /* bound of V row r */
   uint8_t* out_planes; int64_t ld_outp; int64_t out_plane_stride;    /* MID */
   srk_rowbound out_rowbound;                                         /* MID: bound of U row j */
   const double* g_a; const double* g_v;                              /* FINAL: row factors of A8 / V rows */
   const void* counts; int64_t ld_counts;                             /* FINAL (indexed like out_f64) */
   int add_counts, use_evidence;
-  int counts_bits;                                                   /* 16 (default when 0) or 32: element type of counts / out_counts */
+  int counts_bits;                                                   /* 16 (default when 0) or 32: element type of counts / out_counts; COUNTS also 8 */
   double* out_f64; int64_t ld_out; int64_t diag_offset;              /* FINAL */
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;        /* FINAL, TRANSPOSED: see above */
   uint32_t* rowmax_hi;                                               /* FINAL: see above */

@@ -11,9 +11,8 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
-SRK_I8_MID, SRK_I8_FINAL, SRK_I8_COUNTS = 0, 1, 2
 SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
 SRK_X2_DIRECT, SRK_X2_SYMMETRIC, SRK_X2_TRANSPOSED = 0, 1, 2
 
@@ -41,21 +40,6 @@ class RowBound(C.Structure):
         rb = cls()
         rb.vec, rb.mul, rb.add = vec_ptr, float(mul), float(add)
         return rb
-
-
-class I8Args(C.Structure):
-    _fields_ = [("mode", C.c_int), ("ns", C.c_int),
-                ("R", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
-                ("in_planes", C.c_void_p), ("ld_in", C.c_int64), ("in_plane_stride", C.c_int64),
-                ("in_kblock", C.c_int64), ("in_kblock_stride", C.c_int64),
-                ("in_rowbound", RowBound),
-                ("A8", C.c_void_p), ("lda", C.c_int64),
-                ("diag_offset", C.c_int64), ("unit_diag", C.c_int),
-                ("g_row", C.c_void_p), ("g_col", C.c_void_p),
-                ("out_f64", C.c_void_p), ("ld_out", C.c_int64),
-                ("out_planes", C.c_void_p), ("ld_outp", C.c_int64), ("out_plane_stride", C.c_int64),
-                ("out_rowbound", RowBound),
-                ("epi", Epilogue)]
 
 
 class X2Args(C.Structure):
@@ -90,7 +74,6 @@ SYMBOLS = {
     "srk_csr_row_spread": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "srk_csr_to_dense_u8": (_INT, [_P, _P, _I64, _I64, _I64, _P, _I64, _P]),
     "srk_slice_rows_f64": (_INT, [_P, _I64, _I64, _I64, C.POINTER(RowBound), _I64, _INT, _P, _I64, _I64, _P]),
-    "srk_i8_half": (_INT, [C.POINTER(I8Args), _P]),
     "srk_x2_half": (_INT, [C.POINTER(X2Args), _P]),
     "srk_slice_rows_max_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _INT, _P, _I64, _I64, _P, _P]),
     "srk_slice_rows_key_f64": (_INT, [_P, _I64, _I64, _I64, _I64, _INT, _P, _P, _I64, _I64, _P, _P]),

@@ -382,6 +382,7 @@ struct Params {
   // FINAL
   const double* g_a; const double* g_v;
   const void* counts; int64_t ld_counts; int add_counts, use_evidence, counts32;
+  int out_counts8;             // COUNTS: clip to 255 and store uint8 (the evidence counts of SimRank.py:315)
   double* out_f64; int64_t ld_out; int64_t diag_offset;
   double* mirror_out; int64_t ld_mirror; int64_t mirror_col0;
   uint32_t* rowmax_hi;
@@ -680,6 +681,21 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
         if (MODE == SRK_X2_COUNTS) {
           if (!jvalid) continue;
+          if (p.out_counts8) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int x = 0; x < 16; ++x)
+              w[x >> 2] |= ((rc + x < p.R) ? min(a[0][x], 255u) : 0u) << (8 * (x & 3));
+            uint8_t* o = reinterpret_cast<uint8_t*>(p.out_counts) + j * p.ld_out_counts + rc;
+            if (rc + 16 <= p.ld_out_counts && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+              for (int x = 0; x < 16; ++x)
+                if (rc + x < p.R) o[x] = (uint8_t)((w[x >> 2] >> (8 * (x & 3))) & 0xffu);
+            }
+            continue;
+          }
           if (p.counts32) {
             uint32_t* o = reinterpret_cast<uint32_t*>(p.out_counts) + j * p.ld_out_counts + rc;
             if (rc + 16 <= p.ld_out_counts && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -1015,6 +1031,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.g_a = a.g_a; p.g_v = a.g_v;
   p.counts = a.counts; p.ld_counts = a.ld_counts; p.add_counts = a.add_counts; p.use_evidence = a.use_evidence;
   p.counts32 = a.counts_bits == 32;
+  p.out_counts8 = MODE == SRK_X2_COUNTS && a.counts_bits == 8;
   p.out_f64 = a.out_f64; p.ld_out = a.ld_out; p.diag_offset = a.diag_offset;
   p.mirror_out = a.mirror_out; p.ld_mirror = a.ld_mirror; p.mirror_col0 = a.mirror_col0;
   p.rowmax_hi = a.rowmax_hi;
@@ -1099,6 +1116,11 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
 
 using namespace srk;
 
+extern "C" int srk_i8_supported(void) {
+  int cc = srk_device_cc();
+  return cc >= 100 && cc < 103 ? 1 : 0;     // kind::i8 exists on sm_100a/sm_101a only
+}
+
 extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
   SRK_REQUIRE(a, "null args");
   SRK_REQUIRE(a->in_planes && a->A8, "null operand");
@@ -1118,7 +1140,8 @@ extern "C" int srk_x2_half(const srk_x2_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a->mode == SRK_X2_COUNTS) {
     SRK_REQUIRE(a->ns == 1 && a->out_counts && a->ld_out_counts >= a->R, "COUNTS needs ns=1 and a count output");
-    SRK_REQUIRE(a->counts_bits == 0 || a->counts_bits == 16 || a->counts_bits == 32, "counts_bits must be 16 or 32");
+    SRK_REQUIRE(a->counts_bits == 0 || a->counts_bits == 8 || a->counts_bits == 16 || a->counts_bits == 32,
+                "counts_bits must be 8, 16 or 32");
     return x2::launch<1, SRK_X2_COUNTS>(*a, st);
   }
   SRK_REQUIRE(a->ns == 1 || a->in_plane_stride % 16 == 0, "plane stride must be a multiple of 16");

@@ -37,7 +37,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import _ptr, _round_up, _stream, attach_sync_ws, choose_slices, count_bits
+from .engine import _ptr, _round_up, _stream, attach_sync_ws, choose_slices, count_bits, slice_delta
 from .graph import HostOperator
 
 _NO_DIAGONAL = -(1 << 40)
@@ -164,6 +164,7 @@ class ShardedHalf:
         self.symmetric = prior is None
         self.events = None
         self.slices_used = []
+        self.err = self._err_next = 0.0                             # see engine._Half.err
         self.ns_alloc = 3 if ns in (None, "auto") else int(ns)
         self.ex = exchange if exchange is not None else make_exchange(device, group)
         dev = device
@@ -381,6 +382,8 @@ class ShardedHalf:
             if not self.ex.peer:
                 self.send_U = torch.zeros((self.world, ns, self.per, 16), dtype=torch.uint8, device=self.device)
         self.slices_used.append(ns)
+        self._err_next = blend * self.coef * self.rho_max ** 2 * src.err + \
+            slice_delta(ns, self.coef, blend, self.rho_max, src.maxoff)
         guard = 1.0 + 2.0 ** -14
         bound_mul = src.maxoff * guard                             # U[j, :] <= deg_j * max(S_off)
         self._timed("x2_half_mid", lambda: self._mid(src, ns, bound_mul))
@@ -395,6 +398,7 @@ class ShardedHalf:
         self._reduce_scalars()
         maxdiff, maxoff = self.scal.tolist()
         self.maxoff = maxoff
+        self.err = self._err_next
         return maxdiff
 
     def local_result(self) -> torch.Tensor:
@@ -516,20 +520,27 @@ def _rank_world(group=None):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
-def _sharded_mode(mode, *ops) -> str:
-    """'i8' (tensor-core planes, peer-memory exchange) or 'csr' (float64, all-to-all exchange).  The
-    fixed-point planes hold non-negative similarities, so the tensor-core path needs finite,
-    non-negative row scales (as engine.choose_mode demands on one GPU): asked for explicitly on
-    anything else it fails loudly, left to 'auto' such a graph takes the CSR path."""
+def _sharded_mode(mode, *ops, coefs=None, lbds=None, has_prior=False) -> str:
+    """'i8' (tensor-core planes, peer-memory exchange) or 'csr' (float64, all-to-all exchange), by the
+    rules of engine.choose_mode so that 'auto' picks the same arithmetic on 1 and on N GPUs: the
+    fixed-point planes need finite, non-negative row scales, C > 0 and 0 <= lbd <= 1 (asked for
+    explicitly on anything else it fails loudly), and 'auto' keeps small, very sparse or
+    non-contracting problems on the float64 path."""
+    from .engine import choose_mode
     mode = (mode or "auto").lower()
     if mode not in ("auto", "i8", "csr"):
         raise ValueError(f"unknown mode {mode!r} for the row-sharded solver")
-    ok = all(bool(np.all(np.isfinite(np.asarray(op.g))) and np.all(np.asarray(op.g) >= 0)) for op in ops)
-    if mode == "i8" and not ok:
-        raise ValueError("mode='i8' needs finite, non-negative 1/inNeighbors; use mode='csr' (float64)")
-    if mode == "auto":
-        return "i8" if ok else "csr"
-    return mode
+    coefs = coefs or (0.8,) * len(ops)
+    lbds = lbds or (0.0,) * len(ops)
+    if torch.cuda.is_available():
+        picks = {choose_mode(op, mode, c, l, has_prior) for op, c, l in zip(ops, coefs, lbds)}
+    else:            # CPU emulation of the host logic (tests/test_dist_gloo.py): no device to ask
+        from .engine import fixed_point_obstacle
+        bad = [fixed_point_obstacle(op, c, l, has_prior) for op, c, l in zip(ops, coefs, lbds)]
+        if mode == "i8" and any(bad):
+            raise ValueError(f"mode='i8' {next(b for b in bad if b)}; use mode='csr' (float64)")
+        picks = {"csr" if (mode == "csr" or b) else "i8" for b in bad}
+    return picks.pop() if len(picks) == 1 else "csr"
 
 
 class ShardedDirectedSolver:

@@ -110,12 +110,19 @@ def _require_symmetric_prior(*priors):
                                       "AprioriSim on one GPU")
 
 
-def _world():
-    """(rank, world) of the default process group, (0, 1) when torch.distributed is not in use."""
+def _world(sharded=None):
+    """(rank, world) a fit runs on.  ``sharded=None`` (default): the default process group when
+    torch.distributed is initialised with more than one rank -- every rank must then call ``fit``
+    with the same arguments (it is a collective: S is row-sharded over the ranks) -- else (0, 1).
+    ``sharded=False`` keeps a fit on the calling rank's own GPU whatever the process group;
+    ``sharded=True`` insists on a process group."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return dist.get_rank(), dist.get_world_size()
-    return 0, 1
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if sharded is False or (sharded is None and not active):
+        return 0, 1
+    if not active:
+        raise RuntimeError("sharded=True needs an initialised torch.distributed process group with world size > 1")
+    return dist.get_rank(), dist.get_world_size()
 
 
 def _local_rows(t, n, rank, world):
@@ -136,34 +143,37 @@ def _evidence_args(evidence, op: HostOperator, mode: str):
     return evidence.counts, False
 
 
-def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mode=None, device=None, slices=None):
+def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mode=None, device=None, slices=None,
+                    sharded=None):
     dop = _device_op(op, device)
     pr = _prior_tensor(prior, op.M, dop.device)
-    rank, world = _world()
-    if world > 1:                      # one process per GPU: S row-sharded, tensor-core path
+    rank, world = _world(sharded)
+    if world > 1:                      # one process per GPU: S row-sharded
         from . import dist as _sd
         _require_symmetric_prior(prior)
-        smode = _sd._sharded_mode(_mode_with_prior(mode, prior), op)
+        smode = _sd._sharded_mode(_mode_with_prior(mode, prior), op, coefs=(C,), lbds=(lbd,),
+                                  has_prior=prior is not None)
         ev, from_pattern = _evidence_args(evidence, op, smode)
         return _sd.ShardedDirectedSolver(op, C, _local_rows(ev, op.M, rank, world),
                                          _local_rows(pr, op.M, rank, world), lbd, smode,
                                          slices, dop.device, evidence_from_pattern=from_pattern)
-    mode = _eng.choose_mode(op, _mode_with_prior(mode, prior))
+    mode = _eng.choose_mode(op, _mode_with_prior(mode, prior), C, lbd, prior is not None)
     ev, from_pattern = _evidence_args(evidence, op, mode)
     return _eng.DirectedSolver(dop, C, ev, pr, lbd, mode, slices,
                                evidence_from_pattern=from_pattern)
 
 
 def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=None, evidence2=None, prior1=None,
-                     prior2=None, lbd1=0.0, lbd2=0.0, mode=None, device=None, slices=None):
+                     prior2=None, lbd1=0.0, lbd2=0.0, mode=None, device=None, slices=None, sharded=None):
     d12, d21 = _device_op(op12, device), _device_op(op21, device)
     p1 = _prior_tensor(prior1, op12.M, d12.device)
     p2 = _prior_tensor(prior2, op21.M, d21.device)
-    rank, world = _world()
+    rank, world = _world(sharded)
     if world > 1:
         from . import dist as _sd
         _require_symmetric_prior(prior1, prior2)
-        smode = _sd._sharded_mode(_mode_with_prior(mode, prior1, prior2), op12, op21)
+        smode = _sd._sharded_mode(_mode_with_prior(mode, prior1, prior2), op12, op21, coefs=(C1, C2),
+                                  lbds=(lbd1, lbd2), has_prior=prior1 is not None or prior2 is not None)
         e1, pat1 = _evidence_args(evidence1, op12, smode)
         e2, pat2 = _evidence_args(evidence2, op21, smode)
         return _sd.ShardedBipartiteSolver(op12, op21, C1, C2, _local_rows(e1, op12.M, rank, world),
@@ -172,7 +182,8 @@ def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=N
                                           smode, slices, d12.device,
                                           evidence1_from_pattern=pat1, evidence2_from_pattern=pat2)
     mode = _mode_with_prior(mode, prior1, prior2)
-    m1, m2 = _eng.choose_mode(op12, mode), _eng.choose_mode(op21, mode)
+    m1 = _eng.choose_mode(op12, mode, C1, lbd1, prior1 is not None)
+    m2 = _eng.choose_mode(op21, mode, C2, lbd2, prior2 is not None)
     mode = m1 if m1 == m2 else "csr"
     e1, pat1 = _evidence_args(evidence1, op12, mode)
     e2, pat2 = _evidence_args(evidence2, op21, mode)

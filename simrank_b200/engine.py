@@ -18,7 +18,6 @@ plus the reduction behind ``_converged`` (SimRank.py:74) is two kernel launches 
                                              srk_x2_half FINAL  (fused epilogue, in place; only
                                                                  the upper triangle is computed,
                                                                  the lower one is mirrored)
-  i8v1 mode  the first-generation single-CTA kernel (srk_i8_half), kept for comparison
 
 S is updated in place: each epilogue thread reads S_old[r, c] for max|dS| and then writes
 S_new[r, c]; nothing else reads S during the second half.
@@ -157,13 +156,14 @@ class DeviceOperator:
                                                     self.M >= 2048 and self.M * self.lda <= (8 << 30)))
         if use_i8:
             a8 = self.dense_u8()
-            args = _lib.I8Args()
-            args.mode, args.ns = _lib.SRK_I8_COUNTS, 1
-            args.R, args.N, args.K = self.M, self.M, self.K
-            args.in_planes, args.ld_in, args.in_plane_stride = a8.data_ptr(), self.lda, a8.numel()
-            args.A8, args.lda = a8.data_ptr(), self.lda
-            args.out_planes, args.ld_outp, args.out_plane_stride = cnt.data_ptr(), ld, cnt.numel()
-            _lib.check(lib.srk_i8_half(C.byref(args), _stream()), "srk_i8_half(COUNTS)")
+            a = _lib.X2Args()
+            a.mode, a.ns = _lib.SRK_X2_COUNTS, 1
+            a.M, a.R, a.K = self.M, self.M, self.K
+            a.A8, a.lda = a8.data_ptr(), self.lda
+            a.in_planes, a.ld_in, a.in_plane_stride = a8.data_ptr(), self.lda, a8.numel()
+            a.out_counts, a.ld_out_counts, a.counts_bits = cnt.data_ptr(), ld, 8
+            attach_sync_ws(a, self.device)
+            _lib.check(lib.srk_x2_half(C.byref(a), _stream()), "srk_x2_half(COUNTS, uint8)")
         else:
             _lib.check(lib.srk_csr_evidence_counts(_ptr(self.indptr), _ptr(self.indices), _ptr(self.dead), self.M,
                                                    0, self.M, _ptr(cnt), ld, _stream()), "srk_csr_evidence_counts")
@@ -177,20 +177,55 @@ def count_bits(deg: np.ndarray) -> int:
     return 16 if int(np.partition(deg, -2)[-2]) < 65535 else 32
 
 
-def choose_mode(op: HostOperator, requested: str | None = None) -> str:
-    """'csr' (exact f64 gather path) or 'i8' (tcgen05 fixed-point path)."""
+def fixed_point_obstacle(op: HostOperator, coef: float = 0.8, lbd: float = 0.0, has_prior: bool = False):
+    """Why the fixed-point (tensor-core) path cannot hold this problem, or None.  The planes store
+    non-negative similarities and the kernels treat non-positive / non-finite factors as 0, so the
+    path needs finite row scales g >= 0, a decay factor C > 0 and a blend weight 0 <= lbd <= 1."""
+    g = np.asarray(op.g)
+    if not bool(np.all(np.isfinite(g))) or not bool(np.all(g >= 0)):
+        return "needs finite, non-negative 1/inNeighbors (negative or zero weight sums)"
+    if not (np.isfinite(coef) and coef > 0):
+        return f"needs a decay factor C > 0 (got {coef!r})"
+    if has_prior and not (0.0 <= lbd <= 1.0):
+        return f"needs 0 <= lbd <= 1 (got {lbd!r})"
+    return None
+
+
+def contraction(op: HostOperator, coef: float, blend: float = 1.0) -> float:
+    """kappa = blend * C * max_i (row sum of G)^2: factor by which one update shrinks earlier errors."""
+    rho = np.asarray(op.g) * op.deg
+    rho_max = float(np.abs(rho).max()) if rho.size else 0.0
+    return float(blend) * float(coef) * rho_max * rho_max
+
+
+def choose_mode(op: HostOperator, requested: str | None = None, coef: float = 0.8, lbd: float = 0.0,
+                has_prior: bool = False) -> str:
+    """'csr' (exact f64 gather path) or 'i8' (tcgen05 fixed-point path).  An explicit 'i8' that the
+    fixed-point path cannot hold raises; 'auto' sends such problems -- and updates that do not
+    contract (kappa >= 1: the a-priori error bound of choose_slices does not exist) -- to 'csr'."""
     mode = (requested or os.environ.get("SIMRANK_B200_MODE", "auto")).lower()
-    if mode in ("csr", "i8", "i8v1"):
+    if mode == "csr":
+        return mode
+    obstacle = fixed_point_obstacle(op, coef, lbd, has_prior)
+    if mode == "i8":
+        if obstacle:
+            raise ValueError(f"mode='i8' {obstacle}; use mode='csr' (float64)")
         return mode
     if mode != "auto":
         raise ValueError(f"unknown mode {mode!r}")
-    ok = bool(_lib.load().srk_i8_supported()) and bool(np.all(op.g >= 0)) and bool(np.all(np.isfinite(op.g)))
+    blend = (1.0 - lbd) if has_prior else 1.0
+    ok = bool(_lib.load().srk_i8_supported()) and obstacle is None and contraction(op, coef, blend) < 0.999
     dense_bytes = op.M * _round_up(op.K, 128)
     density = op.nnz / max(1, op.M * op.K)
     return "i8" if ok and min(op.M, op.K) >= 1024 and dense_bytes <= (16 << 30) and density >= 1.0 / 1024 else "csr"
 
 
 # --------------------------------------------------------------------------- one similarity matrix
+def slice_delta(ns: int, coef: float, blend: float, rho_max: float, s_off_max: float) -> float:
+    """Largest deviation ONE update adds (see choose_slices)."""
+    return 1.5 * blend * coef * rho_max * rho_max * s_off_max / 256.0 ** ns
+
+
 def choose_slices(requested, coef: float, blend: float, rho_max: float, s_off_max: float) -> int:
     """Planes per matrix for one update of the tensor-core path.
 
@@ -202,16 +237,19 @@ def choose_slices(requested, coef: float, blend: float, rho_max: float, s_off_ma
     G, 1 for unweighted graphs), and the update contracts earlier errors by kappa = blend * coef *
     rho_max^2, so the deviation from the float64 iteration never exceeds delta / (1 - kappa).  The
     smallest NS in {2, 3, 4} that keeps this below ERR_BUDGET is used; an integer request is
-    honoured as is."""
+    honoured as is.  When the update does not contract (kappa >= 1; 'auto' mode sends those graphs
+    to the float64 path, engine.choose_mode) there is no such series: 4 planes are used and the bound
+    that holds after k updates is the recursion the solver tracks (``_Half.err``, FitInfo.error_bound)."""
     if requested not in (None, "auto"):
         ns = int(requested)
         if ns not in (2, 3, 4):
             raise ValueError("slices must be 2, 3, 4 or 'auto'")
         return ns
     kappa = blend * coef * rho_max * rho_max
-    amplification = 1.0 / (1.0 - kappa) if kappa < 0.999 else 1000.0
+    if not kappa < 0.999:
+        return 4
     for ns in (2, 3, 4):
-        if 1.5 * kappa * s_off_max / 256.0 ** ns * amplification <= ERR_BUDGET:
+        if slice_delta(ns, coef, blend, rho_max, s_off_max) / (1.0 - kappa) <= ERR_BUDGET:
             return ns
     return 4
 
@@ -237,6 +275,7 @@ class _Half:
         self.events = None          # set to a list to collect (name, start, end) CUDA events per launch
         self.maxoff = 0.0                                                  # max off-diagonal of current S
         self.slices_used = []                                              # NS of every update (i8 mode)
+        self.err = 0.0              # guaranteed max-abs deviation of S from the float64 iteration (i8 mode)
         if mode == "csr":
             self.ldt = _round_up(max(self.n_out, 1), 16)
             self.T = torch.empty((self.n_in, self.ldt), dtype=torch.float64, device=dev)
@@ -249,15 +288,6 @@ class _Half:
         self.ldu = _round_up(max(self.n_in, 1), 128)                       # planes of U (n_out x n_in)
         self.a8 = op.dense_u8()
         self.deg_dev = torch.from_numpy(host.deg.astype(np.float64)).to(dev)
-        if mode == "i8v1":
-            ns = self.ns = 3 if ns in (None, "auto") else int(ns)
-            self.planes = torch.zeros((ns, self.n_out, self.ldp), dtype=torch.uint8, device=dev)   # S_off = 0
-            self.planes_U = torch.empty((ns, self.n_out, self.ldu), dtype=torch.uint8, device=dev)
-            self.rho_dev = torch.from_numpy(np.ascontiguousarray(self.rho)).to(dev)
-            # bound(r) of the current planes of S_off as (mul, add) over rho, and its maximum
-            self.bound_S = (0.0, 1.0)                                      # planes are all zero: any bound
-            self.bound_S_max = 1.0
-            return
         # ---- paired-SM path: planes are cut from S right before they are used, with exact bounds
         self.ns_alloc = 3 if ns in (None, "auto") else int(ns)
         self.planes = None                                                 # allocated on first use as a source
@@ -325,14 +355,16 @@ class _Half:
                 _ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M, _ptr(self.T), self.ldt, self.n_out,
                 _ptr(self.S), self.ld, C.byref(epi), _stream())), "srk_csr_half_f64(second)")
             return
-        if self.mode == "i8v1":
-            return self._update_v1(src)
         # ---- paired-SM tensor-core path
         blend = (1.0 - self.lbd) if self.prior is not None else 1.0
         ns = choose_slices(self.ns, self.coef, blend, self.rho_max, src.maxoff)
         if ns > self.planes_U.shape[0]:
             self.planes_U = torch.empty((ns, self.n_out, self.ldu), dtype=torch.uint8, device=self.S.device)
         self.slices_used.append(ns)
+        # e_new <= kappa * e(S_in) + delta: the update maps a perturbation of S_in of size e to at most
+        # kappa * e, and its own two roundings add at most delta (choose_slices)
+        self._err_next = blend * self.coef * self.rho_max ** 2 * src.err + \
+            slice_delta(ns, self.coef, blend, self.rho_max, src.maxoff)
         planes_in = src._planes_for(ns)
         # U[j, r] = sum_{k in N(j)} S_off[r, k] <= deg_j * max(S_off); the guard keeps a value that
         # attains the bound below the last level (>= 256^NS / (256^NS - 1) for every NS >= 2)
@@ -371,54 +403,12 @@ class _Half:
                    "srk_x2_half(FINAL)")
         self.version += 1
 
-    def _update_v1(self, src: "_Half") -> None:
-        """First-generation kernel: planes written by the FINAL epilogue with a-priori bounds."""
-        lib = _lib.load()
-        # The planes of S_in were cut with src.bound_S; the ACTUAL off-diagonal maximum of S_in is
-        # known from its epilogue (src.maxoff) and tightens everything derived from it.
-        guard = 1.0 + 2.0 ** -20          # keeps values that attain a bound exactly off the clip
-        s_off = min(src.bound_S_max, src.maxoff * (1.0 + 1e-6) + src.bound_S_max * 2.0 ** -23)
-        # U[j, r] = A[j, r] + sum_m A[j, m] S_off[r, m]  <=  1 + deg_j * max(S_off)
-        bound_U = _lib.RowBound.of(self.deg_dev.data_ptr(), s_off * guard, guard)
-        # S_new[r, j] <= (1-lbd) * coef * rho_r * rho_max * max(1, max S_in)  +  lbd * max(prior)
-        blend = (1.0 - self.lbd) if self.prior is not None else 1.0
-        mul = blend * self.coef * self.rho_max * max(1.0, s_off) * guard
-        add = self.lbd * self.prior_max * guard if self.prior is not None else 0.0
-        bound_new = _lib.RowBound.of(self.rho_dev.data_ptr(), mul, add)
-
-        a = _lib.I8Args()
-        a.mode, a.ns = _lib.SRK_I8_MID, self.ns
-        a.R, a.N, a.K = src.n_out, self.n_out, self.n_in          # planes of S_in: n_in x n_in
-        a.in_planes, a.ld_in, a.in_plane_stride = src.planes.data_ptr(), src.ldp, src.planes.stride(0)
-        a.in_rowbound = _lib.RowBound.of(src.rho_dev.data_ptr(), *src.bound_S)
-        a.A8, a.lda = self.a8.data_ptr(), self.op.lda
-        a.diag_offset, a.unit_diag = 0, 1
-        a.out_planes, a.ld_outp, a.out_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
-        a.out_rowbound = bound_U
-        _lib.check(self._timed("i8_half_mid", lambda: lib.srk_i8_half(C.byref(a), _stream())), "srk_i8_half(MID)")
-
-        b = _lib.I8Args()
-        b.mode, b.ns = _lib.SRK_I8_FINAL, self.ns
-        b.R, b.N, b.K = self.n_out, self.n_out, self.n_in
-        b.in_planes, b.ld_in, b.in_plane_stride = self.planes_U.data_ptr(), self.ldu, self.planes_U.stride(0)
-        b.in_rowbound = bound_U
-        b.A8, b.lda = self.a8.data_ptr(), self.op.lda
-        b.diag_offset, b.unit_diag = 0, 0
-        b.g_row = b.g_col = self.op.g.data_ptr()
-        b.out_f64, b.ld_out = self.S.data_ptr(), self.ld
-        b.out_planes, b.ld_outp, b.out_plane_stride = self.planes.data_ptr(), self.ldp, self.planes.stride(0)
-        b.out_rowbound = bound_new
-        b.epi = self._epilogue()
-        _lib.check(self._timed("i8_half_final", lambda: lib.srk_i8_half(C.byref(b), _stream())),
-                   "srk_i8_half(FINAL)")
-        self._pending_bound = ((mul, add), mul * self.rho_max + add)
-
     def finish(self) -> float:
         """Read back max|dS| (host sync) and commit the range of the new S."""
         maxdiff, maxoff = self.scal.tolist()
         self.maxoff = maxoff
-        if self.mode == "i8v1":
-            self.bound_S, self.bound_S_max = self._pending_bound
+        if self.mode != "csr":
+            self.err = self._err_next
         return maxdiff
 
     def result(self) -> torch.Tensor:
@@ -431,6 +421,8 @@ class FitInfo:
     converged: bool
     last_maxdiff: tuple
     mode: str
+    slices_used: tuple = ()      # i8 mode: planes of every update, per matrix
+    error_bound: tuple = ()      # i8 mode: guaranteed max-abs deviation from the float64 iteration, per matrix
 
 
 class DirectedSolver:
@@ -438,7 +430,7 @@ class DirectedSolver:
 
     def __init__(self, op: DeviceOperator, C_: float, evidence=None, prior=None, lbd=0.0, mode=None, ns=_NS_DEFAULT,
                  evidence_from_pattern=False):
-        self.mode = choose_mode(op.host, mode)
+        self.mode = choose_mode(op.host, mode, C_, lbd, prior is not None)
         self.half = _Half(op, C_, self.mode, ns, evidence, prior, lbd, evidence_from_pattern)
 
     def step(self) -> float:
@@ -456,7 +448,8 @@ class BipartiteSolver:
     def __init__(self, op12: DeviceOperator, op21: DeviceOperator, C1: float, C2: float, evidence1=None,
                  evidence2=None, prior1=None, prior2=None, lbd1=0.0, lbd2=0.0, mode=None, ns=_NS_DEFAULT,
                  evidence1_from_pattern=False, evidence2_from_pattern=False):
-        m1, m2 = choose_mode(op12.host, mode), choose_mode(op21.host, mode)
+        m1 = choose_mode(op12.host, mode, C1, lbd1, prior1 is not None)
+        m2 = choose_mode(op21.host, mode, C2, lbd2, prior2 is not None)
         self.mode = m1 if m1 == m2 else "csr"
         self.h1 = _Half(op12, C1, self.mode, ns, evidence1, prior1, lbd1, evidence1_from_pattern)   # S1 from S2 (G12)
         self.h2 = _Half(op21, C2, self.mode, ns, evidence2, prior2, lbd2, evidence2_from_pattern)   # S2 from S1 (G21)

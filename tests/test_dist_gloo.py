@@ -233,7 +233,7 @@ def test_sharded_solver_refuses_what_the_fixed_point_path_cannot_hold():
     ok = graph.operator_from_edges([0, 1], [1, 0], 2, 2)
     assert sdist._sharded_mode(None, ok) == "i8" and sdist._sharded_mode("csr", ok) == "csr"
     with pytest.raises(ValueError, match="unknown mode"):
-        sdist._sharded_mode("i8v1", ok)
+        sdist._sharded_mode("tf32", ok)
 
 
 def test_sharded_fit_needs_a_symmetric_prior():

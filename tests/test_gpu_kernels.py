@@ -187,7 +187,8 @@ def _pad_u8(a, ld):
 
 @needs_i8
 @pytest.mark.parametrize("M,K", [(10, 10), (128, 128), (129, 257), (300, 1000), (1000, 130), (700, 4100)])
-def test_i8_counts_exact(dev, M, K):
+def test_evidence_counts_tensor_core_uint8(dev, M, K):
+    """The uint8 evidence counts of SimRank.py:315 through srk_x2_half COUNTS (counts_bits = 8)."""
     rng = np.random.default_rng(M + K)
     A = (rng.random((M, K)) < 0.3).astype(np.uint8)
     A[M // 2] = 1                                          # a full row: counts up to K
@@ -197,118 +198,3 @@ def test_i8_counts_exact(dev, M, K):
     torch.cuda.synchronize()
     want = np.minimum(A.astype(np.int64) @ A.astype(np.int64).T, 255).astype(np.uint8)
     np.testing.assert_array_equal(cnt[:, :M].cpu().numpy(), want)
-
-
-def _planes_of(q, ns, ld):
-    R, K = q.shape
-    out = np.zeros((ns, R, ld), dtype=np.uint8)
-    for s in range(ns):
-        out[s, :, :K] = (q >> (8 * (ns - 1 - s))) & 0xFF
-    return out
-
-
-@needs_i8
-@pytest.mark.parametrize("ns", [2, 3, 4])
-@pytest.mark.parametrize("R,N,K", [(10, 10, 10), (128, 160, 128), (200, 333, 515), (513, 170, 129)])
-def test_i8_mid_against_integer_matmul(dev, ns, R, N, K):
-    """MID: planes in -> exact integer product -> (+ unit diagonal) -> re-quantised, transposed."""
-    rng = np.random.default_rng(ns * 100 + R)
-    qmax = 256 ** ns
-    q = rng.integers(0, qmax, (R, K), dtype=np.int64)
-    A = (rng.random((N, K)) < 0.2).astype(np.uint8)
-    ldk, ldr = engine._round_up(K, 128), engine._round_up(R, 128)
-    planes = torch.from_numpy(_planes_of(q, ns, ldk)).to(dev)
-    a8 = torch.from_numpy(_pad_u8(A, ldk)).to(dev)
-    in_vec = torch.from_numpy(rng.random(R) + 0.5).to(dev)
-    out_vec = torch.from_numpy(rng.integers(1, 50, N).astype(np.float64)).to(dev)
-    out = torch.zeros((ns, N, ldr), dtype=torch.uint8, device=dev)
-    a = _lib.I8Args()
-    a.mode, a.ns, a.R, a.N, a.K = _lib.SRK_I8_MID, ns, R, N, K
-    a.in_planes, a.ld_in, a.in_plane_stride = planes.data_ptr(), ldk, R * ldk
-    a.in_rowbound = _lib.RowBound.of(in_vec.data_ptr(), 0.9, 0.0)
-    a.A8, a.lda = a8.data_ptr(), ldk
-    unit = 1 if R <= K else 0
-    a.diag_offset, a.unit_diag = 0, unit
-    a.out_planes, a.ld_outp, a.out_plane_stride = out.data_ptr(), ldr, N * ldr
-    a.out_rowbound = _lib.RowBound.of(out_vec.data_ptr(), 1.5, 1.0)
-    _lib.check(_lib.load().srk_i8_half(C.byref(a), engine._stream()))
-    torch.cuda.synchronize()
-    D = q @ A.astype(np.int64).T                                        # exact
-    inb = in_vec.cpu().numpy() * 0.9
-    outb = out_vec.cpu().numpy() * 1.5 + 1.0
-    U = D.astype(np.float64) * (inb / qmax)[:, None]
-    if unit:
-        U = U + A[:, :R].T.astype(np.float64)
-    want = np.clip(np.rint(U * (qmax / outb)[None, :]), 0, qmax - 1).astype(np.int64).T      # [N, R]
-    p = out.cpu().numpy().astype(np.int64)
-    got = sum(p[s] << (8 * (ns - 1 - s)) for s in range(ns))[:, :R]
-    assert np.abs(got - want).max() <= 1, np.abs(got - want).max()
-    assert (got != want).mean() < 1e-3
-
-
-@needs_i8
-@pytest.mark.parametrize("ns", [2, 3, 4])
-@pytest.mark.parametrize("R,K,with_extras", [(10, 10, False), (160, 128, True), (333, 515, True), (515, 129, False)])
-def test_i8_final_against_integer_matmul(dev, ns, R, K, with_extras):
-    rng = np.random.default_rng(ns * 10 + R)
-    N = R
-    qmax = 256 ** ns
-    q = rng.integers(0, qmax, (R, K), dtype=np.int64)
-    A = (rng.random((N, K)) < 0.2).astype(np.uint8)
-    ldk, ldn = engine._round_up(K, 128), engine._round_up(N, 16)
-    ldp = engine._round_up(N, 128)
-    planes = torch.from_numpy(_planes_of(q, ns, ldk)).to(dev)
-    a8 = torch.from_numpy(_pad_u8(A, ldk)).to(dev)
-    in_vec = torch.from_numpy(rng.random(R) + 0.5).to(dev)
-    g = rng.random(N) * 0.01
-    gd = torch.from_numpy(g).to(dev)
-    S_old = rng.random((R, N))
-    S = torch.zeros((R, ldn), dtype=torch.float64, device=dev)
-    S[:, :N] = torch.from_numpy(S_old)
-    out_planes = torch.zeros((ns, R, ldp), dtype=torch.uint8, device=dev)
-    scal = torch.zeros(2, dtype=torch.float64, device=dev)
-    a = _lib.I8Args()
-    a.mode, a.ns, a.R, a.N, a.K = _lib.SRK_I8_FINAL, ns, R, N, K
-    a.in_planes, a.ld_in, a.in_plane_stride = planes.data_ptr(), ldk, R * ldk
-    a.in_rowbound = _lib.RowBound.of(in_vec.data_ptr(), 2.0, 1.0)
-    a.A8, a.lda = a8.data_ptr(), ldk
-    a.g_row = a.g_col = gd.data_ptr()
-    a.out_f64, a.ld_out = S.data_ptr(), ldn
-    a.out_planes, a.ld_outp, a.out_plane_stride = out_planes.data_ptr(), ldp, R * ldp
-    e = a.epi
-    e.coef = 0.8
-    e.s_old, e.ld_s_old = S.data_ptr(), ldn
-    e.maxdiff, e.maxoff = scal.data_ptr(), scal.data_ptr() + 8
-    cnt = prior = None
-    if with_extras:
-        cnt = rng.integers(0, 60, (R, N)).astype(np.uint8)
-        ev = torch.zeros((R, ldn), dtype=torch.uint8, device=dev)
-        ev[:, :N] = torch.from_numpy(cnt)
-        prior = rng.random((R, N))
-        pr = torch.from_numpy(prior).to(dev)
-        e.evidence, e.ld_evidence = ev.data_ptr(), ldn
-        e.prior, e.ld_prior, e.lambda_ = pr.data_ptr(), N, 0.25
-    D = (q @ A.astype(np.int64).T).astype(np.float64)
-    inb = in_vec.cpu().numpy() * 2.0 + 1.0
-    want = D * (inb / qmax)[:, None] * g[:, None] * g[None, :] * 0.8
-    if with_extras:
-        want = (1 - 0.25) * want * (1 - 0.5 ** cnt.astype(np.int64)) + 0.25 * prior
-    np.fill_diagonal(want, 1.0)
-    off = want.copy()
-    np.fill_diagonal(off, 0.0)
-    bound = off.max() * 1.001
-    a.out_rowbound = _lib.RowBound.of(None, 0.0, bound)
-    _lib.check(_lib.load().srk_i8_half(C.byref(a), engine._stream()))
-    torch.cuda.synchronize()
-    got = S[:, :N].cpu().numpy()
-    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
-    md, mo = scal.tolist()
-    assert md == np.abs(got - S_old).max()
-    goff = got.copy()
-    np.fill_diagonal(goff, 0.0)
-    assert mo == goff.max()
-    p = out_planes.cpu().numpy().astype(np.int64)
-    qq = sum(p[s] << (8 * (ns - 1 - s)) for s in range(ns))[:, :N]
-    wq = np.clip(np.rint(goff * (qmax / bound)), 0, qmax - 1).astype(np.int64)
-    assert np.abs(qq - wq).max() <= 1
-    assert not np.diag(qq).any()
