@@ -43,8 +43,8 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--n", type=int, default=32768, help="nodes (default: the BASELINE cfg4 size)")
     ap.add_argument("--mean-degree", type=int, default=64)
-    ap.add_argument("--mode", default="i8", choices=["i8", "csr"],
-                    help="dense tensor-core chain (graded) or the float64 CSR SpMM path")
+    ap.add_argument("--mode", default="i8", choices=["i8", "csr", "csr16"],
+                    help="dense tensor-core chain (graded), the float64 CSR SpMM path, or the fixed-point CSR SpMM path")
     ap.add_argument("--slices", default="auto", help="uint8 planes per matrix: 2, 3, 4 or auto (error-bound driven)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -247,17 +247,22 @@ def run_engine(args):
                          f"steps; the kernel executes {used} u8 x u8 -> s32 tcgen05 products per algorithmic one"
                          + ("; this launch computes only the upper triangle of the symmetric result" if sym else ""))}
     else:
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        halves_only = {k: v for k, v in kernels.items() if "half" in k}
+        dom = max(halves_only, key=lambda k: halves_only[k]["ms"])
         by = (3 if dom.endswith("final") else 2) * n * n * 8.0 / world
         ach = by / (kernels[dom]["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": ach / pk["hbm"], "traffic": ncu_traffic(dom, 0, n, world), "peak_kind": pk["source"],
-                "note": "algorithmic bytes: first half 2 n^2 s, second half 3 n^2 s (s = 8)"}
+                "note": "algorithmic bytes (SURVEY.md 8d): first half 2 n^2 s, second half 3 n^2 s (s = 8)",
+                "iteration": {"algorithmic_bytes": 5.0 * n * n * 8.0 / world,
+                              "achieved": 5.0 * n * n * 8.0 / world / (ms * 1e-3) / 1e9,
+                              "frac": 5.0 * n * n * 8.0 / world / (ms * 1e-3) / 1e9 / pk["hbm"]}}
 
     line = {"metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": (f"u8 x u8 -> s32 ({used} fixed-point planes), f64 epilogue" if args.mode != "csr" else "f64"),
+            "dtype": {"i8": f"u8 x u8 -> s32 ({used} fixed-point planes), f64 epilogue", "csr": "f64",
+                      "csr16": "u16 gather -> exact u32 sums, f64 epilogue"}[args.mode],
             "data": "synthetic",
             "config": {"workload": name, "mode": args.mode, "slices": args.slices or "auto", "slices_used": used,
                        "l2": "operands (>= 1 GB) are far larger than the 126 MB L2; no flush needed",

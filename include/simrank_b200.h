@@ -69,6 +69,17 @@ typedef struct srk_epilogue {
   int64_t diag_offset;       /* srk_csr_half_f64 only: see above */
 } srk_epilogue;
 
+/* Fixed-point planes (tensor-core path): a non-negative matrix V (R x K) with V[r,k] <= bound(r) is held as
+ * NS uint8 planes, plane s at `planes + s*plane_stride`, row-major with leading dimension
+ * ldp (multiple of 16), such that  V[r,k] ~= q[r,k] * bound(r) / 256^NS,
+ * q = sum_s plane_s[r,k] * 256^(NS-1-s).  The per-row bound is the affine form
+ * bound(r) = vec[r]*mul + add (vec == NULL: bound(r) = add), so that the caller can derive it
+ * from a constant per-node vector (degree, row sum of G) and per-iteration scalars.          */
+typedef struct srk_rowbound {
+  const double* vec;
+  double mul, add;
+} srk_rowbound;
+
 /* ----------------------------------------------------------------------------- CSR path (f64)
  * One half-product  OUT[c, i] = g[i] * sum_{m in N(i)} X[m, c]   (i < M, c < L), i.e.
  * OUT = (G X)^T, written transposed through shared memory so that two calls give
@@ -86,6 +97,55 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
                      const double* X, int64_t ldx, int64_t L,
                      double* OUT, int64_t ldo,
                      const srk_epilogue* final_epi, void* stream);
+
+/* The same half-product with the gather in FIXED POINT (elem = SRK_ELEM_U16), struct-argument form.
+ *
+ * X is a uint16 matrix with one scale per COLUMN: value(m, c) = X[m, c] * unit(c), unit(c) =
+ * in_unit.vec[c] * in_unit.mul + in_unit.add.  The sum over the neighbours m of a graph row is then
+ * an exact integer (row degrees < 65536), scaled once per output element -- 4x fewer gathered bytes
+ * than float64 with the rounding of the tensor-core path's 2 planes (DESIGN.md "K3").  The unit
+ * diagonal of S stays outside the fixed-point matrices (S = I + S_off, as in srk_x2_half):
+ *   mode SRK_CSR_FIRST  OUT[c, i] = rint(D[i, c] * unit(c) / (out_bound(i) / 65535)) as uint16, clipped;
+ *                       D[i, c] = sum_{m in N(i)} X[m, c].  With X = srk_quantize_rows_u16(S_in) this
+ *                       is U = A S_off transposed (`G.dot(S)` of SimRank.py:139 without g), column i
+ *                       in units of out_bound(i) / 65535, out_bound(i) >= deg(i) * max(S_off).
+ *   mode SRK_CSR_FINAL  x = g[i] * g_col[r] * (D[i, r] * unit(r) + counts[r, i])   (counts = A A^T when
+ *                       add_counts, the unit-diagonal term), then the srk_epilogue chain with the
+ *                       evidence factor taken from `counts` when use_evidence, stored as float64 at
+ *                       OUT[r, i] (r = column of X = output row).
+ *   symmetric != 0      (FINAL; square problem, whole row range, no prior, diag_offset 0, OUT row-major
+ *                       n x n): only pairs r >= i are computed and every value is stored at (i, r) AND
+ *                       (r, i); counts / s_old / evidence are read at (i, r) (they are symmetric).
+ * elem = SRK_ELEM_F64 is srk_csr_half_f64 (in_unit, out_bound, g_col, counts ignored), plus the
+ * symmetric second half.
+ * Bulk asynchronous copies need 16-byte aligned rows of X (X % 16 == 0, ldx * sizeof(elem) % 16 ==
+ * 0); other operands are gathered with plain loads (slower, same results).                      */
+#define SRK_ELEM_F64 0
+#define SRK_ELEM_U16 1
+#define SRK_CSR_FIRST 0
+#define SRK_CSR_FINAL 1
+typedef struct srk_csr_args {
+  int elem, mode, symmetric;
+  const int64_t* indptr; const int32_t* indices; const double* g;
+  int64_t M, row_begin, row_end;
+  const void* X; int64_t ldx; int64_t L;
+  void* OUT; int64_t ldo;
+  srk_rowbound in_unit;                                   /* U16: unit of column c of X */
+  srk_rowbound out_bound;                                 /* U16 FIRST: bound of output column i */
+  const double* g_col;                                    /* U16 FINAL: row factor of output row r */
+  const void* counts; int64_t ld_counts;                  /* uint16 / uint32 A A^T, indexed like OUT */
+  int counts_bits, add_counts, use_evidence;
+  srk_epilogue epi;                                       /* FINAL */
+} srk_csr_args;
+int srk_csr_half(const srk_csr_args* args, void* stream);
+
+/* Source operand of the fixed-point gather: unit[r] = max_k V[r, k] / 65535 (element (r, r +
+ * zero_diag_offset) excluded and stored as 0; negatives and NaN as 0), XT[k, r] = rint(V[r, k] /
+ * unit[r]) -- the TRANSPOSED matrix [K x ldxt] with one scale per column r.  For the symmetric S of
+ * SimRank this is S_off itself with column scales; for a row shard (R local rows) it is the column
+ * block the first half gathers from.  Columns R..ldxt-1 are zero-filled.                        */
+int srk_quantize_rows_u16(const double* V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
+                          uint16_t* XT, int64_t ldxt, double* unit, void* stream);
 
 /* Common-in-neighbour counts cnt[i,j] = |N(i) & N(j)| clipped to 255, for rows
  * [row_begin,row_end) x all j < M: `np.dot((G>0).astype(int), (G>0).T.astype(int))`
@@ -105,18 +165,7 @@ int srk_csr_row_spread(const int64_t* indptr, const double* vals, const double* 
 int srk_csr_to_dense_u8(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
                         int64_t row_end, int64_t K, uint8_t* A8, int64_t lda, void* stream);
 
-/* ----------------------------------------------------------------------------- tensor-core path
- * Fixed-point planes: a non-negative matrix V (R x K) with V[r,k] <= bound(r) is held as
- * NS uint8 planes, plane s at `planes + s*plane_stride`, row-major with leading dimension
- * ldp (multiple of 16), such that  V[r,k] ~= q[r,k] * bound(r) / 256^NS,
- * q = sum_s plane_s[r,k] * 256^(NS-1-s).  The per-row bound is the affine form
- * bound(r) = vec[r]*mul + add (vec == NULL: bound(r) = add), so that the caller can derive it
- * from a constant per-node vector (degree, row sum of G) and per-iteration scalars.          */
-typedef struct srk_rowbound {
-  const double* vec;
-  double mul, add;
-} srk_rowbound;
-
+/* ----------------------------------------------------------------------------- tensor-core path */
 /* Quantise rows [0,R) of a f64 matrix into planes (round to nearest, clip to 256^NS-1).
  * zero_diag_offset >= 0 forces element (r, r + zero_diag_offset) to 0: the unit diagonal of S
  * is carried separately (S = I + S_off).                                                      */

@@ -24,6 +24,10 @@ METRICS = [
     "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
     "l1tex__m_l1tex2xbar_write_bytes.sum", "lts__t_sectors_srcunit_ltcfabric.sum",
     "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed.sum",
+    "lts__t_bytes.sum", "lts__t_bytes.sum.per_second", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+    "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum", "l1tex__t_bytes.sum.per_second",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "smsp__cycles_active.avg",
 ]
 
 

@@ -42,6 +42,23 @@ class RowBound(C.Structure):
         return rb
 
 
+SRK_ELEM_F64, SRK_ELEM_U16 = 0, 1
+SRK_CSR_FIRST, SRK_CSR_FINAL = 0, 1
+
+
+class CsrArgs(C.Structure):
+    _fields_ = [("elem", C.c_int), ("mode", C.c_int), ("symmetric", C.c_int),
+                ("indptr", C.c_void_p), ("indices", C.c_void_p), ("g", C.c_void_p),
+                ("M", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
+                ("X", C.c_void_p), ("ldx", C.c_int64), ("L", C.c_int64),
+                ("OUT", C.c_void_p), ("ldo", C.c_int64),
+                ("in_unit", RowBound), ("out_bound", RowBound),
+                ("g_col", C.c_void_p),
+                ("counts", C.c_void_p), ("ld_counts", C.c_int64),
+                ("counts_bits", C.c_int), ("add_counts", C.c_int), ("use_evidence", C.c_int),
+                ("epi", Epilogue)]
+
+
 class X2Args(C.Structure):
     _fields_ = [("mode", C.c_int), ("ns", C.c_int), ("layout", C.c_int),
                 ("M", C.c_int64), ("R", C.c_int64), ("K", C.c_int64),
@@ -70,6 +87,8 @@ SYMBOLS = {
     "srk_last_error": (C.c_char_p, []),
     "srk_device_cc": (_INT, []),
     "srk_csr_half_f64": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, C.POINTER(Epilogue), _P]),
+    "srk_csr_half": (_INT, [C.POINTER(CsrArgs), _P]),
+    "srk_quantize_rows_u16": (_INT, [_P, _I64, _I64, _I64, _I64, _P, _I64, _P, _P]),
     "srk_csr_evidence_counts": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P]),
     "srk_csr_row_spread": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "srk_csr_to_dense_u8": (_INT, [_P, _P, _I64, _I64, _I64, _P, _I64, _P]),

@@ -9,7 +9,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libsimrank_b200.so")
-SOURCES = [os.path.join(PKG, "csrc", f) for f in ("csr_kernels.cu", "dense_i8x2.cu")]
+SOURCES = [os.path.join(PKG, "csrc", f) for f in ("csr_kernels.cu", "csr_gather.cu", "dense_i8x2.cu")]
 HEADERS = [os.path.join(PKG, "csrc", "common.cuh"), os.path.join(ROOT, "include", "simrank_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]

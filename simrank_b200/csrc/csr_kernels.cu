@@ -1,9 +1,6 @@
-// CSR (float64) half-products and the small preprocessing / retrieval kernels.
-//
-// The CSR half-product is the exact-arithmetic path of the engine and the one used when the
-// graph is too sparse/large for a dense operand (BASELINE cfg5).  It is bound by HBM for the
-// streamed operands (S read once per column panel, result written once) and by L2 for the row
-// gather; see DESIGN.md "K3".
+// The small preprocessing / retrieval kernels around the half-products (evidence counts, row
+// spread, CSR -> dense pattern, fixed-point slicing, top-k).  The CSR half-products themselves are
+// in csr_gather.cu, the tensor-core ones in dense_i8x2.cu.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -13,119 +10,6 @@ namespace srk {
 char* error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
-}
-
-// ------------------------------------------------------------------------------------------
-// OUT[c, i] = g[i] * sum_{m in N(i)} X[m, c]           (then the optional fused epilogue)
-//
-// CTA tile: TI output columns (graph rows i) x TC output rows (columns c of X).
-//   phase 1  each warp owns graph rows i0+w, i0+w+8, ...; it walks the neighbour list (indices
-//            fetched 32 at a time, broadcast with shuffles) and gathers X[m, c0 + lane + 32q],
-//            q<4: every load instruction is one fully used 256 B segment of a row of X.  All
-//            CTAs of a grid column share the same column panel of X (TC*8 B per row), which is
-//            what keeps the gather in L2.
-//   phase 2  the TI x TC tile is transposed through shared memory and written as 256 B rows of
-//            OUT, where the SimRank epilogue (C, evidence, prior, diagonal, max|dS|) is fused.
-constexpr int TI = 32;
-constexpr int CSR_THREADS = 256;
-
-// TC = columns of X per CTA = width of the panel all CTAs of a grid column gather from: the panel
-// (rows of X x TC x 8 B, held once per L2 die) has to survive next to the result streams.
-template <bool kFinal, int TC>
-__global__ void __launch_bounds__(CSR_THREADS)
-csr_half_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                const double* __restrict__ g, int64_t row_begin, int64_t row_end,
-                const double* __restrict__ X, int64_t ldx, int64_t L,
-                double* __restrict__ OUT, int64_t ldo, EpilogueDev epi,
-                double* maxdiff, double* maxoff) {
-  __shared__ double tile[TC][TI + 1];
-  __shared__ double red[2][CSR_THREADS / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t i0 = row_begin + (int64_t)blockIdx.x * TI;
-  const int64_t c0 = (int64_t)blockIdx.y * TC;
-
-  for (int il = warp; il < TI; il += CSR_THREADS / 32) {
-    const int64_t i = i0 + il;
-    constexpr int TQ = TC / 32;
-    double acc[TQ];
-#pragma unroll
-    for (int q = 0; q < TQ; ++q) acc[q] = 0.0;
-    if (i < row_end) {
-      const int64_t beg = indptr[i], end = indptr[i + 1];
-      for (int64_t e = beg; e < end; e += 32) {
-        const int cnt = (int)min((int64_t)32, end - e);
-        const int my = (lane < cnt) ? indices[e + lane] : 0;
-        int t = 0;
-        for (; t + 4 <= cnt; t += 4) {          // 4 neighbours in flight, summed in list order
-          double v[4][TQ];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const double* row = X + (int64_t)__shfl_sync(0xffffffffu, my, t + u) * ldx + c0;
-#pragma unroll
-            for (int q = 0; q < TQ; ++q) {
-              const int64_t c = lane + 32 * q;
-              v[u][q] = (c0 + c < L) ? __ldg(row + c) : 0.0;
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int q = 0; q < TQ; ++q) acc[q] += v[u][q];
-        }
-        for (; t < cnt; ++t) {
-          const double* row = X + (int64_t)__shfl_sync(0xffffffffu, my, t) * ldx + c0;
-#pragma unroll
-          for (int q = 0; q < TQ; ++q) {
-            const int64_t c = lane + 32 * q;
-            acc[q] += (c0 + c < L) ? __ldg(row + c) : 0.0;
-          }
-        }
-      }
-      const double gi = g[i];
-#pragma unroll
-      for (int q = 0; q < TQ; ++q) acc[q] *= gi;
-    }
-#pragma unroll
-    for (int q = 0; q < TQ; ++q) tile[lane + 32 * q][il] = acc[q];
-  }
-  __syncthreads();
-
-  double dmax = 0.0, omax = 0.0;
-  const int64_t i = i0 + lane;
-  for (int cl = warp; cl < TC; cl += CSR_THREADS / 32) {
-    const int64_t r = c0 + cl;
-    if (r >= L || i >= row_end) continue;
-    double v = tile[cl][lane];
-    if (kFinal) {
-      v *= epi.coef;
-      // the epilogue streams (evidence, prior, S_old, the result) are touched once: evict-first
-      // loads/stores keep them from pushing the gathered panel of X out of L2
-      if (epi.evidence) v *= evidence_factor(__ldcs(epi.evidence + r * epi.ld_evidence + i));
-      if (epi.prior) v = (1.0 - epi.lambda) * v + epi.lambda * __ldcs(epi.prior + r * epi.ld_prior + i);
-      if (r + epi.diag_offset == i) v = 1.0; else if (v > omax) omax = v;
-      if (epi.s_old) {
-        const double d = fabs(v - __ldcs(epi.s_old + r * epi.ld_s_old + i));
-        if (d > dmax) dmax = d;                  // NaN compares false: ignored like SimRank.py:74
-      }
-    }
-    __stcs(OUT + r * ldo + i, v);
-  }
-  if (kFinal) {
-    dmax = warp_max(dmax);
-    omax = warp_max(omax);
-    if (lane == 0) { red[0][warp] = dmax; red[1][warp] = omax; }
-    __syncthreads();
-    if (warp == 0) {
-      dmax = (lane < CSR_THREADS / 32) ? red[0][lane] : 0.0;
-      omax = (lane < CSR_THREADS / 32) ? red[1][lane] : 0.0;
-      dmax = warp_max(dmax);
-      omax = warp_max(omax);
-      if (lane == 0) {
-        if (maxdiff && dmax > 0.0) atomic_max_nonneg(maxdiff, dmax);
-        if (maxoff && omax > 0.0) atomic_max_nonneg(maxoff, omax);
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -427,38 +311,6 @@ extern "C" int srk_device_cc(void) {
   SRK_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   SRK_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
   return major * 10 + minor;
-}
-
-extern "C" int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double* g,
-                                int64_t M, int64_t row_begin, int64_t row_end, const double* X,
-                                int64_t ldx, int64_t L, double* OUT, int64_t ldo,
-                                const srk_epilogue* final_epi, void* stream) {
-  SRK_REQUIRE(indptr && indices && g && X && OUT, "null pointer");
-  SRK_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= M, "row range");
-  // OUT is addressed as OUT[c * ldo + i] for i in [row_begin, row_end) only: a caller that stores just
-  // those columns passes the address of (virtual) column 0, i.e. its buffer minus row_begin elements
-  SRK_REQUIRE(L >= 0 && ldx >= L && ldo >= row_end - row_begin, "leading dimensions");
-  if (row_end == row_begin || L == 0) return SRK_OK;
-  // Panel width.  The first half only streams its result next to the gathered panel of X: 128
-  // columns (rows of X x 1 KB, held once per L2 die).  The second half also streams S_old; with 128
-  // columns its panel fell out of L2 and the gather came from DRAM (93 ms against 35 ms for the same
-  // gather volume at n = 32768), with 64 columns it stays (42 ms).  SRK_CSR_TC=64|128 forces one
-  // width for A/B profiling.
-  int tc = final_epi ? 64 : 128;
-  if (const char* e = getenv("SRK_CSR_TC")) tc = atoi(e) == 128 ? 128 : 64;
-  const int64_t gx = (row_end - row_begin + TI - 1) / TI, gy = (L + tc - 1) / tc;
-  SRK_REQUIRE(gy <= 65535, "too many column panels");
-  dim3 grid((unsigned)gx, (unsigned)gy);
-  cudaStream_t st = (cudaStream_t)stream;
-  EpilogueDev ed = {};
-  double *md = nullptr, *mo = nullptr;
-  if (final_epi) { ed = to_dev(*final_epi); md = final_epi->maxdiff; mo = final_epi->maxoff; }
-#define SRK_CSR_LAUNCH(F, T) csr_half_kernel<F, T><<<grid, CSR_THREADS, 0, st>>>(indptr, indices, g, row_begin, row_end, X, ldx, L, OUT, ldo, ed, md, mo)
-  if (final_epi) { if (tc == 128) SRK_CSR_LAUNCH(true, 128); else SRK_CSR_LAUNCH(true, 64); }
-  else { if (tc == 128) SRK_CSR_LAUNCH(false, 128); else SRK_CSR_LAUNCH(false, 64); }
-#undef SRK_CSR_LAUNCH
-  SRK_CUDA_OK(cudaGetLastError());
-  return SRK_OK;
 }
 
 extern "C" int srk_csr_evidence_counts(const int64_t* indptr, const int32_t* indices,

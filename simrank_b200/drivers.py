@@ -138,7 +138,7 @@ def _evidence_args(evidence, op: HostOperator, mode: str):
     """(uint8 counts tensor or None, take-it-from-the-pattern flag) for one update."""
     if evidence is None:
         return None, False
-    if mode == "i8" and evidence.is_pattern_of(op):
+    if mode in ("i8", "csr16") and evidence.is_pattern_of(op):
         return None, True
     return evidence.counts, False
 

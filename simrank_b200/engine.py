@@ -12,6 +12,11 @@ plus the reduction behind ``_converged`` (SimRank.py:74) is two kernel launches 
 
   csr mode   T = (G S)^T                     srk_csr_half_f64   (gather, transposed store)
              S = epilogue((G T)^T)           srk_csr_half_f64   (fused epilogue, in place)
+  csr16 mode Xq = uint16(S_off), column units srk_quantize_rows_u16  (S = I + S_off)
+             Tq = uint16((A S_off)^T)        srk_csr_half FIRST  (integer gather, re-quantised)
+             S = epilogue(g g^T o (A Tq + A A^T))
+                                             srk_csr_half FINAL  (integer gather, fused epilogue, in
+                                                                 place; pairs r >= i only, mirrored)
   i8 mode    planes(S_off), exact row bounds srk_slice_rows_max_f64   (S = I + S_off)
              U = A S_off (re-quantised)      srk_x2_half MID    (tcgen05 cta_group::2 kind::i8)
              S = epilogue(g g^T o (A U^T + A A^T))
@@ -207,9 +212,14 @@ def choose_mode(op: HostOperator, requested: str | None = None, coef: float = 0.
     if mode == "csr":
         return mode
     obstacle = fixed_point_obstacle(op, coef, lbd, has_prior)
-    if mode == "i8":
+    if mode == "csr16" and not obstacle:
+        if has_prior:
+            obstacle = "does not take a prior (the symmetric second half mirrors every value)"
+        elif op.deg.size and int(op.deg.max()) >= 65536:
+            obstacle = "needs row degrees below 65536 (exact 32-bit sums of uint16 values)"
+    if mode in ("i8", "csr16"):
         if obstacle:
-            raise ValueError(f"mode='i8' {obstacle}; use mode='csr' (float64)")
+            raise ValueError(f"mode={mode!r} {obstacle}; use mode='csr' (float64)")
         return mode
     if mode != "auto":
         raise ValueError(f"unknown mode {mode!r}")
@@ -281,6 +291,19 @@ class _Half:
             self.T = torch.empty((self.n_in, self.ldt), dtype=torch.float64, device=dev)
             return
         host = op.host
+        if mode == "csr16":
+            # uint16 matrices are held as int16 tensors (only the bytes matter)
+            self.rho = op.g_host * host.deg
+            self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
+            self.ldxt = _round_up(max(self.n_out, 1), 64)                  # Xq of the own S (as a source)
+            self.Xq, self.unit = None, torch.zeros(max(self.n_out, 1), dtype=torch.float64, device=dev)
+            self.ldt = _round_up(max(self.n_out, 1), 64)
+            self.Tq = torch.empty((self.n_in, self.ldt), dtype=torch.int16, device=dev)
+            self.deg_dev = torch.from_numpy(host.deg.astype(np.float64)).to(dev)
+            self.evidence_from_pattern = bool(evidence_from_pattern)
+            self.counts = op.pattern_counts()
+            self.version, self._quantized_version = 0, -1
+            return
         self.rho = op.g_host * host.deg                                    # row sums of G
         self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
         self.prior_max = float(prior.max()) if prior is not None else 0.0
@@ -350,11 +373,20 @@ class _Half:
             _lib.check(self._timed("csr_half_first", lambda: lib.srk_csr_half_f64(
                 _ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M, _ptr(src.S), src.ld, self.n_in,
                 _ptr(self.T), self.ldt, None, _stream())), "srk_csr_half_f64(first)")
-            epi = self._epilogue()
-            _lib.check(self._timed("csr_half_final", lambda: lib.srk_csr_half_f64(
-                _ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M, _ptr(self.T), self.ldt, self.n_out,
-                _ptr(self.S), self.ld, C.byref(epi), _stream())), "srk_csr_half_f64(second)")
+            b = _lib.CsrArgs()
+            b.elem, b.mode = _lib.SRK_ELEM_F64, _lib.SRK_CSR_FINAL
+            # without a prior the result is symmetric: each unordered pair is computed once and mirrored
+            b.symmetric = 1 if self.prior is None and os.environ.get("SIMRANK_B200_CSR_SYMMETRIC", "1") != "0" else 0
+            b.indptr, b.indices, b.g = op.indptr.data_ptr(), op.indices.data_ptr(), op.g.data_ptr()
+            b.M, b.row_begin, b.row_end = op.M, 0, op.M
+            b.X, b.ldx, b.L = self.T.data_ptr(), self.ldt, self.n_out
+            b.OUT, b.ldo = self.S.data_ptr(), self.ld
+            b.epi = self._epilogue()
+            _lib.check(self._timed("csr_half_final", lambda: lib.srk_csr_half(C.byref(b), _stream())),
+                       "srk_csr_half(f64, second)")
             return
+        if self.mode == "csr16":
+            return self._update_csr16(src)
         # ---- paired-SM tensor-core path
         blend = (1.0 - self.lbd) if self.prior is not None else 1.0
         ns = choose_slices(self.ns, self.coef, blend, self.rho_max, src.maxoff)
@@ -401,6 +433,54 @@ class _Half:
         attach_sync_ws(b, self.S.device)
         _lib.check(self._timed("x2_half_final", lambda: lib.srk_x2_half(C.byref(b), _stream())),
                    "srk_x2_half(FINAL)")
+        self.version += 1
+
+    def _quantized(self):
+        """uint16 source operand of the CURRENT S for the fixed-point gather (cached per version of S):
+        Xq[k, r] = rint(S_off[r, k] / unit[r]), unit[r] = row maximum / 65535."""
+        if self.Xq is None:
+            self.Xq = torch.empty((self.n_out, self.ldxt), dtype=torch.int16, device=self.S.device)
+        if self._quantized_version != self.version:
+            lib = _lib.load()
+            _lib.check(self._timed("quantize_rows_u16", lambda: lib.srk_quantize_rows_u16(
+                _ptr(self.S), self.ld, self.n_out, self.n_out, 0, _ptr(self.Xq), self.ldxt, _ptr(self.unit),
+                _stream())), "srk_quantize_rows_u16")
+            self._quantized_version = self.version
+        return self.Xq, self.unit
+
+    def _update_csr16(self, src: "_Half") -> None:
+        """Fixed-point CSR path: the two gathers sum uint16 values as exact integers."""
+        lib, op = _lib.load(), self.op
+        # same two roundings as the tensor-core path with 2 planes (bounds: exact row maximum of S_off,
+        # deg * max(S_off) for U -- not even rounded up to a power of two here)
+        self.slices_used.append(2)
+        self._err_next = self.coef * self.rho_max ** 2 * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff)
+        xq, unit = src._quantized()
+        guard = 1.0 + 2.0 ** -14
+        a = _lib.CsrArgs()
+        a.elem, a.mode = _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST
+        a.indptr, a.indices, a.g = op.indptr.data_ptr(), op.indices.data_ptr(), op.g.data_ptr()
+        a.M, a.row_begin, a.row_end = op.M, 0, op.M
+        a.X, a.ldx, a.L = xq.data_ptr(), src.ldxt, self.n_in
+        a.OUT, a.ldo = self.Tq.data_ptr(), self.ldt
+        a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
+        a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard, 0.0)
+        _lib.check(self._timed("csr16_half_first", lambda: lib.srk_csr_half(C.byref(a), _stream())),
+                   "srk_csr_half(u16, first)")
+        b = _lib.CsrArgs()
+        b.elem, b.mode, b.symmetric = _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL, 1
+        b.indptr, b.indices, b.g = a.indptr, a.indices, a.g
+        b.M, b.row_begin, b.row_end = op.M, 0, op.M
+        b.X, b.ldx, b.L = self.Tq.data_ptr(), self.ldt, self.n_out
+        b.OUT, b.ldo = self.S.data_ptr(), self.ld
+        b.in_unit = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard / 65535.0, 0.0)
+        b.g_col = op.g.data_ptr()
+        b.counts, b.ld_counts = self.counts.data_ptr(), self.counts.stride(0)
+        b.counts_bits, b.add_counts = 8 * self.counts.element_size(), 1
+        b.use_evidence = 1 if self.evidence_from_pattern else 0
+        b.epi = self._epilogue()
+        _lib.check(self._timed("csr16_half_final", lambda: lib.srk_csr_half(C.byref(b), _stream())),
+                   "srk_csr_half(u16, second)")
         self.version += 1
 
     def finish(self) -> float:

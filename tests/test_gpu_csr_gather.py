@@ -1,0 +1,248 @@
+"""Kernel-level tests of the CSR half-products with the shared-memory gather ring
+(srk_csr_half: float64 and uint16 fixed point) and of srk_quantize_rows_u16, through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from simrank_b200 import _lib, engine, graph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return engine.require_cuda()
+
+
+def _rand_graph(rng, M, K, density, empty_rows=0):
+    mask = rng.random((M, K)) < density
+    if empty_rows:
+        mask[rng.choice(M, size=empty_rows, replace=False)] = False
+    return graph.operator_from_edges(*np.nonzero(mask), M, K, rng.random(M) * 0.2 + 0.01), mask.astype(np.int64)
+
+
+def _u16(t):                      # torch has no uint16 arithmetic: int16 tensors carry the bytes
+    return torch.from_numpy(t.astype(np.uint16).view(np.int16))
+
+
+def _args(dop, elem, mode):
+    a = _lib.CsrArgs()
+    a.elem, a.mode = elem, mode
+    a.indptr, a.indices, a.g = dop.indptr.data_ptr(), dop.indices.data_ptr(), dop.g.data_ptr()
+    a.M, a.row_begin, a.row_end = dop.M, 0, dop.M
+    return a
+
+
+@pytest.mark.parametrize("R,K,diag", [(5, 7, -1), (64, 64, 0), (200, 333, 17), (130, 65, -1)])
+def test_quantize_rows_u16(dev, R, K, diag):
+    rng = np.random.default_rng(R + K)
+    V = rng.random((R, K)) * rng.random((R, 1))
+    V[R // 2] = 0.0                                        # an all-zero row: unit 0, zeros out
+    V[0, :2] = [-1.0, np.nan]
+    ldxt = engine._round_up(R, 64)
+    Vd = torch.from_numpy(V).to(dev)
+    xt = torch.full((K, ldxt), -1, dtype=torch.int16, device=dev)
+    unit = torch.zeros(R, dtype=torch.float64, device=dev)
+    _lib.check(_lib.load().srk_quantize_rows_u16(engine._ptr(Vd), K, R, K, diag, engine._ptr(xt), ldxt,
+                                                 engine._ptr(unit), engine._stream()))
+    torch.cuda.synchronize()
+    W = np.where(np.isnan(V) | (V < 0), 0.0, V)
+    if diag >= 0:
+        idx = np.arange(R)
+        ok = idx + diag < K
+        W[idx[ok], idx[ok] + diag] = 0.0
+    u = W.max(axis=1) / 65535.0
+    np.testing.assert_array_equal(unit.cpu().numpy(), u)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = np.where(u[:, None] > 0, np.rint(W / u[:, None]), 0.0)
+    got = xt.cpu().numpy().view(np.uint16)
+    np.testing.assert_array_equal(got[:, :R], q.T.astype(np.uint16))
+    assert not got[:, R:].any()
+
+
+@pytest.mark.parametrize("M,K,L,density", [(37, 53, 29, 0.3), (300, 257, 260, 0.05), (129, 130, 515, 0.5),
+                                           (64, 2000, 128, 0.02), (1, 1, 1, 1.0)])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_csr16_first_half(dev, M, K, L, density, aligned):
+    """uint16 gather, exact integer sums, re-quantised transposed store -- bulk-copy ring (aligned
+    operand) and plain-load fallback (odd leading dimension)."""
+    rng = np.random.default_rng(M * 7 + L)
+    op, A = _rand_graph(rng, M, K, density, empty_rows=min(2, M - 1))
+    dop = engine.DeviceOperator(op, dev)
+    ldx = engine._round_up(L, 8) if aligned else engine._round_up(L, 8) + 3
+    Xq = rng.integers(0, 65536, (K, L), dtype=np.int64)
+    Xq[:, 0] = 65535                                       # a column at the top of the range
+    xp = np.zeros((K, ldx), dtype=np.int64)
+    xp[:, :L] = Xq
+    X = _u16(xp).to(dev)
+    unit = rng.random(L) * 1e-6
+    ob = rng.random(M) * 0.05 + 1e-4
+    ob[M // 3] = 0.0                                       # bound 0: the column is stored as zeros
+    ud, od = torch.from_numpy(unit).to(dev), torch.from_numpy(ob).to(dev)
+    ldo = engine._round_up(M, 8)
+    out = torch.full((L, ldo), -1, dtype=torch.int16, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST)
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), ldx, L, out.data_ptr(), ldo
+    a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+    a.out_bound = _lib.RowBound.of(od.data_ptr(), 2.0, 0.0)
+    _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+    torch.cuda.synchronize()
+    D = A @ Xq                                             # [M, L] exact
+    with np.errstate(divide="ignore"):
+        inv = np.where(ob > 0, 65535.0 / (2.0 * ob), 0.0)
+    want = np.clip(np.rint(D.astype(np.float64) * unit[None, :] * inv[:, None]), 0, 65535).T
+    got = out.cpu().numpy().view(np.uint16)[:, :M].astype(np.int64)
+    np.testing.assert_array_equal(got, want.astype(np.int64))
+
+
+def _final_case(rng, dev, n, density, evidence_from_counts):
+    op, A = _rand_graph(rng, n, n, density, empty_rows=3)
+    dop = engine.DeviceOperator(op, dev)
+    Tq = rng.integers(0, 65536, (n, n), dtype=np.int64)
+    ldt = engine._round_up(n, 64)
+    tp = np.zeros((n, ldt), dtype=np.int64)
+    tp[:, :n] = Tq
+    cnt = rng.integers(0, 40, (n, n))
+    cnt = np.triu(cnt) + np.triu(cnt, 1).T                 # counts / S_old are symmetric in the product
+    S_old = rng.random((n, n))
+    S_old = np.triu(S_old) + np.triu(S_old, 1).T
+    unit = rng.random(n) * 1e-5
+    gcol = rng.random(n) * 0.3
+    D2 = A @ Tq                                            # [i, r]
+    x = op.g[:, None] * gcol[None, :] * (D2 * unit[None, :] + cnt) * 0.8          # [i, r]
+    if evidence_from_counts:
+        x = x * (1 - 0.5 ** cnt.astype(np.float64))
+    return op, dop, tp, ldt, cnt, S_old, unit, gcol, x
+
+
+@pytest.mark.parametrize("n,density", [(70, 0.3), (300, 0.05), (515, 0.1)])
+@pytest.mark.parametrize("evidence", [False, True])
+def test_csr16_final_transposed(dev, n, density, evidence):
+    rng = np.random.default_rng(n)
+    op, dop, tp, ldt, cnt, S_old, unit, gcol, x = _final_case(rng, dev, n, density, evidence)
+    r0, L = 16, n - 23                                     # a row block of the output: panel T[:, r0 : r0 + L)
+    ld = engine._round_up(n, 16)
+    ldx = engine._round_up(L, 8)
+    xp = np.zeros((n, ldx), dtype=np.int64)
+    xp[:, :L] = tp[:, r0:r0 + L]
+    X = _u16(xp).to(dev)
+    out = torch.zeros((L, ld), dtype=torch.float64, device=dev)
+    out[:, :n] = torch.from_numpy(S_old[r0:r0 + L])
+    c16 = torch.from_numpy(np.ascontiguousarray(cnt[r0:r0 + L]).astype(np.uint16).view(np.int16)).to(dev)
+    ud, gd = torch.from_numpy(unit[r0:r0 + L].copy()).to(dev), torch.from_numpy(gcol[r0:r0 + L].copy()).to(dev)
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), ldx, L, out.data_ptr(), ld
+    a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+    a.g_col = gd.data_ptr()
+    a.counts, a.ld_counts, a.counts_bits, a.add_counts, a.use_evidence = c16.data_ptr(), n, 16, 1, int(evidence)
+    a.epi.coef = 0.8
+    a.epi.s_old, a.epi.ld_s_old = out.data_ptr(), ld
+    a.epi.maxdiff, a.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
+    a.epi.diag_offset = r0
+    _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+    torch.cuda.synchronize()
+    want = x.T[r0:r0 + L].copy()                           # [r, i]
+    want[np.arange(L), r0 + np.arange(L)] = 1.0
+    got = out[:, :n].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-300)
+    md, mo = scal.tolist()
+    assert md == np.abs(got - S_old[r0:r0 + L]).max()
+    off = got.copy()
+    off[np.arange(L), r0 + np.arange(L)] = 0.0
+    assert mo == off.max()
+
+
+@pytest.mark.parametrize("n,density", [(70, 0.3), (300, 0.05), (515, 0.1), (1100, 0.02)])
+@pytest.mark.parametrize("evidence", [False, True])
+def test_csr16_final_symmetric(dev, n, density, evidence):
+    """Pairs r >= i are computed once (from row i of the graph) and mirrored: the result is the
+    upper triangle of the full product, reflected."""
+    rng = np.random.default_rng(n + 1)
+    op, dop, tp, ldt, cnt, S_old, unit, gcol, x = _final_case(rng, dev, n, density, evidence)
+    ld = engine._round_up(n, 16)
+    X = _u16(tp).to(dev)
+    out = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+    out[:, :n] = torch.from_numpy(S_old)
+    c16 = torch.from_numpy(cnt.astype(np.uint16).view(np.int16)).to(dev)
+    ud, gd = torch.from_numpy(unit).to(dev), torch.from_numpy(gcol).to(dev)
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
+    a.symmetric = 1
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), ldt, n, out.data_ptr(), ld
+    a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+    a.g_col = gd.data_ptr()
+    a.counts, a.ld_counts, a.counts_bits, a.add_counts, a.use_evidence = c16.data_ptr(), n, 16, 1, int(evidence)
+    a.epi.coef = 0.8
+    a.epi.s_old, a.epi.ld_s_old = out.data_ptr(), ld
+    a.epi.maxdiff, a.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
+    _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+    torch.cuda.synchronize()
+    want = np.triu(x, 1)                                   # x[i, r] for r > i
+    want = want + want.T
+    np.fill_diagonal(want, 1.0)
+    got = out[:, :n].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-300)
+    assert np.array_equal(got, got.T)
+    md, mo = scal.tolist()
+    assert md == np.abs(got - S_old).max()
+    off = got.copy()
+    np.fill_diagonal(off, 0.0)
+    assert mo == off.max()
+
+
+@pytest.mark.parametrize("n,density", [(203, 0.1), (700, 0.03)])
+def test_csr_f64_final_symmetric_matches_the_full_product(dev, n, density):
+    rng = np.random.default_rng(n + 2)
+    op, A = _rand_graph(rng, n, n, density, empty_rows=4)
+    dop = engine.DeviceOperator(op, dev)
+    G = op.to_dense()
+    S0 = rng.random((n, n))
+    S0 = (S0 + S0.T) / 2
+    T = (G @ S0).T                                         # exact first half of a symmetric S
+    ld = engine._round_up(n, 16)
+    Td = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+    Td[:, :n] = torch.from_numpy(T)
+    out = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+    out[:, :n] = torch.from_numpy(S0)
+    ev = rng.integers(0, 60, (n, n))
+    ev = (np.triu(ev) + np.triu(ev, 1).T).astype(np.uint8)
+    evd = torch.zeros((n, ld), dtype=torch.uint8, device=dev)
+    evd[:, :n] = torch.from_numpy(ev)
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_F64, _lib.SRK_CSR_FINAL)
+    a.symmetric = 1
+    a.X, a.ldx, a.L, a.OUT, a.ldo = Td.data_ptr(), ld, n, out.data_ptr(), ld
+    a.epi.coef = 0.6
+    a.epi.evidence, a.epi.ld_evidence = evd.data_ptr(), ld
+    a.epi.s_old, a.epi.ld_s_old = out.data_ptr(), ld
+    a.epi.maxdiff, a.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
+    _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+    torch.cuda.synchronize()
+    want = (1 - 0.5 ** ev.astype(np.float64)) * 0.6 * (G @ S0 @ G.T)
+    np.fill_diagonal(want, 1.0)
+    got = out[:, :n].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+    assert np.array_equal(got, got.T)
+    md, mo = scal.tolist()
+    assert md == np.abs(got - S0).max()
+
+
+def test_csr_half_rejects_bad_arguments(dev):
+    rng = np.random.default_rng(0)
+    op, _ = _rand_graph(rng, 20, 20, 0.3)
+    dop = engine.DeviceOperator(op, dev)
+    lib = _lib.load()
+    X = torch.zeros((20, 24), dtype=torch.float64, device=dev)
+    a = _args(dop, 7, _lib.SRK_CSR_FIRST)
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), 24, 20, X.data_ptr(), 24
+    assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"elem" in lib.srk_last_error()
+    a = _args(dop, _lib.SRK_ELEM_F64, _lib.SRK_CSR_FINAL)
+    a.symmetric, a.row_end = 1, 10
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), 24, 20, X.data_ptr(), 24
+    assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"symmetric" in lib.srk_last_error()
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), 24, 20, X.data_ptr(), 24
+    assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"g_col" in lib.srk_last_error()

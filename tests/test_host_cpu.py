@@ -36,7 +36,8 @@ def test_struct_layouts_match_c_compiler(tmp_path):
     """sizeof/offsetof of every ABI struct as gcc sees the header == the ctypes mirror."""
     import ctypes as C
     import subprocess
-    structs = {"srk_epilogue": _lib.Epilogue, "srk_rowbound": _lib.RowBound, "srk_x2_args": _lib.X2Args}
+    structs = {"srk_epilogue": _lib.Epilogue, "srk_rowbound": _lib.RowBound, "srk_x2_args": _lib.X2Args,
+               "srk_csr_args": _lib.CsrArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "simrank_b200.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
