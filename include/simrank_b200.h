@@ -118,8 +118,8 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
  *                       (r, i); counts / s_old / evidence are read at (i, r) (they are symmetric).
  * elem = SRK_ELEM_F64 is srk_csr_half_f64 (in_unit, out_bound, g_col, counts ignored), plus the
  * symmetric second half.
- * Bulk asynchronous copies need 16-byte aligned rows of X (X % 16 == 0, ldx * sizeof(elem) % 16 ==
- * 0); other operands are gathered with plain loads (slower, same results).                      */
+ * The TMA gather needs 16-byte aligned rows of X (X % 16 == 0, ldx * sizeof(elem) % 16 == 0); other
+ * operands are gathered with plain loads (slower, same results).                                 */
 #define SRK_ELEM_F64 0
 #define SRK_ELEM_U16 1
 #define SRK_CSR_FIRST 0
@@ -129,6 +129,7 @@ typedef struct srk_csr_args {
   const int64_t* indptr; const int32_t* indices; const double* g;
   int64_t M, row_begin, row_end;
   const void* X; int64_t ldx; int64_t L;
+  int64_t K;                                              /* rows of X (= columns of the graph operator); 0 = not given */
   void* OUT; int64_t ldo;
   srk_rowbound in_unit;                                   /* U16: unit of column c of X */
   srk_rowbound out_bound;                                 /* U16 FIRST: bound of output column i */

@@ -271,9 +271,10 @@ def fit_directed(data, kind="simrank", C=0.8, weighted=False, from_node_column="
 
 
 def fit_bipartite(data, kind="simrank", C1=0.8, C2=0.8, weighted=False, node_group1_column="user",
-                  node_group2_column="item", weight_column="weight", iterations=100, eps=1e-4):
-    """``BipartiteSimRank().fit`` / ``BipartiteSimRankPP().fit`` end to end
-    (SR.py:227-303, 393-425).  Returns (labels1, labels2, S1, S2, applied, converged)."""
+                  node_group2_column="item", weight_column="weight", iterations=100, eps=1e-4,
+                  prior1=None, prior2=None, lbd1=0.5, lbd2=0.5):
+    """``BipartiteSimRank().fit`` / ``BipartiteSimRankPP().fit`` / ``BipartitleAprioriSimRank().fit``
+    end to end (SR.py:227-303, 393-425, 461-493).  Returns (labels1, labels2, S1, S2, applied, converged)."""
     l1, l2, G12, G21 = bipartite_graph(data, weighted, node_group1_column, node_group2_column,
                                        weight_column)
     if kind == "simrank":
@@ -281,6 +282,9 @@ def fit_bipartite(data, kind="simrank", C1=0.8, C2=0.8, weighted=False, node_gro
     elif kind == "simrank_pp":
         S1, S2, k, c = bipartite_simrank_pp(weight(G12), weight(G21), evidence(G12), evidence(G21),
                                             C1, C2, iterations, eps)
+    elif kind == "apriori":
+        S1, S2, k, c = bipartite_apriori_simrank(weight(G12), weight(G21), evidence(G12), evidence(G21),
+                                                 prior1, prior2, C1, C2, lbd1, lbd2, iterations, eps)
     else:
         raise ValueError(kind)
     return l1, l2, S1, S2, k, c

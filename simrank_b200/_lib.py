@@ -50,7 +50,7 @@ class CsrArgs(C.Structure):
     _fields_ = [("elem", C.c_int), ("mode", C.c_int), ("symmetric", C.c_int),
                 ("indptr", C.c_void_p), ("indices", C.c_void_p), ("g", C.c_void_p),
                 ("M", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
-                ("X", C.c_void_p), ("ldx", C.c_int64), ("L", C.c_int64),
+                ("X", C.c_void_p), ("ldx", C.c_int64), ("L", C.c_int64), ("K", C.c_int64),
                 ("OUT", C.c_void_p), ("ldo", C.c_int64),
                 ("in_unit", RowBound), ("out_bound", RowBound),
                 ("g_col", C.c_void_p),

@@ -1,27 +1,30 @@
-// CSR half-products: the neighbour rows of X are gathered through shared memory by bulk
-// asynchronous copies (cp.async.bulk, the 1-D form of TMA) and summed by the warp that owns the
-// graph row.  Two arithmetic modes share the kernel:
+// CSR half-products: the neighbour rows of X are gathered into shared memory by TMA
+// (cp.async.bulk.tensor.2d.tile::gather4: FOUR rows of X per instruction, completion counted on an
+// mbarrier) and summed by the warp that owns the graph row.  Two arithmetic modes share the kernel:
 //
 //   f64  OUT[c, i] = g[i] * sum_{m in N(i)} X[m, c]                      exact float64 (DADD)
 //   u16  D[i, c]   = sum_{m in N(i)} Xq[m, c]    Xq uint16 fixed point with one scale per COLUMN of
 //        X, so the sum over m is an exact integer (deg < 65536 keeps it inside 32 bits); the scales
 //        are applied once per output element in the epilogue.  4x fewer gathered bytes.
 //
-// Why it looks like this (DESIGN.md "K3").  The streamed operands are O(n^2) bytes, the gather is
+// Why it looks like this (DESIGN.md "K3"; numbers from profiles/r2_ncu_full_csr_f64_baseline.json and
+// profiles/r2_micro_tma_gather_rate.txt).  The streamed operands are O(n^2) bytes, the gather is
 // nnz * n * sizeof(element): 550 GB per half-product at BASELINE cfg4 in float64, served by L2 (all
-// CTAs of a grid column share one column panel of X, which is what keeps it there).  Measured on
-// the previous kernel (ncu, profiles/r2_ncu_full_csr_f64_baseline.json): 549 GB over the
-// L2->SM crossbar in 35.4 ms = 15.5 TB/s, L1 hit rate 0 -- the half-product sits on the L2
-// bandwidth roof, not on HBM (27 GB of DRAM traffic).  So the bytes are cut (uint16 planes of the
-// same row-max-scaled fixed point the tensor-core path uses, symmetric second half) and the loads
-// are taken off the register file: every warp keeps kDepth row segments in flight in a private
-// shared-memory ring, one elected lane per segment issues the copy, completion is an mbarrier
-// transaction count, and the lanes read the landed segment with conflict-free ld.shared.
+// CTAs of a grid column share one column panel of X, which is what keeps it there).  The previous
+// kernel (4 __ldg row segments in flight per warp) moved 549 GB over the L2->SM crossbar in 35.4 ms
+// = 15.5 TB/s with an L1 hit rate of 0: the half-product sits on the L2 bandwidth roof (51 B/clk per
+// SM), not on HBM (27 GB of DRAM traffic).  So (1) the bytes are cut: uint16 planes of the same
+// row-max-scaled fixed point the tensor-core path uses, and a symmetric second half; (2) the gather
+// is taken off the register file and the LSU: a TMA instruction costs ~30-40 issue cycles per SM
+// whatever it moves (a 1-D bulk copy of 256 B .. 1 KB tops out at 9 .. 25 B/clk per SM), so rows are
+// fetched four at a time in 1 KB segments -- 4 KB per instruction, ~100 B/clk per SM, twice the L2
+// roof -- into a per-warp ring; the lanes read the landed rows with conflict-free 16-byte
+// ld.shared and add them up.
 //
-// CTA tile: TI = 32 graph rows x TC columns of X (TC * sizeof(element) = 512 B or 1 KB segments).
-// Warp w owns the 4 CONSECUTIVE graph rows i0 + 4w .. i0 + 4w + 3: their neighbour lists are one
-// contiguous range of `indices`, which the warp walks as a single stream -- the ring never drains
-// at a row boundary.
+// CTA tile: TI = 32 graph rows x TC columns of X.  The rows are dealt to the 8 warps in contiguous
+// runs of about equal EDGE count (a hub row gets a warp to itself), and a warp walks its rows'
+// neighbour lists four entries at a time; the TMA issue runs kDepth instructions ahead of the
+// consumption, across row boundaries.
 //
 // Epilogues
 //   FIRST            T = (G X)^T: per finished row the values go to a shared-memory tile, the CTA
@@ -30,10 +33,11 @@
 //   FINAL            the same transposed store with the fused SimRank epilogue (srk_epilogue).
 //   FINAL symmetric  square problems whose result is symmetric (no prior): only tiles that contain
 //                    an element c >= i are computed, the epilogue runs in the row-major orientation
-//                    straight from the accumulators (coalesced loads of S_old / counts, coalesced
-//                    store of row i) and every off-diagonal value is ALSO stored at (c, i): each
-//                    unordered pair is computed once, S stays bit-exactly symmetric, the second
-//                    half gathers 3/4 .. 1/2 of the bytes.
+//                    straight from the accumulators (vector loads of S_old / counts, vector store of
+//                    row i) and every off-diagonal value is ALSO stored at (c, i): each unordered pair
+//                    is computed once, S stays bit-exactly symmetric, the second half gathers
+//                    about half of the bytes.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -44,8 +48,7 @@ namespace gat {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int TI = 32;                      // graph rows per CTA
-constexpr int kRowsPerWarp = TI / kWarps;   // consecutive rows per warp
-constexpr int kDepth = 8;                   // row segments in flight per warp (power of two, <= 32)
+constexpr int kRowsPerOp = 4;               // rows of X per TMA instruction (tile::gather4)
 
 constexpr int MODE_FIRST = 0, MODE_FINAL = 1, MODE_FINAL_SYM = 2;
 
@@ -58,9 +61,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -79,11 +79,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// global -> this CTA's shared memory, `bytes` (multiple of 16) counted on `bar`
-__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+// rows r0..r3 of the 2-D tensor, box-width columns from column `col`, into 4 consecutive row
+// segments at dst; 4 * segment bytes are counted on `bar`
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, uint64_t* bar, uint64_t pol, int col,
+                                            int r0, int r1, int r2, int r3) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_last() {
@@ -96,6 +99,7 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
   asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct Params {
   const int64_t* indptr; const int32_t* indices; const double* g;
@@ -107,7 +111,8 @@ struct Params {
   const double* g_col;         // u16 FINAL: row factor of output row r (= column of X)
   const void* counts; int64_t ld_counts; int counts32, add_counts, use_evidence;
   EpilogueDev epi; double* maxdiff; double* maxoff;
-  int bulk;                    // rows of X are 16-byte aligned: bulk copies; else plain loads
+  int tma;                     // rows of X are 16-byte aligned: TMA gather; else plain loads
+  int vec_aligned;             // OUT, S_old and counts are 16-byte aligned (vector epilogue of the symmetric half)
   int flags;                   // SRK_CSR_FLAGS (A/B profiling): 1 = default L2 policy for the gather
 };
 
@@ -115,60 +120,70 @@ __device__ __forceinline__ uint32_t load_count(const void* base, int64_t idx, in
   return c32 ? reinterpret_cast<const uint32_t*>(base)[idx] : (uint32_t)reinterpret_cast<const uint16_t*>(base)[idx];
 }
 
-// Accumulators of one graph row: TC columns spread over the 32 lanes.
+// Accumulators of one graph row.  A row segment is kSeg bytes = G groups of 512 B; lane l reads the
+// 16 bytes at 16 l of every group (one conflict-free ld.shared.v4 per group), so it owns
+// kVec = 16 / sizeof(element) CONSECUTIVE columns per group: column(j) = (j / kVec) * (512 / size) +
+// kVec * l + j % kVec.
 template <typename E, int TC>
 struct Acc;
 
-// float64: lane holds columns lane + 32 k
 template <int TC>
 struct Acc<double, TC> {
-  static constexpr int kCols = TC / 32;
+  static constexpr int kGroups = TC * 8 / 512, kVec = 2, kCols = kGroups * kVec, kGroupCols = 64;
   double v[kCols];
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int k = 0; k < kCols; ++k) v[k] = 0.0;
   }
-  __device__ __forceinline__ static int col(int j, int lane) { return lane + 32 * j; }
   __device__ __forceinline__ void add_smem(const uint8_t* seg, int lane) {
-    const double* s = reinterpret_cast<const double*>(seg);
 #pragma unroll
-    for (int k = 0; k < kCols; ++k) v[k] += s[lane + 32 * k];
+    for (int gq = 0; gq < kGroups; ++gq) {
+      const double2 x = *reinterpret_cast<const double2*>(seg + gq * 512 + lane * 16);
+      v[2 * gq] += x.x;
+      v[2 * gq + 1] += x.y;
+    }
   }
   __device__ __forceinline__ void add_global(const void* row, int lane, int64_t valid) {
     const double* s = reinterpret_cast<const double*>(row);
 #pragma unroll
-    for (int k = 0; k < kCols; ++k) v[k] += (lane + 32 * k < valid) ? __ldg(s + lane + 32 * k) : 0.0;
+    for (int j = 0; j < kCols; ++j) {
+      const int c = (j / kVec) * kGroupCols + kVec * lane + j % kVec;
+      v[j] += c < valid ? __ldg(s + c) : 0.0;
+    }
   }
   __device__ __forceinline__ double val(int j) const { return v[j]; }
 };
 
-// uint16: lane holds the 32-bit words lane + 32 w, i.e. columns 2 (lane + 32 w) and + 1.  The low
-// halves are not masked out per element: aw accumulates the whole words modulo 2^32 and ah the high
-// halves, so sum(lo) = aw - (ah << 16) (mod 2^32), which is exact because sum(lo) < 2^32.
+// uint16: the low halves of the 32-bit words are not masked out per element: aw accumulates the
+// whole words modulo 2^32 and ah the high halves, so sum(lo) = aw - (ah << 16) (mod 2^32), which is
+// exact because sum(lo) < 2^32.
 template <int TC>
 struct Acc<uint16_t, TC> {
-  static constexpr int kWords = TC / 64;
-  static constexpr int kCols = 2 * kWords;
-  uint32_t aw[kWords], ah[kWords];
+  static constexpr int kGroups = TC * 2 / 512, kVec = 8, kCols = kGroups * kVec, kGroupCols = 256;
+  uint32_t aw[kCols / 2], ah[kCols / 2];
   __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int w = 0; w < kWords; ++w) aw[w] = ah[w] = 0u;
+    for (int w = 0; w < kCols / 2; ++w) aw[w] = ah[w] = 0u;
   }
-  __device__ __forceinline__ static int col(int j, int lane) { return 2 * (lane + 32 * (j >> 1)) + (j & 1); }
+  __device__ __forceinline__ void add_word(int w, uint32_t x) {
+    aw[w] += x;
+    ah[w] += x >> 16;
+  }
   __device__ __forceinline__ void add_smem(const uint8_t* seg, int lane) {
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(seg);
 #pragma unroll
-    for (int w = 0; w < kWords; ++w) {
-      const uint32_t x = s[lane + 32 * w];
-      aw[w] += x;
-      ah[w] += x >> 16;
+    for (int gq = 0; gq < kGroups; ++gq) {
+      const uint4 x = *reinterpret_cast<const uint4*>(seg + gq * 512 + lane * 16);
+      add_word(4 * gq, x.x);
+      add_word(4 * gq + 1, x.y);
+      add_word(4 * gq + 2, x.z);
+      add_word(4 * gq + 3, x.w);
     }
   }
   __device__ __forceinline__ void add_global(const void* row, int lane, int64_t valid) {
     const uint16_t* s = reinterpret_cast<const uint16_t*>(row);
 #pragma unroll
-    for (int w = 0; w < kWords; ++w) {
-      const int c = 2 * (lane + 32 * w);
+    for (int w = 0; w < kCols / 2; ++w) {
+      const int c = (w / 4) * kGroupCols + kVec * lane + 2 * (w % 4);
       const uint32_t lo = c < valid ? (uint32_t)__ldg(s + c) : 0u, hi = c + 1 < valid ? (uint32_t)__ldg(s + c + 1) : 0u;
       aw[w] += lo | (hi << 16);
       ah[w] += hi;
@@ -177,6 +192,11 @@ struct Acc<uint16_t, TC> {
   __device__ __forceinline__ uint32_t raw(int j) const { return (j & 1) ? ah[j >> 1] : aw[j >> 1] - (ah[j >> 1] << 16); }
   __device__ __forceinline__ double val(int j) const { return (double)raw(j); }
 };
+
+template <typename E, int TC>
+__device__ __forceinline__ int col_of(int j, int lane) {
+  return (j / Acc<E, TC>::kVec) * Acc<E, TC>::kGroupCols + Acc<E, TC>::kVec * lane + j % Acc<E, TC>::kVec;
+}
 
 template <typename E, int MODE>
 struct TileElem { typedef double type; };
@@ -188,87 +208,154 @@ struct TileElem<uint16_t, MODE_FINAL> { typedef uint32_t type; };
 template <typename E, int TC, int MODE>
 struct Smem {
   typedef typename TileElem<E, MODE>::type TileT;
-  static constexpr int kSeg = TC * (int)sizeof(E);
-  static constexpr int kRing = kWarps * kDepth * kSeg;
+  static constexpr int kSeg = TC * (int)sizeof(E);                   // bytes of one row segment (<= 1024)
+  static constexpr int kSlot = kRowsPerOp * kSeg;
+  // TMA instructions in flight per warp: as many as shared memory allows with two CTAs per SM
+  static constexpr int kDepth = kSlot >= 4096 ? (MODE == MODE_FINAL_SYM ? 3 : 2) : 4;
+  static constexpr int kRing = kWarps * kDepth * kSlot;
   static constexpr int kBars = kWarps * kDepth * 8;
+  // FINAL symmetric: per-column factors of the panel, fa = coef g_col unit, fb = coef g_col
+  static constexpr int kFac = (MODE == MODE_FINAL_SYM && sizeof(E) == 2) ? TC * 16 : 0;
   // transposed-store tile [TC][kPitch]: odd pitch in 32-bit words where the element size allows
   static constexpr int kPitch = sizeof(TileT) == 2 ? TI + 2 : TI + 1;
   static constexpr int kTile = MODE == MODE_FINAL_SYM ? 0 : TC * kPitch * (int)sizeof(TileT);
-  static constexpr int kBytes = kRing + kBars + kTile;
+  static constexpr int kBytes = kRing + kBars + kFac + kTile + 128;
+  static_assert(kSeg % 512 == 0 && kSeg <= 1024, "row segments are 512 B or 1 KB (TMA box <= 256 elements of 4 B)");
 };
 
 template <typename E, int TC, int MODE>
 __global__ void __launch_bounds__(kThreads)
-csr_gather_kernel(const Params p) {
+csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   typedef Smem<E, TC, MODE> SM;
   typedef typename SM::TileT TileT;
+  typedef Acc<E, TC> A;
   constexpr bool kU16 = sizeof(E) == 2;
-  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int kDepth = SM::kDepth;
+  extern __shared__ uint8_t smem_raw[];
   __shared__ double red[2][kWarps];
+  __shared__ int next_row;                    // rows of the tile are claimed by the warps as they go
+  __shared__ uint8_t fifo[kWarps][TI];        // rows a warp has claimed, in order (issue side -> consume side)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kRing);
-  TileT* tile = reinterpret_cast<TileT*>(smem + SM::kRing + SM::kBars);
+  double2* fac = reinterpret_cast<double2*>(smem + SM::kRing + SM::kBars);
+  TileT* tile = reinterpret_cast<TileT*>(smem + SM::kRing + SM::kBars + SM::kFac);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i0 = p.row_begin + (int64_t)blockIdx.x * TI;
   const int64_t c0 = (int64_t)blockIdx.y * TC;
   if (MODE == MODE_FINAL_SYM && c0 + TC - 1 < i0) return;      // every element has c < i: mirrored from above
+  const int rows_here = (int)min((int64_t)TI, p.row_end - i0);
 
-  uint8_t* wring = smem + (size_t)warp * kDepth * SM::kSeg;
+  uint8_t* wring = smem + (size_t)warp * kDepth * SM::kSlot;
   uint64_t* wbar = bars + warp * kDepth;
-  if (p.bulk) {
-    if (lane < kDepth) mbar_init(&wbar[lane], 1);
-    fence_barrier_init();
-    __syncwarp();
+  if (p.tma && lane < kDepth) mbar_init(&wbar[lane], 1);
+  if (p.tma) fence_barrier_init();
+  if (threadIdx.x == 0) next_row = 0;
+  if (MODE == MODE_FINAL_SYM && kU16) {
+    for (int c = threadIdx.x; c < TC; c += kThreads) {
+      const int64_t cc = c0 + c;
+      const double gc = cc < p.L ? p.g_col[cc] * p.epi.coef : 0.0;
+      fac[c] = make_double2(cc < p.L ? gc * row_bound(p.in_unit, cc) : 0.0, gc);
+    }
   }
+  __syncthreads();
 
   double dmax = 0.0, omax = 0.0;
-  const int64_t r_lo = i0 + (int64_t)warp * kRowsPerWarp;
-  const int64_t r_hi = min(r_lo + (int64_t)kRowsPerWarp, p.row_end);
-  if (r_lo < p.row_end) {
-    const int64_t eb = p.indptr[r_lo], ee = p.indptr[r_hi];
+  {
     const int64_t valid = min((int64_t)TC, p.ldx - c0);               // columns of X this panel can read
-    const uint32_t seg_bytes = (uint32_t)(valid * (int64_t)sizeof(E));
     const uint8_t* xbase = reinterpret_cast<const uint8_t*>(p.X) + c0 * (int64_t)sizeof(E);
     const int64_t pitch = p.ldx * (int64_t)sizeof(E);
     const uint64_t pol = (p.flags & 1) ? policy_evict_normal() : policy_evict_last();
-    int idx_cur = (eb + lane < ee) ? p.indices[eb + lane] : 0;
-    int idx_nxt = (eb + 32 + lane < ee) ? p.indices[eb + 32 + lane] : 0;
-    int64_t chunk_base = eb;                                        // stream position held by lane 0 of idx_cur
-    if (p.bulk && lane < kDepth && eb + lane < ee) {
-      mbar_expect_tx(&wbar[lane], seg_bytes);
-      bulk_copy(wring + lane * SM::kSeg, xbase + (int64_t)idx_cur * pitch, seg_bytes, &wbar[lane], pol);
+    const int col32 = (int)(c0 * (int64_t)sizeof(E) / 4);             // TMA coordinate in 4-byte elements
+
+    // ---- issue side.  Rows are claimed from the tile's counter when the previous one runs out (a warp
+    // stuck on a hub row claims nothing while the others share the rest) and pushed to the warp's FIFO
+    // for the consume side; the neighbour indices of the NEXT instruction are loaded one step early,
+    // so the refill of a slot does not wait for them.
+    int wi = 0, ri = 0;                                               // FIFO write / read positions
+    int64_t ip = 0, iend = 0;
+    int pre_my = 0;
+    bool have_pre = false;
+    unsigned issued = 0;
+    auto advance = [&]() {
+      have_pre = false;
+      while (ip >= iend) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&next_row, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= rows_here) return;
+        if (lane == 0) fifo[warp][wi] = (uint8_t)r;
+        ++wi;
+        ip = p.indptr[i0 + r];
+        iend = p.indptr[i0 + r + 1];
+      }
+      const int cnt = (int)min((int64_t)kRowsPerOp, iend - ip);
+      pre_my = p.indices[ip + min(lane & 3, cnt - 1)];                // a short group repeats its last row
+      ip += kRowsPerOp;
+      have_pre = true;
+    };
+    auto issue_next = [&]() {
+      if (!have_pre) return;
+      const int m0 = __shfl_sync(0xffffffffu, pre_my, 0), m1 = __shfl_sync(0xffffffffu, pre_my, 1);
+      const int m2 = __shfl_sync(0xffffffffu, pre_my, 2), m3 = __shfl_sync(0xffffffffu, pre_my, 3);
+      if (lane == 0) {
+        const int slot = (int)(issued % kDepth);
+        mbar_expect_tx(&wbar[slot], SM::kSlot);
+        tma_gather4(wring + slot * SM::kSlot, &map_x, &wbar[slot], pol, col32, m0, m1, m2, m3);
+      }
+      ++issued;
+      advance();
+    };
+    advance();
+    if (p.tma) {
+#pragma unroll 1
+      for (int d = 0; d < kDepth; ++d) issue_next();
     }
-    Acc<E, TC> acc;
-    acc.clear();
-    int64_t e = eb;
-    for (int64_t row = r_lo; row < r_hi; ++row) {
-      const int64_t rend = p.indptr[row + 1];
-      for (; e < rend; ++e) {
-        if (e - chunk_base == 32) {
-          idx_cur = idx_nxt;
-          chunk_base += 32;
-          idx_nxt = (chunk_base + 32 + lane < ee) ? p.indices[chunk_base + 32 + lane] : 0;
-        }
-        if (p.bulk) {
-          const unsigned q = (unsigned)(e - eb);
-          const int slot = (int)(q % kDepth);
-          mbar_wait(&wbar[slot], (q / kDepth) & 1u);
-          acc.add_smem(wring + slot * SM::kSeg, lane);
-          __syncwarp();                                             // every lane has read the slot
-          const int64_t pe = e + kDepth;                            // stream position that reuses it
-          if (pe < ee) {
-            const int poff = (int)(pe - chunk_base);                // < 32 + kDepth
-            if (lane == (poff & 31)) {
-              const int m = poff < 32 ? idx_cur : idx_nxt;
-              fence_proxy_async();                                  // generic-proxy reads before the async write
-              mbar_expect_tx(&wbar[slot], seg_bytes);
-              bulk_copy(wring + slot * SM::kSeg, xbase + (int64_t)m * pitch, seg_bytes, &wbar[slot], pol);
-            }
+
+    A acc;
+    unsigned consumed = 0;
+    while (true) {
+      __syncwarp();                                                   // FIFO entries written by lane 0
+      if (ri == wi) break;                                            // every claimed row is done, none left to claim
+      const int64_t row = i0 + fifo[warp][ri];
+      ++ri;
+      const int64_t rbeg = p.indptr[row], rend = p.indptr[row + 1];
+      if (MODE == MODE_FINAL_SYM && p.epi.s_old) {
+        // the epilogue of this row reads S_old (and the counts) once the gather is done: pull its
+        // lines into L2 now, so that it sees L2 latency instead of DRAM latency
+#pragma unroll
+        for (int gq = 0; gq < A::kGroups; ++gq) {
+          const int64_t c = c0 + gq * A::kGroupCols + A::kVec * lane;
+          if (c < p.L && c + A::kVec > row) {
+            prefetch_l2(p.epi.s_old + row * p.epi.ld_s_old + c);
+            if (A::kVec > 4 && c + 4 < p.L) prefetch_l2(p.epi.s_old + row * p.epi.ld_s_old + c + 4);
           }
-        } else {
-          const int m = __shfl_sync(0xffffffffu, idx_cur, (int)(e - chunk_base));
-          acc.add_global(xbase + (int64_t)m * pitch, lane, valid);
         }
+      }
+      acc.clear();
+      if (p.tma) {
+        for (int64_t e = rbeg; e < rend; e += kRowsPerOp) {
+          const int cnt = (int)min((int64_t)kRowsPerOp, rend - e);
+          const int slot = (int)(consumed % kDepth);
+          mbar_wait(&wbar[slot], (consumed / kDepth) & 1u);
+          const uint8_t* sp = wring + slot * SM::kSlot;
+          acc.add_smem(sp, lane);
+          if (cnt > 1) acc.add_smem(sp + SM::kSeg, lane);
+          if (cnt > 2) acc.add_smem(sp + 2 * SM::kSeg, lane);
+          if (cnt > 3) acc.add_smem(sp + 3 * SM::kSeg, lane);
+          ++consumed;
+          __syncwarp();                                             // every lane has read the slot
+          issue_next();                                             // refills it (kDepth steps ahead)
+        }
+      } else {
+        for (int64_t e = rbeg; e < rend; e += 32) {
+          const int cnt = (int)min((int64_t)32, rend - e);
+          const int my = lane < cnt ? p.indices[e + lane] : 0;
+          for (int t = 0; t < cnt; ++t)
+            acc.add_global(xbase + (int64_t)__shfl_sync(0xffffffffu, my, t) * pitch, lane, valid);
+        }
+        ip = iend;                                                  // plain loads: the issue side only claims rows
+        advance();
       }
 
       // ------------------------------------------------------------------ row `row` is complete
@@ -278,8 +365,8 @@ csr_gather_kernel(const Params p) {
           const double bo = row_bound(p.out_bound, row);
           const double inv = bo > 0.0 ? 65535.0 / bo : 0.0;
 #pragma unroll
-          for (int j = 0; j < Acc<E, TC>::kCols; ++j) {
-            const int cl = Acc<E, TC>::col(j, lane);
+          for (int j = 0; j < A::kCols; ++j) {
+            const int cl = col_of<E, TC>(j, lane);
             const int64_t c = c0 + cl;
             double q = c < p.L ? rint(acc.val(j) * row_bound(p.in_unit, c) * inv) : 0.0;
             if (!(q > 0.0)) q = 0.0;
@@ -289,46 +376,92 @@ csr_gather_kernel(const Params p) {
         } else {
           const double gi = p.g[row];
 #pragma unroll
-          for (int j = 0; j < Acc<E, TC>::kCols; ++j)
-            tile[Acc<E, TC>::col(j, lane) * SM::kPitch + il] = (TileT)(acc.val(j) * gi);
+          for (int j = 0; j < A::kCols; ++j) tile[col_of<E, TC>(j, lane) * SM::kPitch + il] = (TileT)(acc.val(j) * gi);
         }
       } else if (MODE == MODE_FINAL) {
         if (kU16) {
 #pragma unroll
-          for (int j = 0; j < Acc<E, TC>::kCols; ++j) tile[Acc<E, TC>::col(j, lane) * SM::kPitch + il] = (TileT)acc.val(j);
+          for (int j = 0; j < A::kCols; ++j) tile[col_of<E, TC>(j, lane) * SM::kPitch + il] = (TileT)acc.val(j);
         } else {
           const double gi = p.g[row];
 #pragma unroll
-          for (int j = 0; j < Acc<E, TC>::kCols; ++j)
-            tile[Acc<E, TC>::col(j, lane) * SM::kPitch + il] = (TileT)(acc.val(j) * gi);
+          for (int j = 0; j < A::kCols; ++j) tile[col_of<E, TC>(j, lane) * SM::kPitch + il] = (TileT)(acc.val(j) * gi);
         }
       } else {
-        // symmetric FINAL: element (row, c) for c >= row, also stored at (c, row)
-        const double gi = p.g[row] * p.epi.coef;
+        // symmetric FINAL: element (row, c) for c >= row, also stored at (c, row).  Per group the
+        // lane owns kVec consecutive columns: vector loads of counts / S_old, vector store of the row.
+        const double gi = kU16 ? p.g[row] : p.g[row] * p.epi.coef;
         double* orow = reinterpret_cast<double*>(p.OUT) + row * p.ldo;
 #pragma unroll
-        for (int j = 0; j < Acc<E, TC>::kCols; ++j) {
-          const int64_t c = c0 + Acc<E, TC>::col(j, lane);
-          if (c >= p.L || c < row) continue;
-          uint32_t cnt = 0u;
-          if (p.counts) cnt = load_count(p.counts, row * p.ld_counts + c, p.counts32);
-          double v;
-          if (kU16)
-            v = gi * p.g_col[c] * (acc.val(j) * row_bound(p.in_unit, c) + (p.add_counts ? (double)cnt : 0.0));
-          else
-            v = acc.val(j) * gi;
-          if (p.use_evidence) v *= evidence_factor(cnt);
-          else if (p.epi.evidence) v *= evidence_factor(__ldcs(p.epi.evidence + row * p.epi.ld_evidence + c));
-          if (c == row) v = 1.0; else if (v > omax) omax = v;
-          if (p.epi.s_old) {
-            const double d = fabs(v - __ldcs(p.epi.s_old + row * p.epi.ld_s_old + c));
-            if (d > dmax) dmax = d;
+        for (int gq = 0; gq < A::kGroups; ++gq) {
+          const int cl0 = gq * A::kGroupCols + A::kVec * lane;
+          const int64_t cb = c0 + cl0;                              // first of the kVec columns
+          if (cb >= p.L || cb + A::kVec <= row) continue;           // nothing at or right of the diagonal
+          const bool whole = cb >= row && cb + A::kVec <= p.L;      // every element is stored
+          uint32_t cnt[A::kVec];
+          double so[A::kVec], v[A::kVec];
+#pragma unroll
+          for (int x = 0; x < A::kVec; ++x) { cnt[x] = 0u; so[x] = 0.0; }
+          const bool vec_ok = whole && p.vec_aligned && ((p.ld_counts | p.epi.ld_s_old | p.ldo) & (A::kVec - 1)) == 0;
+          if (p.counts) {
+            if (vec_ok && !p.counts32 && A::kVec == 8) {
+              const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.counts) + row * p.ld_counts + cb);
+              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int x = 0; x < A::kVec; ++x) cnt[x] = (w[x >> 1] >> (16 * (x & 1))) & 0xffffu;
+            } else {
+#pragma unroll
+              for (int x = 0; x < A::kVec; ++x)
+                if (cb + x < p.L && cb + x >= row) cnt[x] = load_count(p.counts, row * p.ld_counts + cb + x, p.counts32);
+            }
           }
-          __stcs(orow + c, v);
-          if (c > row) __stcs(reinterpret_cast<double*>(p.OUT) + c * p.ldo + row, v);
+          if (p.epi.s_old) {
+            if (vec_ok) {
+#pragma unroll
+              for (int x = 0; x < A::kVec; x += 2) {
+                const double2 d = *reinterpret_cast<const double2*>(p.epi.s_old + row * p.epi.ld_s_old + cb + x);
+                so[x] = d.x; so[x + 1] = d.y;
+              }
+            } else {
+#pragma unroll
+              for (int x = 0; x < A::kVec; ++x)
+                if (cb + x < p.L && cb + x >= row) so[x] = p.epi.s_old[row * p.epi.ld_s_old + cb + x];
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < A::kVec; ++x) {
+            const int64_t c = cb + x;
+            const int j = gq * A::kVec + x;
+            double val;
+            if (kU16) {
+              const double2 f = fac[cl0 + x];
+              val = gi * (acc.val(j) * f.x + (p.add_counts ? (double)cnt[x] * f.y : 0.0));
+            } else {
+              val = acc.val(j) * gi;
+            }
+            if (p.use_evidence) val *= evidence_factor(cnt[x]);
+            else if (p.epi.evidence && c < p.L && c >= row) val *= evidence_factor(p.epi.evidence[row * p.epi.ld_evidence + c]);
+            const bool live = c < p.L && c >= row;
+            if (c == row) val = 1.0; else if (live && val > omax) omax = val;
+            if (live && p.epi.s_old) {
+              const double d = fabs(val - so[x]);
+              if (d > dmax) dmax = d;                 // NaN compares false: ignored like SimRank.py:74
+            }
+            v[x] = val;
+          }
+          if (vec_ok) {
+#pragma unroll
+            for (int x = 0; x < A::kVec; x += 2) __stcs(reinterpret_cast<double2*>(orow + cb + x), make_double2(v[x], v[x + 1]));
+          } else {
+#pragma unroll
+            for (int x = 0; x < A::kVec; ++x)
+              if (cb + x < p.L && cb + x >= row) __stcs(orow + cb + x, v[x]);
+          }
+#pragma unroll
+          for (int x = 0; x < A::kVec; ++x)
+            if (cb + x < p.L && cb + x > row) __stcs(reinterpret_cast<double*>(p.OUT) + (cb + x) * p.ldo + row, v[x]);
         }
       }
-      acc.clear();
     }
   }
 
@@ -437,12 +570,44 @@ quantize_transpose_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t
   }
 }
 
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
 template <typename E, int TC, int MODE>
-static int launch_one(const Params& p, dim3 grid, cudaStream_t st) {
+static int launch_one(Params& p, int64_t x_rows, dim3 grid, cudaStream_t st) {
   typedef Smem<E, TC, MODE> SM;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (p.tma) {
+    // X as a 2-D tensor of 4-byte elements [x_rows][ldx * sizeof(E) / 4]; a box is one row segment
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(SRK_ERR_CUDA, "%s", "cuTensorMapEncodeTiled is not available from the driver");
+    const int64_t row_bytes = p.ldx * (int64_t)sizeof(E);
+    cuuint64_t dims[2] = {(cuuint64_t)(row_bytes / 4), (cuuint64_t)x_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(SM::kSeg / 4), 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(p.X), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) p.tma = 0;                                   // shapes TMA cannot describe: plain loads
+  }
   auto kern = csr_gather_kernel<E, TC, MODE>;
   SRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-  kern<<<grid, kThreads, SM::kBytes, st>>>(p);
+  kern<<<grid, kThreads, SM::kBytes, st>>>(map, p);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }
@@ -459,6 +624,7 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   // OUT is addressed as OUT[c * ldo + i] for i in [row_begin, row_end) only: a caller that stores just
   // those columns passes the address of (virtual) column 0, i.e. its buffer minus row_begin elements
   SRK_REQUIRE(a->L >= 0 && a->ldx >= a->L && a->ldo >= a->row_end - a->row_begin, "leading dimensions");
+  SRK_REQUIRE(a->K >= 0 && a->K < (1ll << 31), "K (rows of X) out of range");
   SRK_REQUIRE(a->elem == SRK_ELEM_F64 || a->elem == SRK_ELEM_U16, "elem must be SRK_ELEM_F64 or SRK_ELEM_U16");
   SRK_REQUIRE(a->mode == SRK_CSR_FIRST || a->mode == SRK_CSR_FINAL, "mode must be SRK_CSR_FIRST or SRK_CSR_FINAL");
   SRK_REQUIRE(a->counts_bits == 0 || a->counts_bits == 16 || a->counts_bits == 32, "counts_bits must be 16 or 32");
@@ -482,32 +648,35 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   p.add_counts = a->add_counts; p.use_evidence = a->use_evidence;
   if (a->mode == SRK_CSR_FINAL) { p.epi = to_dev(a->epi); p.maxdiff = a->epi.maxdiff; p.maxoff = a->epi.maxoff; }
   const int64_t esz = a->elem == SRK_ELEM_U16 ? 2 : 8;
-  p.bulk = ((uintptr_t)a->X % 16 == 0) && ((a->ldx * esz) % 16 == 0);
-  { const char* e = getenv("SRK_CSR_FLAGS"); p.flags = e ? atoi(e) : 0; if (p.flags & 2) p.bulk = 0; }
+  // TMA needs 16-byte aligned rows
+  p.tma = ((uintptr_t)a->X % 16 == 0) && ((a->ldx * esz) % 16 == 0);
+  p.vec_aligned = (((uintptr_t)a->OUT | (uintptr_t)a->epi.s_old | (uintptr_t)a->counts) % 16) == 0;
+  const int64_t x_rows = a->K > 0 ? a->K : (1ll << 31) - 1;        // bound of TMA's row check (K unknown: none)
+  { const char* e = getenv("SRK_CSR_FLAGS"); p.flags = e ? atoi(e) : 0; if (p.flags & 2) p.tma = 0; }
 
   // Panel width = columns of X per CTA = what all CTAs of a grid column gather from; the panel (rows
   // of X x segment bytes, held once per L2 die) has to survive in L2 next to the streams of the
-  // epilogue.  float64: 128 columns (1 KB segments) for the first half, 64 for the second, which also
-  // streams S_old (with 128 its panel fell out of L2: 93 ms against 42 ms at n = 32768).  uint16: 256
-  // columns (512 B segments).
+  // epilogue.  1 KB segments (uint16: 512 columns, float64: 128) reach the L2 roof, 512 B ones stop at
+  // two thirds of it (profiles/r2_micro_tma_gather_rate.txt); the transposed second half keeps a
+  // 4-byte tile per element in shared memory and takes the narrower panel.
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = a->row_end - a->row_begin;
   const int mode = a->mode == SRK_CSR_FIRST ? gat::MODE_FIRST : (sym ? gat::MODE_FINAL_SYM : gat::MODE_FINAL);
-  const int tc = a->elem == SRK_ELEM_U16 ? 256 : (mode == gat::MODE_FIRST ? 128 : 64);
+  const int tc = a->elem == SRK_ELEM_U16 ? (mode == gat::MODE_FINAL ? 256 : 512) : (mode == gat::MODE_FINAL ? 64 : 128);
   const int64_t gx = (rows + gat::TI - 1) / gat::TI, gy = (a->L + tc - 1) / tc;
   SRK_REQUIRE(gy <= 65535, "too many column panels");
   dim3 grid((unsigned)gx, (unsigned)gy);
   if (a->elem == SRK_ELEM_U16) {
     switch (mode) {
-      case gat::MODE_FIRST: return gat::launch_one<uint16_t, 256, gat::MODE_FIRST>(p, grid, st);
-      case gat::MODE_FINAL: return gat::launch_one<uint16_t, 256, gat::MODE_FINAL>(p, grid, st);
-      default: return gat::launch_one<uint16_t, 256, gat::MODE_FINAL_SYM>(p, grid, st);
+      case gat::MODE_FIRST: return gat::launch_one<uint16_t, 512, gat::MODE_FIRST>(p, x_rows, grid, st);
+      case gat::MODE_FINAL: return gat::launch_one<uint16_t, 256, gat::MODE_FINAL>(p, x_rows, grid, st);
+      default: return gat::launch_one<uint16_t, 512, gat::MODE_FINAL_SYM>(p, x_rows, grid, st);
     }
   }
   switch (mode) {
-    case gat::MODE_FIRST: return gat::launch_one<double, 128, gat::MODE_FIRST>(p, grid, st);
-    case gat::MODE_FINAL: return gat::launch_one<double, 64, gat::MODE_FINAL>(p, grid, st);
-    default: return gat::launch_one<double, 64, gat::MODE_FINAL_SYM>(p, grid, st);
+    case gat::MODE_FIRST: return gat::launch_one<double, 128, gat::MODE_FIRST>(p, x_rows, grid, st);
+    case gat::MODE_FINAL: return gat::launch_one<double, 64, gat::MODE_FINAL>(p, x_rows, grid, st);
+    default: return gat::launch_one<double, 128, gat::MODE_FINAL_SYM>(p, x_rows, grid, st);
   }
 }
 

@@ -95,9 +95,131 @@ def pair_tasks(plan: ShardPlan, q: int, symmetric: bool):
     return tasks
 
 
+# --------------------------------------------------------------------------- communicators
+# Every collective of the sharded solvers goes through these four helpers, so that ``group`` can be a
+# torch.distributed process group (None = the default one) or a LocalRank: one of P logical ranks that
+# share ONE GPU inside one process (LocalCluster below).
+def _rank_world(group=None):
+    if isinstance(group, LocalRank):
+        return group.rank, group.world
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _all_reduce_max(t, group):
+    if isinstance(group, LocalRank):
+        return group.all_reduce_max(t)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+
+
+def _all_to_all(recv, send, group):
+    if isinstance(group, LocalRank):
+        return group.all_to_all(recv, send)
+    dist.all_to_all_single(recv, send, group=group)
+
+
+def _all_gather_into(full, part, group):
+    if isinstance(group, LocalRank):
+        return group.all_gather_into(full, part)
+    dist.all_gather_into_tensor(full, part, group=group)
+
+
+class LocalCluster:
+    """P logical ranks on ONE GPU in one process, one Python thread per rank (SURVEY.md section 4 iv:
+    "same kernels, P logical shards on 1 GPU").  The ranks run the unmodified sharded solvers; their
+    collectives are thread barriers plus device copies, and "peer" pointers are simply the other
+    ranks' buffers on the same device, so the kernels' peer-store paths (U blocks, mirrored S blocks,
+    row-maximum keys) execute exactly as they do over NVLink.  All ranks launch on the same CUDA
+    stream, and a launch is enqueued before its thread reaches the next barrier, so stream order
+    respects every barrier.  Used by the single-GPU tests of the multi-GPU algorithms and for
+    debugging a sharded fit without a multi-GPU box."""
+
+    def __init__(self, world: int):
+        import threading
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.lock = threading.Lock()
+        self.slots = {}
+        self.arenas = {}
+
+    def run(self, fn):
+        """Call ``fn(group)`` on every logical rank (group = its LocalRank); -> list of results."""
+        import threading
+        out, err = [None] * self.world, [None] * self.world
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+
+        def body(r):
+            try:
+                if dev is not None:
+                    torch.cuda.set_device(dev)
+                out[r] = fn(LocalRank(self, r))
+            except BaseException as exc:                       # noqa: BLE001 -- re-raised below
+                err[r] = exc
+                self.barrier.abort()
+
+        threads = [threading.Thread(target=body, args=(r,)) for r in range(self.world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        real = [e for e in err if e is not None and not isinstance(e, __import__("threading").BrokenBarrierError)]
+        if real or any(err):
+            raise (real or [e for e in err if e is not None])[0]
+        return out
+
+
+class LocalRank:
+    """Communicator handle of one logical rank of a LocalCluster (passed as ``group``)."""
+
+    def __init__(self, cluster: LocalCluster, rank: int):
+        self.cluster, self.rank, self.world = cluster, rank, cluster.world
+        self._allocs = 0
+
+    def _publish(self, key, value):
+        c = self.cluster
+        with c.lock:
+            c.slots.setdefault(key, [None] * self.world)[self.rank] = value
+        c.barrier.wait()
+        return c.slots[key]
+
+    def _done(self):
+        self.cluster.barrier.wait()                            # everybody has read the published values
+
+    def all_reduce_max(self, t):
+        parts = self._publish("max", t)
+        m = torch.stack([x.to(t.device) for x in parts]).amax(dim=0)
+        self._done()
+        t.copy_(m)
+
+    def all_to_all(self, recv, send):
+        parts = self._publish("a2a", send)
+        for s in range(self.world):
+            recv[s].copy_(parts[s][self.rank])
+        self._done()
+
+    def all_gather_into(self, full, part):
+        parts = self._publish("gather", part)
+        n = part.shape[0]
+        for s in range(self.world):
+            full[s * n:(s + 1) * n].copy_(parts[s])
+        self._done()
+
+    def barrier(self):
+        self.cluster.barrier.wait()
+
+    def alloc_shared(self, shape, dtype, device):
+        """The rank's buffer of a symmetric allocation and the device pointers of every rank's."""
+        c, key = self.cluster, self._allocs
+        self._allocs += 1
+        with c.lock:
+            if key not in c.arenas:
+                c.arenas[key] = [torch.zeros(shape, dtype=dtype, device=device) for _ in range(self.world)]
+        bufs = c.arenas[key]
+        return bufs[self.rank], [int(b.data_ptr()) for b in bufs]
+
+
 # --------------------------------------------------------------------------- exchange strategies
 class StagedExchange:
-    """Kernels store into local staging blocks; torch.distributed collectives move them."""
+    """Kernels store into local staging blocks; collectives move them."""
 
     peer = False
 
@@ -133,16 +255,51 @@ class PeerExchange:
         self._handles[0].barrier(channel=0)
 
 
+class LocalPeerExchange:
+    """PeerExchange of a LocalCluster: the peers' buffers live on the same device."""
+
+    peer = True
+
+    def __init__(self, group: LocalRank):
+        self.group = group
+
+    def alloc(self, shape, dtype, device):
+        return self.group.alloc_shared(tuple(shape), dtype, device)
+
+    def barrier(self):
+        self.group.barrier()
+
+
 def make_exchange(device, group=None):
+    """Peer-memory exchange when every rank can map symmetric memory, else the staged fallback.  The
+    decision is agreed across the ranks (MIN all-reduce of a probe allocation + rendezvous), so that a
+    box without P2P / NVLink takes the staged path on all ranks instead of failing on some."""
     want = os.environ.get("SIMRANK_B200_EXCHANGE", "auto").lower()
+    if isinstance(group, LocalRank):
+        return StagedExchange(group) if want == "staged" else LocalPeerExchange(group)
     if want == "staged" or torch.device(device).type != "cuda":
         return StagedExchange(group)
+    ex, ok = None, 1
     try:
-        return PeerExchange(group)
+        ex = PeerExchange(group)
+        ex.symm.empty(256, dtype=torch.uint8, device=device)          # local part of the probe
     except Exception:
-        if want == "peer":
-            raise
-        return StagedExchange(group)
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()):
+        try:
+            ex.alloc((256,), torch.uint8, device)                      # collective part: rendezvous
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()):
+        ex._handles.clear()                                            # barrier() uses the first REAL allocation
+        return ex
+    if want == "peer":
+        raise RuntimeError("SIMRANK_B200_EXCHANGE=peer, but symmetric memory is not available on every rank")
+    return StagedExchange(group)
 
 
 class ShardedHalf:
@@ -232,7 +389,7 @@ class ShardedHalf:
             self.planes.stride(0), _ptr(self.bound_vec), _stream()), "srk_slice_rows_max_f64")
 
     def _reduce_scalars(self):
-        dist.all_reduce(self.scal, op=dist.ReduceOp.MAX, group=self.group)
+        _all_reduce_max(self.scal, self.group)
 
     # ---- pieces of one update ------------------------------------------------------------------
     def _pattern_counts(self) -> torch.Tensor:
@@ -304,7 +461,7 @@ class ShardedHalf:
             self.ex.barrier()
             return
         recv = torch.empty_like(self.send_U)
-        dist.all_to_all_single(recv, self.send_U, group=self.group)
+        _all_to_all(recv, self.send_U, self.group)
         for s in range(self.world):                               # block from rank s = its rows as my columns
             cnt = src.plan.count(s)
             if cnt:
@@ -361,7 +518,7 @@ class ShardedHalf:
         """Staged mode: deliver the mirrored blocks and place them (peer mode stored them already)."""
         if self.ex.peer or self.mirror_send is None:
             return
-        dist.all_to_all_single(self.mirror_recv, self.mirror_send, group=self.group)
+        _all_to_all(self.mirror_recv, self.mirror_send, self.group)
         for s in range(self.world):
             if s == self.rank:
                 continue
@@ -410,7 +567,7 @@ class ShardedHalf:
         pad = torch.zeros((per, self.n_out), dtype=self.S.dtype, device=self.S.device)
         pad[: self.rows] = self.local_result()
         full = torch.empty((self.world * per, self.n_out), dtype=self.S.dtype, device=self.S.device)
-        dist.all_gather_into_tensor(full, pad, group=self.group)
+        _all_gather_into(full, pad, self.group)
         return full[: self.n_out]
 
 
@@ -465,7 +622,7 @@ class ShardedCsrHalf:
                    "srk_csr_half_f64")
 
     def _reduce_scalars(self):
-        dist.all_reduce(self.scal, op=dist.ReduceOp.MAX, group=self.group)
+        _all_reduce_max(self.scal, self.group)
 
     _timed = ShardedHalf._timed
 
@@ -480,15 +637,17 @@ class ShardedCsrHalf:
         def first():
             if src.rows == 0:
                 return
-            # column block of the symmetric S_in = its local row block, transposed (a copy, no arithmetic)
-            xt = src.S[: src.rows, : self.n_in].t().contiguous()                  # [n_in, rows_in_q]
+            # column block of the symmetric S_in = its local row block, transposed (a copy, no arithmetic);
+            # rows padded to the block height so that they stay 16-byte aligned for the TMA gather
+            xt = torch.empty((self.n_in, per_in), dtype=torch.float64, device=self.device)
+            xt[:, : src.rows] = src.S[: src.rows, : self.n_in].t()
             for p in range(P):
                 lo, hi = self.plan.start(p), self.plan.stop(p)
                 if hi > lo:        # OUT[c, i] lands at send[p][c, i - lo]: shift the base by -lo columns
-                    self._launch_csr(lo, hi, xt.data_ptr(), src.rows, src.rows,
+                    self._launch_csr(lo, hi, xt.data_ptr(), per_in, src.rows,
                                      self._send[p].data_ptr() - 8 * lo, per_out, None)
         self._timed("csr_half_first", first)
-        self._timed("exchange", lambda: dist.all_to_all_single(self._recv, self._send, group=self.group))
+        self._timed("exchange", lambda: _all_to_all(self._recv, self._send, self.group))
 
         def second():
             if self.rows == 0:
@@ -503,6 +662,18 @@ class ShardedCsrHalf:
             e.maxdiff, e.maxoff = self.scal.data_ptr(), self.scal.data_ptr() + 8
             e.diag_offset = self.row0
             # block q of the receive buffer holds rows start_in(q).. of the panel: [P * per_in, per_out]
+            if getattr(self, "evidence_from_pattern", False):       # a float64 update of the csr16 mode
+                b = _lib.CsrArgs()
+                b.elem, b.mode = _lib.SRK_ELEM_F64, _lib.SRK_CSR_FINAL
+                b.indptr, b.indices, b.g = self.indptr.data_ptr(), self.indices.data_ptr(), self.g.data_ptr()
+                b.M, b.row_begin, b.row_end = self.n_out, 0, self.n_out
+                b.X, b.ldx, b.L, b.K = self._recv.data_ptr(), per_out, self.rows, P * per_in
+                b.OUT, b.ldo = self.S.data_ptr(), self.ld
+                b.counts, b.ld_counts = self.counts.data_ptr(), self.counts.stride(0)
+                b.counts_bits, b.use_evidence = 8 * self.counts.element_size(), 1
+                b.epi = e
+                _lib.check(_lib.load().srk_csr_half(C.byref(b), _stream()), "srk_csr_half(f64, second)")
+                return
             self._launch_csr(0, self.n_out, self._recv.data_ptr(), per_out, self.rows, self.S.data_ptr(), self.ld, e)
         self._timed("csr_half_final", second)
 
@@ -510,14 +681,127 @@ class ShardedCsrHalf:
         self._reduce_scalars()
         maxdiff, maxoff = self.scal.tolist()
         self.maxoff = maxoff
+        self.err = getattr(self, "_err_next", 0.0)
         return maxdiff
 
     local_result = ShardedHalf.local_result
     gathered_result = ShardedHalf.gathered_result
 
 
-def _rank_world(group=None):
-    return dist.get_rank(group), dist.get_world_size(group)
+class ShardedCsr16Half(ShardedCsrHalf):
+    """ShardedCsrHalf with the gathers in uint16 fixed point (engine._Half csr16 mode, row-sharded):
+
+      1. quantise  Xq = srk_quantize_rows_u16(local rows of S_in): the transposed local row block with one
+                   unit per local row -- the column block of S_off the first half gathers from.
+      2. first     Tq[rows_in_q, rows_out_p] per destination rank p (exact integer sums, re-quantised
+                   with the bound deg(i) * max(S_off) of its column), stored into the send block for p.
+      3. exchange  the same block transpose, 2 bytes per element instead of 8.
+      4. second    srk_csr_half FINAL on the received panel with counts = A A^T of the local rows (the
+                   unit-diagonal term, also the SimRank++ evidence) and the fused epilogue.
+
+    An update whose 16-bit error bound would exceed engine.ERR_BUDGET runs in float64 (the parent's
+    update): both kinds read and write the same float64 S."""
+
+    def __init__(self, op: HostOperator, coef, rank, world, device, evidence=None, prior=None, lbd=0.0, group=None,
+                 evidence_from_pattern=False):
+        super().__init__(op, coef, rank, world, device, evidence, prior, lbd, group)
+        if prior is not None:
+            raise ValueError("mode='csr16' does not take a prior; use mode='csr' (float64)")
+        self.evidence_from_pattern = bool(evidence_from_pattern)
+        g = np.ascontiguousarray(op.g, dtype=np.float64)
+        self.rho_max = float((g * op.deg).max()) if g.size else 0.0
+        self.deg_dev = torch.from_numpy(op.deg.astype(np.float64)).to(device)
+        self.lda = _round_up(max(self.n_in, 1), 128)
+        self.a8 = self._dense_pattern()
+        self.counts = self._pattern_counts()
+        del self.a8                                                # only needed for the counts
+        self.err = self._err_next = 0.0
+        self.ldxt = _round_up(self.per, 64)
+        self.Xq, self.unit = None, torch.zeros(self.per, dtype=torch.float64, device=device)
+        self.version, self._quantized_version = 0, -1
+        self._send16 = self._recv16 = None
+
+    _dense_pattern = ShardedHalf._dense_pattern
+    _pattern_counts = ShardedHalf._pattern_counts
+    _launch = ShardedHalf._launch
+
+    def _quantized(self):
+        """uint16 transposed local row block of the CURRENT S (cached per version)."""
+        if self.Xq is None:
+            self.Xq = torch.zeros((self.n_out, self.ldxt), dtype=torch.int16, device=self.device)
+        if self._quantized_version != self.version and self.rows:
+            _lib.check(_lib.load().srk_quantize_rows_u16(_ptr(self.S), self.ld, self.rows, self.n_out, self.row0,
+                                                         _ptr(self.Xq), self.ldxt, _ptr(self.unit), _stream()),
+                       "srk_quantize_rows_u16")
+        self._quantized_version = self.version
+        return self.Xq, self.unit
+
+    def _args(self, elem, mode):
+        a = _lib.CsrArgs()
+        a.elem, a.mode = elem, mode
+        a.indptr, a.indices, a.g = self.indptr.data_ptr(), self.indices.data_ptr(), self.g.data_ptr()
+        a.M = self.n_out
+        return a
+
+    def update(self, src: "ShardedCsr16Half") -> None:
+        kappa = self.coef * self.rho_max ** 2
+        if choose_slices(None, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
+            self.slices_used.append(0)                              # 0 = float64 update
+            self._err_next = kappa * src.err
+            super().update(src)
+            self.version += 1
+            return
+        self.slices_used.append(2)
+        self._err_next = kappa * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff)
+        self.scal.zero_()
+        lib = _lib.load()
+        P, per_in, per_out = self.world, src.per, self.per
+        if self._send16 is None or self._send16.shape != (P, per_in, per_out):
+            self._send16 = torch.zeros((P, per_in, per_out), dtype=torch.int16, device=self.device)
+            self._recv16 = torch.zeros((P, per_in, per_out), dtype=torch.int16, device=self.device)
+        guard = 1.0 + 2.0 ** -14
+        bound_mul = src.maxoff * guard                              # U[i, :] <= deg_i * max(S_off)
+
+        def first():
+            if src.rows == 0:
+                return
+            xq, unit = src._quantized()
+            for p in range(P):
+                lo, hi = self.plan.start(p), self.plan.stop(p)
+                if hi <= lo:
+                    continue
+                a = self._args(_lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST)
+                a.row_begin, a.row_end = lo, hi
+                a.X, a.ldx, a.L, a.K = xq.data_ptr(), src.ldxt, src.rows, self.n_in
+                a.OUT, a.ldo = self._send16[p].data_ptr() - 2 * lo, per_out      # column i lands at i - lo
+                a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
+                a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), bound_mul, 0.0)
+                _lib.check(lib.srk_csr_half(C.byref(a), _stream()), "srk_csr_half(u16, first)")
+        self._timed("csr16_half_first", first)
+        self._timed("exchange", lambda: _all_to_all(self._recv16, self._send16, self.group))
+
+        def second():
+            if self.rows == 0:
+                return
+            b = self._args(_lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
+            b.row_begin, b.row_end = 0, self.n_out
+            b.X, b.ldx, b.L, b.K = self._recv16.data_ptr(), per_out, self.rows, P * per_in
+            b.OUT, b.ldo = self.S.data_ptr(), self.ld
+            b.in_unit = _lib.RowBound.of(self.deg_dev.data_ptr() + 8 * self.row0, bound_mul / 65535.0, 0.0)
+            b.g_col = self.g.data_ptr() + 8 * self.row0
+            esz = self.counts.element_size()
+            b.counts, b.ld_counts, b.counts_bits, b.add_counts = self.counts.data_ptr(), self.counts.stride(0), 8 * esz, 1
+            b.use_evidence = 1 if self.evidence_from_pattern else 0
+            e = b.epi
+            e.coef = self.coef
+            if self.evidence is not None and not self.evidence_from_pattern:
+                e.evidence, e.ld_evidence = self.evidence.data_ptr(), self.evidence.stride(0)
+            e.s_old, e.ld_s_old = self.S.data_ptr(), self.ld
+            e.maxdiff, e.maxoff = self.scal.data_ptr(), self.scal.data_ptr() + 8
+            e.diag_offset = self.row0
+            _lib.check(lib.srk_csr_half(C.byref(b), _stream()), "srk_csr_half(u16, second)")
+        self._timed("csr16_half_final", second)
+        self.version += 1
 
 
 def _sharded_mode(mode, *ops, coefs=None, lbds=None, has_prior=False) -> str:
@@ -528,7 +812,7 @@ def _sharded_mode(mode, *ops, coefs=None, lbds=None, has_prior=False) -> str:
     non-contracting problems on the float64 path."""
     from .engine import choose_mode
     mode = (mode or "auto").lower()
-    if mode not in ("auto", "i8", "csr"):
+    if mode not in ("auto", "i8", "csr", "csr16"):
         raise ValueError(f"unknown mode {mode!r} for the row-sharded solver")
     coefs = coefs or (0.8,) * len(ops)
     lbds = lbds or (0.0,) * len(ops)
@@ -537,9 +821,9 @@ def _sharded_mode(mode, *ops, coefs=None, lbds=None, has_prior=False) -> str:
     else:            # CPU emulation of the host logic (tests/test_dist_gloo.py): no device to ask
         from .engine import fixed_point_obstacle
         bad = [fixed_point_obstacle(op, c, l, has_prior) for op, c, l in zip(ops, coefs, lbds)]
-        if mode == "i8" and any(bad):
-            raise ValueError(f"mode='i8' {next(b for b in bad if b)}; use mode='csr' (float64)")
-        picks = {"csr" if (mode == "csr" or b) else "i8" for b in bad}
+        if mode in ("i8", "csr16") and any(bad):
+            raise ValueError(f"mode={mode!r} {next(b for b in bad if b)}; use mode='csr' (float64)")
+        picks = {mode if mode in ("csr", "csr16") else ("csr" if b else "i8") for b in bad}
     return picks.pop() if len(picks) == 1 else "csr"
 
 
@@ -548,12 +832,16 @@ class ShardedDirectedSolver:
 
     half_cls = ShardedHalf
     csr_half_cls = ShardedCsrHalf
+    csr16_half_cls = ShardedCsr16Half
 
     def __init__(self, op: HostOperator, C_, evidence=None, prior=None, lbd=0.0, mode="i8", ns=None, device=None,
                  group=None, evidence_from_pattern=False):
         rank, world = _rank_world(group)
-        self.mode = _sharded_mode(mode, op)
-        if self.mode == "csr":
+        self.mode = _sharded_mode(mode, op, coefs=(C_,), lbds=(lbd,), has_prior=prior is not None)
+        if self.mode == "csr16":
+            self.half = self.csr16_half_cls(op, C_, rank, world, device, evidence, prior, lbd, group,
+                                            evidence_from_pattern)
+        elif self.mode == "csr":
             if evidence_from_pattern:
                 raise ValueError("the CSR path takes evidence counts, not the pattern flag")
             self.half = self.csr_half_cls(op, C_, rank, world, device, evidence, prior, lbd, group)
@@ -576,12 +864,21 @@ class ShardedBipartiteSolver:
 
     half_cls = ShardedHalf
     csr_half_cls = ShardedCsrHalf
+    csr16_half_cls = ShardedCsr16Half
 
     def __init__(self, op12: HostOperator, op21: HostOperator, C1, C2, evidence1=None, evidence2=None, prior1=None,
                  prior2=None, lbd1=0.0, lbd2=0.0, mode="i8", ns=None, device=None, group=None,
                  evidence1_from_pattern=False, evidence2_from_pattern=False):
         rank, world = _rank_world(group)
-        self.mode = _sharded_mode(mode, op12, op21)
+        self.mode = _sharded_mode(mode, op12, op21, coefs=(C1, C2), lbds=(lbd1, lbd2),
+                                  has_prior=prior1 is not None or prior2 is not None)
+        if self.mode == "csr16":
+            self.h1 = self.csr16_half_cls(op12, C1, rank, world, device, evidence1, prior1, lbd1, group,
+                                          evidence1_from_pattern)
+            self.h2 = self.csr16_half_cls(op21, C2, rank, world, device, evidence2, prior2, lbd2, group,
+                                          evidence2_from_pattern)
+            self.halves = [self.h1, self.h2]
+            return
         if self.mode == "csr":
             if evidence1_from_pattern or evidence2_from_pattern:
                 raise ValueError("the CSR path takes evidence counts, not the pattern flag")

@@ -115,14 +115,23 @@ def _world(sharded=None):
     torch.distributed is initialised with more than one rank -- every rank must then call ``fit``
     with the same arguments (it is a collective: S is row-sharded over the ranks) -- else (0, 1).
     ``sharded=False`` keeps a fit on the calling rank's own GPU whatever the process group;
-    ``sharded=True`` insists on a process group."""
+    ``sharded=True`` insists on a process group; a ``dist.LocalRank`` runs the fit as one of P logical
+    ranks that share one GPU (dist.LocalCluster)."""
     import torch.distributed as dist
+    from .dist import LocalRank
+    if isinstance(sharded, LocalRank):                # a logical rank of a dist.LocalCluster (one GPU)
+        return sharded.rank, sharded.world
     active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     if sharded is False or (sharded is None and not active):
         return 0, 1
     if not active:
         raise RuntimeError("sharded=True needs an initialised torch.distributed process group with world size > 1")
     return dist.get_rank(), dist.get_world_size()
+
+
+def _group_of(sharded):
+    from .dist import LocalRank
+    return sharded if isinstance(sharded, LocalRank) else None
 
 
 def _local_rows(t, n, rank, world):
@@ -156,7 +165,8 @@ def directed_solver(op: HostOperator, C, evidence=None, prior=None, lbd=0.0, mod
         ev, from_pattern = _evidence_args(evidence, op, smode)
         return _sd.ShardedDirectedSolver(op, C, _local_rows(ev, op.M, rank, world),
                                          _local_rows(pr, op.M, rank, world), lbd, smode,
-                                         slices, dop.device, evidence_from_pattern=from_pattern)
+                                         slices, dop.device, group=_group_of(sharded),
+                                         evidence_from_pattern=from_pattern)
     mode = _eng.choose_mode(op, _mode_with_prior(mode, prior), C, lbd, prior is not None)
     ev, from_pattern = _evidence_args(evidence, op, mode)
     return _eng.DirectedSolver(dop, C, ev, pr, lbd, mode, slices,
@@ -179,7 +189,7 @@ def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=N
         return _sd.ShardedBipartiteSolver(op12, op21, C1, C2, _local_rows(e1, op12.M, rank, world),
                                           _local_rows(e2, op21.M, rank, world), _local_rows(p1, op12.M, rank, world),
                                           _local_rows(p2, op21.M, rank, world), lbd1, lbd2,
-                                          smode, slices, d12.device,
+                                          smode, slices, d12.device, group=_group_of(sharded),
                                           evidence1_from_pattern=pat1, evidence2_from_pattern=pat2)
     mode = _mode_with_prior(mode, prior1, prior2)
     m1 = _eng.choose_mode(op12, mode, C1, lbd1, prior1 is not None)

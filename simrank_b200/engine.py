@@ -287,8 +287,7 @@ class _Half:
         self.slices_used = []                                              # NS of every update (i8 mode)
         self.err = 0.0              # guaranteed max-abs deviation of S from the float64 iteration (i8 mode)
         if mode == "csr":
-            self.ldt = _round_up(max(self.n_out, 1), 16)
-            self.T = torch.empty((self.n_in, self.ldt), dtype=torch.float64, device=dev)
+            self.T = None                                                  # allocated by the first update
             return
         host = op.host
         if mode == "csr16":
@@ -369,22 +368,7 @@ class _Half:
         lib = _lib.load()
         self.scal.zero_()
         if self.mode == "csr":
-            op = self.op
-            _lib.check(self._timed("csr_half_first", lambda: lib.srk_csr_half_f64(
-                _ptr(op.indptr), _ptr(op.indices), _ptr(op.g), op.M, 0, op.M, _ptr(src.S), src.ld, self.n_in,
-                _ptr(self.T), self.ldt, None, _stream())), "srk_csr_half_f64(first)")
-            b = _lib.CsrArgs()
-            b.elem, b.mode = _lib.SRK_ELEM_F64, _lib.SRK_CSR_FINAL
-            # without a prior the result is symmetric: each unordered pair is computed once and mirrored
-            b.symmetric = 1 if self.prior is None and os.environ.get("SIMRANK_B200_CSR_SYMMETRIC", "1") != "0" else 0
-            b.indptr, b.indices, b.g = op.indptr.data_ptr(), op.indices.data_ptr(), op.g.data_ptr()
-            b.M, b.row_begin, b.row_end = op.M, 0, op.M
-            b.X, b.ldx, b.L = self.T.data_ptr(), self.ldt, self.n_out
-            b.OUT, b.ldo = self.S.data_ptr(), self.ld
-            b.epi = self._epilogue()
-            _lib.check(self._timed("csr_half_final", lambda: lib.srk_csr_half(C.byref(b), _stream())),
-                       "srk_csr_half(f64, second)")
-            return
+            return self._update_f64(src)
         if self.mode == "csr16":
             return self._update_csr16(src)
         # ---- paired-SM tensor-core path
@@ -435,6 +419,36 @@ class _Half:
                    "srk_x2_half(FINAL)")
         self.version += 1
 
+    def _update_f64(self, src: "_Half") -> None:
+        """Float64 CSR update: T = (G S_in)^T, then S = epilogue((G T)^T)."""
+        lib, op = _lib.load(), self.op
+        if getattr(self, "T", None) is None:
+            self.ldt64 = _round_up(max(self.n_out, 1), 16)
+            self.T = torch.empty((self.n_in, self.ldt64), dtype=torch.float64, device=self.S.device)
+        a = _lib.CsrArgs()
+        a.elem, a.mode = _lib.SRK_ELEM_F64, _lib.SRK_CSR_FIRST
+        a.indptr, a.indices, a.g = op.indptr.data_ptr(), op.indices.data_ptr(), op.g.data_ptr()
+        a.M, a.row_begin, a.row_end = op.M, 0, op.M
+        a.X, a.ldx, a.L, a.K = src.S.data_ptr(), src.ld, self.n_in, self.n_in
+        a.OUT, a.ldo = self.T.data_ptr(), self.ldt64
+        _lib.check(self._timed("csr_half_first", lambda: lib.srk_csr_half(C.byref(a), _stream())),
+                   "srk_csr_half(f64, first)")
+        b = _lib.CsrArgs()
+        b.elem, b.mode = _lib.SRK_ELEM_F64, _lib.SRK_CSR_FINAL
+        # without a prior the result is symmetric: each unordered pair is computed once and mirrored
+        b.symmetric = 1 if self.prior is None and os.environ.get("SIMRANK_B200_CSR_SYMMETRIC", "1") != "0" else 0
+        b.indptr, b.indices, b.g = op.indptr.data_ptr(), op.indices.data_ptr(), op.g.data_ptr()
+        b.M, b.row_begin, b.row_end = op.M, 0, op.M
+        b.X, b.ldx, b.L, b.K = self.T.data_ptr(), self.ldt64, self.n_out, self.n_in
+        b.OUT, b.ldo = self.S.data_ptr(), self.ld
+        if getattr(self, "evidence_from_pattern", False):          # a float64 update of the csr16 mode
+            b.counts, b.ld_counts = self.counts.data_ptr(), self.counts.stride(0)
+            b.counts_bits, b.use_evidence = 8 * self.counts.element_size(), 1
+        b.epi = self._epilogue()
+        _lib.check(self._timed("csr_half_final", lambda: lib.srk_csr_half(C.byref(b), _stream())),
+                   "srk_csr_half(f64, second)")
+        self.version = getattr(self, "version", 0) + 1
+
     def _quantized(self):
         """uint16 source operand of the CURRENT S for the fixed-point gather (cached per version of S):
         Xq[k, r] = rint(S_off[r, k] / unit[r]), unit[r] = row maximum / 65535."""
@@ -451,17 +465,24 @@ class _Half:
     def _update_csr16(self, src: "_Half") -> None:
         """Fixed-point CSR path: the two gathers sum uint16 values as exact integers."""
         lib, op = _lib.load(), self.op
-        # same two roundings as the tensor-core path with 2 planes (bounds: exact row maximum of S_off,
-        # deg * max(S_off) for U -- not even rounded up to a power of two here)
+        # Same two roundings as the tensor-core path with 2 planes (bounds: exact row maximum of S_off,
+        # deg * max(S_off) for U -- not even rounded up to a power of two here).  When 16 bits cannot
+        # keep the guaranteed deviation inside ERR_BUDGET (large similarities, C close to 1) THIS update
+        # runs in float64: both kinds of update read and write the same float64 S.
+        kappa = self.coef * self.rho_max ** 2
+        if choose_slices(self.ns, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
+            self.slices_used.append(0)                                     # 0 = float64 update
+            self._err_next = kappa * src.err
+            return self._update_f64(src)                                   # bumps self.version
         self.slices_used.append(2)
-        self._err_next = self.coef * self.rho_max ** 2 * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff)
+        self._err_next = kappa * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff)
         xq, unit = src._quantized()
         guard = 1.0 + 2.0 ** -14
         a = _lib.CsrArgs()
         a.elem, a.mode = _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST
         a.indptr, a.indices, a.g = op.indptr.data_ptr(), op.indices.data_ptr(), op.g.data_ptr()
         a.M, a.row_begin, a.row_end = op.M, 0, op.M
-        a.X, a.ldx, a.L = xq.data_ptr(), src.ldxt, self.n_in
+        a.X, a.ldx, a.L, a.K = xq.data_ptr(), src.ldxt, self.n_in, self.n_in
         a.OUT, a.ldo = self.Tq.data_ptr(), self.ldt
         a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
         a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard, 0.0)
@@ -471,7 +492,7 @@ class _Half:
         b.elem, b.mode, b.symmetric = _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL, 1
         b.indptr, b.indices, b.g = a.indptr, a.indices, a.g
         b.M, b.row_begin, b.row_end = op.M, 0, op.M
-        b.X, b.ldx, b.L = self.Tq.data_ptr(), self.ldt, self.n_out
+        b.X, b.ldx, b.L, b.K = self.Tq.data_ptr(), self.ldt, self.n_out, self.n_in
         b.OUT, b.ldo = self.S.data_ptr(), self.ld
         b.in_unit = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard / 65535.0, 0.0)
         b.g_col = op.g.data_ptr()

@@ -47,11 +47,24 @@ def main():
     S1, S2 = M.BipartitleSimRankPP(mode="csr").fit(df, weighted=True, iterations=3, eps=0.0, verbose=False)
     assert list(S1.index) == l1 and list(S2.index) == l2
     worst = max(worst, float(np.abs(S1.to_numpy() - S1o).max()), float(np.abs(S2.to_numpy() - S2o).max()))
-    t = torch.tensor([worst], device="cuda", dtype=torch.float64)
+    # the same solver with the gathers in uint16 fixed point (mode="csr16"): 1e-6 bound
+    worst16 = 0.0
+    df = synth.directed_frame(1000, 20000, 0.8, 21)
+    nodes, So, ko, co = orc.fit_directed(df, iterations=50, eps=1e-4)
+    obj = M.SimRank(mode="csr16")
+    S = obj.fit(df, iterations=50, eps=1e-4, verbose=False)
+    assert obj.fit_info_.mode == "csr16" and (obj.fit_info_.applied, obj.fit_info_.converged) == (ko, co)
+    worst16 = max(worst16, float(np.abs(S.to_numpy() - So).max()))
+    df = synth.config_frame("cfg5", scale=1 / 32)
+    l1, l2, S1o, S2o, _, _ = orc.fit_bipartite(df, kind="simrank_pp", weighted=True, iterations=3, eps=0.0)
+    S1, S2 = M.BipartitleSimRankPP(mode="csr16").fit(df, weighted=True, iterations=3, eps=0.0, verbose=False)
+    worst16 = max(worst16, float(np.abs(S1.to_numpy() - S1o).max()), float(np.abs(S2.to_numpy() - S2o).max()))
+    t = torch.tensor([worst, worst16], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"DIST_CSR_OK world={world} max_abs_err={t.item():.3e}")
-    assert t.item() <= 1e-12, t.item()
+        print(f"DIST_CSR_OK world={world} max_abs_err={t[0].item():.3e} csr16_max_abs_err={t[1].item():.3e}")
+    assert t[0].item() <= 1e-12, t[0].item()
+    assert t[1].item() <= 1e-6, t[1].item()
     dist.barrier()
     dist.destroy_process_group()
 

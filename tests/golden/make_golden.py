@@ -257,6 +257,33 @@ def reference_fixtures():
                            "sorted1": np.array(sorted(df["user"].unique())),
                            "sorted2": np.array(sorted(df["item"].unique())),
                            "ref_labels1": np.array(list(S1.index)), "ref_labels2": np.array(list(S2.index))}, k))
+        # ---- bipartite SimRank++ with priors (SimRank.py:457-493): 100 % reference code.  Priors are
+        # given positionally in the label-sorted (pivot) order of the matrices they are added to.
+        for name, n, m, sym, kw in [
+            ("bip_apriori_sq_w", 14, 60, True, dict(weighted=True, iterations=8, eps=0.0, lbd1=0.3, lbd2=0.6)),
+            ("bip_apriori_sq_unw", 11, 45, False, dict(weighted=False, iterations=100, eps=1e-4, C1=0.7, C2=0.9)),
+        ]:
+            df = _rand_bipartite(rng, n, n, m)
+            p1, p2 = rng.random((n, n)), rng.random((n, n))
+            if sym:
+                p1, p2 = (p1 + p1.T) / 2, (p2 + p2.T) / 2
+            obj = ref.BipartitleAprioriSimRank()
+            (S1, S2), k, _ = _capture(lambda: obj.fit(df, p1, p2, verbose=True, **kw))
+            cases.append((name, "bipartite", "BipartitleAprioriSimRank", df, kw,
+                          {"S1": S1.values, "S2": S2.values, "prior1": p1, "prior2": p2,
+                           "sorted1": np.array(sorted(df["user"].unique())),
+                           "sorted2": np.array(sorted(df["item"].unique())),
+                           "ref_labels1": np.array(list(S1.index)), "ref_labels2": np.array(list(S2.index))}, k))
+        # n1 != n2 raises for the Apriori variant too (Evidence_N1 in the group-2 update, SimRank.py:491)
+        df = _rand_bipartite(rng, 9, 13, 40)
+        try:
+            _capture(lambda: ref.BipartitleAprioriSimRank().fit(df, rng.random((9, 9)), rng.random((13, 13)),
+                                                                verbose=False))
+            raised_apriori = ""
+        except ValueError as e:
+            raised_apriori = str(e)
+        assert "broadcast" in raised_apriori
+
         # n1 != n2: the reference raises (SimRank.py:423) -- recorded as a fact
         df = _rand_bipartite(rng, 9, 13, 40)
         try:
@@ -273,6 +300,7 @@ def reference_fixtures():
         index[name] = {"family": family, "class": cls, "kwargs": kw, "converged_at": k,
                        "columns": list(df.columns)}
     index["_bipartite_pp_rectangular_raises"] = raised
+    index["_bipartite_apriori_rectangular_raises"] = raised_apriori
     return index
 
 
@@ -281,4 +309,4 @@ if __name__ == "__main__":
     json.dump(nb, open(os.path.join(HERE, "notebook_outputs.json"), "w"), indent=1)
     idx = reference_fixtures()
     json.dump(idx, open(os.path.join(HERE, "ref_index.json"), "w"), indent=1)
-    print("wrote", len(nb), "notebook entries and", len(idx) - 1, "reference cases")
+    print("wrote", len(nb), "notebook entries and", len([k for k in idx if not k.startswith("_")]), "reference cases")

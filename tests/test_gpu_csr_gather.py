@@ -85,6 +85,7 @@ def test_csr16_first_half(dev, M, K, L, density, aligned):
     out = torch.full((L, ldo), -1, dtype=torch.int16, device=dev)
     a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST)
     a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), ldx, L, out.data_ptr(), ldo
+    a.K = K if M % 2 else 0                                # rows of X given / not given (TMA bounds check)
     a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
     a.out_bound = _lib.RowBound.of(od.data_ptr(), 2.0, 0.0)
     _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
@@ -134,7 +135,7 @@ def test_csr16_final_transposed(dev, n, density, evidence):
     ud, gd = torch.from_numpy(unit[r0:r0 + L].copy()).to(dev), torch.from_numpy(gcol[r0:r0 + L].copy()).to(dev)
     scal = torch.zeros(2, dtype=torch.float64, device=dev)
     a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
-    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), ldx, L, out.data_ptr(), ld
+    a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), ldx, L, n, out.data_ptr(), ld
     a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
     a.g_col = gd.data_ptr()
     a.counts, a.ld_counts, a.counts_bits, a.add_counts, a.use_evidence = c16.data_ptr(), n, 16, 1, int(evidence)
@@ -171,7 +172,7 @@ def test_csr16_final_symmetric(dev, n, density, evidence):
     scal = torch.zeros(2, dtype=torch.float64, device=dev)
     a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
     a.symmetric = 1
-    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), ldt, n, out.data_ptr(), ld
+    a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), ldt, n, n, out.data_ptr(), ld
     a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
     a.g_col = gd.data_ptr()
     a.counts, a.ld_counts, a.counts_bits, a.add_counts, a.use_evidence = c16.data_ptr(), n, 16, 1, int(evidence)
@@ -214,7 +215,7 @@ def test_csr_f64_final_symmetric_matches_the_full_product(dev, n, density):
     scal = torch.zeros(2, dtype=torch.float64, device=dev)
     a = _args(dop, _lib.SRK_ELEM_F64, _lib.SRK_CSR_FINAL)
     a.symmetric = 1
-    a.X, a.ldx, a.L, a.OUT, a.ldo = Td.data_ptr(), ld, n, out.data_ptr(), ld
+    a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = Td.data_ptr(), ld, n, n, out.data_ptr(), ld
     a.epi.coef = 0.6
     a.epi.evidence, a.epi.ld_evidence = evd.data_ptr(), ld
     a.epi.s_old, a.epi.ld_s_old = out.data_ptr(), ld

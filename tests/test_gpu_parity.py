@@ -99,12 +99,19 @@ def test_reference_loop_fixtures(mode, name):
         np.testing.assert_allclose(_aligned(S, labels), arr["S"], rtol=0, atol=TOL[mode])
         assert np.all(np.diag(S.to_numpy()) == 1.0)
     else:
+        args = ()
+        if meta["class"] == "BipartitleAprioriSimRank":
+            if mode == "csr16":
+                with pytest.raises(ValueError, match="prior"):
+                    cls(mode=mode).fit(df, arr["prior1"], arr["prior2"], verbose=False, **kw)
+                return
+            args = (arr["prior1"], arr["prior2"])          # positional in sorted-label order (SimRank.py:488,491)
         obj = cls(mode=mode)
-        S1, S2 = obj.fit(df, verbose=False, **kw)
+        S1, S2 = obj.fit(df, *args, verbose=False, **kw)
         assert list(S1.index) == arr["sorted1"].tolist() and list(S2.index) == arr["sorted2"].tolist()
         np.testing.assert_allclose(S1.to_numpy(), arr["S1"], rtol=0, atol=TOL[mode])
         np.testing.assert_allclose(S2.to_numpy(), arr["S2"], rtol=0, atol=TOL[mode])
-        ref = cls(mode=mode, label_order="reference").fit(df, verbose=False, **kw)
+        ref = cls(mode=mode, label_order="reference").fit(df, *args, verbose=False, **kw)
         assert set(ref[0].index) == set(S1.index)
         np.testing.assert_array_equal(ref[0].to_numpy(), S1.to_numpy())
     info = obj.fit_info_
