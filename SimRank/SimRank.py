@@ -29,7 +29,8 @@ class _Base(object):
     """Engine options shared by every class.  All arguments are optional so that the
     reference's ``Cls()`` construction keeps working.
 
-    mode   : None/'auto' | 'csr' (float64 gather path) | 'i8' (tcgen05 fixed-point path)
+    mode   : None/'auto' | 'csr' (float64 gather path) | 'csr16' (uint16 fixed-point gather path) |
+             'i8' (tcgen05 fixed-point dense path); 'auto' picks by size and density
     device : CUDA device (default: current)
     slices : uint8 planes per matrix in i8 mode: 2, 3, 4 or None/'auto' = the fewest planes whose
              guaranteed error bound stays below 5e-7 (simrank_b200.engine.choose_slices)

@@ -144,9 +144,11 @@ int srk_csr_half(const srk_csr_args* args, void* stream);
  * zero_diag_offset) excluded and stored as 0; negatives and NaN as 0), XT[k, r] = rint(V[r, k] /
  * unit[r]) -- the TRANSPOSED matrix [K x ldxt] with one scale per column r.  For the symmetric S of
  * SimRank this is S_off itself with column scales; for a row shard (R local rows) it is the column
- * block the first half gathers from.  Columns R..ldxt-1 are zero-filled.                        */
+ * block the first half gathers from.  Columns R..ldxt-1 are zero-filled.  symmetric != 0: the caller
+ * guarantees V == V^T bit for bit (R == K; what the symmetric second half leaves behind), and
+ * XT[k, r] is read as V[k, r]: the same result in one streaming pass without the transposition.  */
 int srk_quantize_rows_u16(const double* V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
-                          uint16_t* XT, int64_t ldxt, double* unit, void* stream);
+                          uint16_t* XT, int64_t ldxt, double* unit, int symmetric, void* stream);
 
 /* Common-in-neighbour counts cnt[i,j] = |N(i) & N(j)| clipped to 255, for rows
  * [row_begin,row_end) x all j < M: `np.dot((G>0).astype(int), (G>0).T.astype(int))`
@@ -165,6 +167,19 @@ int srk_csr_row_spread(const int64_t* indptr, const double* vals, const double* 
  * 0..), zero-filling the rest; replaces the pivot + row scatter of SimRank.py:50-52.          */
 int srk_csr_to_dense_u8(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
                         int64_t row_end, int64_t K, uint8_t* A8, int64_t lda, void* stream);
+
+/* Edge list -> CSR on the device: what `pivot(index=to, columns=from)` + the row scatter build
+ * (SimRank.py:50-52, 199-200), without the dense matrix.  rows / cols are int32 positions of the
+ * edge endpoints in the node order the host derived (set order / sorted labels stay host logic),
+ * m edges, M rows, K columns.  indptr[M+1] and indices[m] (columns increasing inside each row) are
+ * written; *status (device int32) receives bit 0 when a (row, column) pair occurs twice -- the
+ * reference's pivot raises "Index contains duplicate entries, cannot reshape" -- and bit 1 when an
+ * index is out of range.  workspace: srk_edges_to_csr_workspace(m, M) bytes of device memory.
+ * K <= 819200 (a row's columns are sorted through a K-bit bitmap in shared memory).              */
+size_t srk_edges_to_csr_workspace(int64_t m, int64_t M);
+int srk_edges_to_csr(const int32_t* rows, const int32_t* cols, int64_t m, int64_t M, int64_t K,
+                     int64_t* indptr, int32_t* indices, int32_t* status,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ----------------------------------------------------------------------------- tensor-core path */
 /* Quantise rows [0,R) of a f64 matrix into planes (round to nearest, clip to 256^NS-1).

@@ -88,7 +88,9 @@ SYMBOLS = {
     "srk_device_cc": (_INT, []),
     "srk_csr_half_f64": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, C.POINTER(Epilogue), _P]),
     "srk_csr_half": (_INT, [C.POINTER(CsrArgs), _P]),
-    "srk_quantize_rows_u16": (_INT, [_P, _I64, _I64, _I64, _I64, _P, _I64, _P, _P]),
+    "srk_quantize_rows_u16": (_INT, [_P, _I64, _I64, _I64, _I64, _P, _I64, _P, _INT, _P]),
+    "srk_edges_to_csr_workspace": (C.c_size_t, [_I64, _I64]),
+    "srk_edges_to_csr": (_INT, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, C.c_size_t, _P]),
     "srk_csr_evidence_counts": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P]),
     "srk_csr_row_spread": (_INT, [_P, _P, _P, _I64, _P, _P]),
     "srk_csr_to_dense_u8": (_INT, [_P, _P, _I64, _I64, _I64, _P, _I64, _P]),
@@ -123,7 +125,7 @@ def load():
     return lib
 
 
-LAUNCHES = 0      # successful library calls so far; every one of them enqueues exactly one kernel
+LAUNCHES = 0      # successful library calls so far; every one of them enqueues at least one kernel
 
 
 def check(rc: int, what: str = ""):

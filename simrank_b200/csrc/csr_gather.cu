@@ -114,6 +114,7 @@ struct Params {
   int tma;                     // rows of X are 16-byte aligned: TMA gather; else plain loads
   int vec_aligned;             // OUT, S_old and counts are 16-byte aligned (vector epilogue of the symmetric half)
   int flags;                   // SRK_CSR_FLAGS (A/B profiling): 1 = default L2 policy for the gather
+  int64_t tiles_x;             // row tiles of the problem (symmetric second half: triangular 1-D grid)
 };
 
 __device__ __forceinline__ uint32_t load_count(const void* base, int64_t idx, int c32) {
@@ -241,9 +242,25 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   TileT* tile = reinterpret_cast<TileT*>(smem + SM::kRing + SM::kBars + SM::kFac);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t i0 = p.row_begin + (int64_t)blockIdx.x * TI;
-  const int64_t c0 = (int64_t)blockIdx.y * TC;
-  if (MODE == MODE_FINAL_SYM && c0 + TC - 1 < i0) return;      // every element has c < i: mirrored from above
+  int64_t bx = blockIdx.x, by = blockIdx.y;
+  if (MODE == MODE_FINAL_SYM) {
+    // 1-D grid over the tiles that contain an element c >= i: panel y needs the row tiles
+    // x < min(tiles_x, (y + 1) * TC / TI); tiles are numbered panel by panel
+    constexpr int64_t kPer = TC / TI;                           // row tiles added per panel
+    const int64_t t = blockIdx.x, full = p.tiles_x / kPer;      // panels before the count saturates at tiles_x
+    const int64_t tri = kPer * full * (full + 1) / 2;           // tiles in panels 0 .. full - 1
+    if (t < tri) {
+      by = (int64_t)((sqrt(1.0 + 8.0 * (double)t / (double)kPer) - 1.0) * 0.5);
+      while (kPer * by * (by + 1) / 2 > t) --by;
+      while (kPer * (by + 1) * (by + 2) / 2 <= t) ++by;
+      bx = t - kPer * by * (by + 1) / 2;
+    } else {
+      by = full + (t - tri) / p.tiles_x;
+      bx = (t - tri) % p.tiles_x;
+    }
+  }
+  const int64_t i0 = p.row_begin + bx * TI;
+  const int64_t c0 = by * TC;
   const int rows_here = (int)min((int64_t)TI, p.row_end - i0);
 
   uint8_t* wring = smem + (size_t)warp * kDepth * SM::kSlot;
@@ -329,6 +346,8 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
           if (c < p.L && c + A::kVec > row) {
             prefetch_l2(p.epi.s_old + row * p.epi.ld_s_old + c);
             if (A::kVec > 4 && c + 4 < p.L) prefetch_l2(p.epi.s_old + row * p.epi.ld_s_old + c + 4);
+            if (p.counts && (lane & 1) == 0)                      // 32 B of counts cover two lanes' columns
+              prefetch_l2(reinterpret_cast<const uint8_t*>(p.counts) + (row * p.ld_counts + c) * (p.counts32 ? 4 : 2));
           }
         }
       }
@@ -586,6 +605,46 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Symmetric V (R == K, bit-exactly symmetric as the symmetric second half leaves it): XT[k, r] =
+// rint(V[r, k] / unit[r]) = rint(V[k, r] / unit[r]) -- a streaming pass, no transposition.
+__global__ void __launch_bounds__(256)
+quantize_sym_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t n, int64_t zero_diag_offset,
+                        const double* __restrict__ unit, uint16_t* __restrict__ XT, int64_t ldxt) {
+  // a warp covers 256 consecutive columns of one row: lane l takes the column pairs 2 l + 64 j, j < 4
+  // (512 B per load instruction, 128 B per store instruction, four independent loads in flight)
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_per_row = (ldxt + 255) / 256;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n * warps_per_row) return;
+  const int64_t k = w / warps_per_row, cbase = (w % warps_per_row) * 256;
+  const bool vec = ((reinterpret_cast<uintptr_t>(V) | (uintptr_t)(ldv * 8)) & 15) == 0;
+  double2 v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t r = cbase + 64 * j + 2 * lane;
+    if (vec && r + 1 < n) v[j] = __ldcs(reinterpret_cast<const double2*>(V + k * ldv + r));
+    else v[j] = make_double2(r < n ? V[k * ldv + r] : 0.0, r + 1 < n ? V[k * ldv + r + 1] : 0.0);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t r = cbase + 64 * j + 2 * lane;
+    if (r >= ldxt) continue;
+    uint32_t out = 0u;
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int64_t rr = r + x;
+      if (rr >= n) continue;
+      const double u = unit[rr];
+      const double val = (zero_diag_offset >= 0 && k == rr + zero_diag_offset) ? 0.0 : (x ? v[j].y : v[j].x);
+      double y = u > 0.0 ? rint(val / u) : 0.0;
+      if (!(y > 0.0)) y = 0.0;
+      if (y > 65535.0) y = 65535.0;
+      out |= (uint32_t)y << (16 * x);
+    }
+    *reinterpret_cast<uint32_t*>(XT + k * ldxt + r) = out;
+  }
+}
+
 template <typename E, int TC, int MODE>
 static int launch_one(Params& p, int64_t x_rows, dim3 grid, cudaStream_t st) {
   typedef Smem<E, TC, MODE> SM;
@@ -666,6 +725,14 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   const int64_t gx = (rows + gat::TI - 1) / gat::TI, gy = (a->L + tc - 1) / tc;
   SRK_REQUIRE(gy <= 65535, "too many column panels");
   dim3 grid((unsigned)gx, (unsigned)gy);
+  p.tiles_x = gx;
+  if (sym) {
+    const int64_t per = tc / gat::TI, full = gx / per;               // see the kernel: triangular numbering
+    int64_t total = per * full * (full + 1) / 2;
+    if (gy > full) total += (gy - full) * gx;
+    SRK_REQUIRE(total < (1ll << 31), "too many tiles");
+    grid = dim3((unsigned)total, 1);
+  }
   if (a->elem == SRK_ELEM_U16) {
     switch (mode) {
       case gat::MODE_FIRST: return gat::launch_one<uint16_t, 512, gat::MODE_FIRST>(p, x_rows, grid, st);
@@ -696,13 +763,21 @@ extern "C" int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, c
 }
 
 extern "C" int srk_quantize_rows_u16(const double* V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
-                                     uint16_t* XT, int64_t ldxt, double* unit, void* stream) {
+                                     uint16_t* XT, int64_t ldxt, double* unit, int symmetric, void* stream) {
   SRK_REQUIRE(V && XT && unit, "null pointer");
   SRK_REQUIRE(ldv >= K && ldxt >= R && ldxt % 8 == 0 && ((uintptr_t)XT % 16) == 0,
               "XT must be 16-byte aligned with ldxt a multiple of 8 and >= R");
+  SRK_REQUIRE(!symmetric || R == K, "a symmetric matrix is square");
   if (R == 0 || K == 0) return SRK_OK;
   cudaStream_t st = (cudaStream_t)stream;
   gat::row_unit_kernel<<<(unsigned)R, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, unit);
+  if (symmetric) {
+    const int64_t threads = K * ((ldxt + 255) / 256) * 32;
+    SRK_REQUIRE((threads + 255) / 256 < (1ll << 31), "matrix too large for one launch");
+    gat::quantize_sym_u16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(V, ldv, K, zero_diag_offset, unit, XT, ldxt);
+    SRK_CUDA_OK(cudaGetLastError());
+    return SRK_OK;
+  }
   dim3 grid((unsigned)((K + gat::QT - 1) / gat::QT), (unsigned)((ldxt + gat::QT - 1) / gat::QT));
   SRK_REQUIRE(grid.y <= 65535, "too many row tiles");
   gat::quantize_transpose_u16_kernel<<<grid, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, unit, XT, ldxt);

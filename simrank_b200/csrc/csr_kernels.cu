@@ -63,6 +63,124 @@ __global__ void row_spread_kernel(const int64_t* __restrict__ indptr, const doub
 }
 
 // ------------------------------------------------------------------------------------------
+// Edge list -> CSR on the device (the pivot + row scatter of SimRank.py:50-52, 199-200):
+//   1. degree histogram (one atomicAdd per edge)                          edge_degree_kernel
+//   2. exclusive scan of the degrees -> indptr (three small kernels)      scan_*_kernel
+//   3. scatter of the column indices into their row, in arrival order     edge_scatter_kernel
+//   4. per row: a K-bit bitmap in shared memory is set from the row's columns (a bit that is already
+//      set is a duplicate (row, column) pair: the reference's pivot raises on those), its popcount
+//      prefix gives every set bit its rank, and the columns are written back in increasing order --
+//      a counting sort that needs no comparison and does not care how long the row is.
+constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 4;
+__global__ void edge_degree_kernel(const int32_t* __restrict__ rows, int64_t m, int64_t M, int32_t* __restrict__ deg,
+                                   int32_t* __restrict__ bad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  const int32_t r = rows[e];
+  if (r < 0 || r >= M) { atomicOr(bad, 2); return; }
+  atomicAdd(deg + r, 1);
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_blocks_kernel(const int32_t* __restrict__ deg, int64_t M, int64_t* __restrict__ indptr, int64_t* __restrict__ block_sum) {
+  __shared__ int64_t warp_tot[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
+  int64_t v[SCAN_ITEMS], run = 0;
+#pragma unroll
+  for (int x = 0; x < SCAN_ITEMS; ++x) { v[x] = run; run += base + x < M ? (int64_t)deg[base + x] : 0; }
+  int64_t inc = run;                                         // inclusive scan of the thread totals over the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int64_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int64_t w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int64_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    warp_tot[lane] = w;                                       // inclusive over the warps
+  }
+  __syncthreads();
+  const int64_t before = (warp ? warp_tot[warp - 1] : 0) + inc - run;
+#pragma unroll
+  for (int x = 0; x < SCAN_ITEMS; ++x)
+    if (base + x < M) indptr[base + x] = before + v[x];      // block-local exclusive prefix
+  if (threadIdx.x == SCAN_THREADS - 1) block_sum[blockIdx.x] = warp_tot[SCAN_THREADS / 32 - 1];
+}
+__global__ void scan_sums_kernel(int64_t* __restrict__ block_sum, int64_t blocks) {   // one thread: a few thousand adds
+  if (blockIdx.x || threadIdx.x) return;
+  int64_t run = 0;
+  for (int64_t b = 0; b < blocks; ++b) { const int64_t t = block_sum[b]; block_sum[b] = run; run += t; }
+}
+__global__ void scan_add_kernel(int64_t* __restrict__ indptr, int64_t M, int64_t m, const int64_t* __restrict__ block_sum) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) indptr[i] += block_sum[i / (SCAN_THREADS * SCAN_ITEMS)];
+  if (i == M) indptr[M] = m;
+}
+__global__ void edge_scatter_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int64_t m, int64_t M,
+                                    int64_t K, const int64_t* __restrict__ indptr, int32_t* __restrict__ cursor,
+                                    int32_t* __restrict__ tmp, int32_t* __restrict__ bad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m) return;
+  const int32_t r = rows[e], c = cols[e];
+  if (r < 0 || r >= M) return;
+  if (c < 0 || c >= K) { atomicOr(bad, 2); return; }
+  tmp[indptr[r] + atomicAdd(cursor + r, 1)] = c;
+}
+constexpr int SORT_THREADS = 256;
+__global__ void __launch_bounds__(SORT_THREADS)
+row_bitmap_sort_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ tmp, int64_t M, int64_t K,
+                       int32_t* __restrict__ indices, int32_t* __restrict__ bad) {
+  extern __shared__ uint32_t bm[];                            // [words] bitmap, then [words] popcount prefix
+  __shared__ uint32_t warp_tot[SORT_THREADS / 32];
+  __shared__ uint32_t carry;
+  const int words = (int)((K + 31) / 32);
+  uint32_t* pre = bm + words;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
+    const int64_t beg = indptr[r], end = indptr[r + 1];
+    if (end - beg <= 1) {                                     // nothing to sort
+      if (end > beg && threadIdx.x == 0) indices[beg] = tmp[beg];
+      continue;
+    }
+    for (int w = threadIdx.x; w < words; w += SORT_THREADS) bm[w] = 0u;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (int64_t e = beg + threadIdx.x; e < end; e += SORT_THREADS) {
+      const int32_t c = tmp[e];
+      const uint32_t bit = 1u << (c & 31);
+      if (atomicOr(&bm[c >> 5], bit) & bit) atomicOr(bad, 1);  // duplicate (row, column) pair
+    }
+    __syncthreads();
+    // exclusive prefix of the word popcounts, SORT_THREADS words per round
+    for (int w0 = 0; w0 < words; w0 += SORT_THREADS) {
+      const int w = w0 + threadIdx.x;
+      const uint32_t cnt = w < words ? __popc(bm[w]) : 0u;
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) warp_tot[warp] = inc;
+      __syncthreads();
+      uint32_t before = carry;
+      for (int x = 0; x < warp; ++x) before += warp_tot[x];
+      if (w < words) pre[w] = before + inc - cnt;
+      __syncthreads();
+      if (threadIdx.x == SORT_THREADS - 1) carry = before + inc;
+      __syncthreads();
+    }
+    for (int w = threadIdx.x; w < words; w += SORT_THREADS) {
+      uint32_t b = bm[w];
+      int64_t o = beg + pre[w];
+      while (b) {
+        const int t = __ffs(b) - 1;
+        indices[o++] = w * 32 + t;
+        b &= b - 1;
+      }
+    }
+    __syncthreads();                                          // bm / pre are reused by the next row
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 __global__ void csr_scatter_u8_kernel(const int64_t* __restrict__ indptr,
                                       const int32_t* __restrict__ indices, int64_t row_begin,
                                       int64_t row_end, int64_t K, uint8_t* __restrict__ A8, int64_t lda) {
@@ -347,6 +465,52 @@ extern "C" int srk_csr_to_dense_u8(const int64_t* indptr, const int32_t* indices
   const int64_t threads = (row_end - row_begin) * 32;
   csr_scatter_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(indptr, indices, row_begin,
                                                                           row_end, K, A8, lda);
+  SRK_CUDA_OK(cudaGetLastError());
+  return SRK_OK;
+}
+
+extern "C" size_t srk_edges_to_csr_workspace(int64_t m, int64_t M) {
+  const size_t blocks = (size_t)((M + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS)) + 1;
+  // degree + cursor (int32 [M] each), arrival-order columns (int32 [m]), block sums (int64), each 256-byte aligned
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  return up((size_t)M * 4) * 2 + up((size_t)m * 4) + up(blocks * 8) + 256;
+}
+
+extern "C" int srk_edges_to_csr(const int32_t* rows, const int32_t* cols, int64_t m, int64_t M, int64_t K,
+                                int64_t* indptr, int32_t* indices, int32_t* status, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  SRK_REQUIRE(indptr && status && (m == 0 || (rows && cols && indices)), "null pointer");
+  SRK_REQUIRE(m >= 0 && M >= 0 && K >= 0 && m < (1ll << 31) && M < (1ll << 31), "shape");
+  SRK_REQUIRE(workspace_bytes >= srk_edges_to_csr_workspace(m, M) && (M == 0 || workspace), "workspace too small");
+  const size_t bitmap_bytes = (size_t)((K + 31) / 32) * 8;
+  SRK_REQUIRE(bitmap_bytes <= 200 * 1024, "too many columns for the shared-memory row bitmap (K <= 819200)");
+  cudaStream_t st = (cudaStream_t)stream;
+  SRK_CUDA_OK(cudaMemsetAsync(status, 0, 4, st));
+  if (M == 0) { SRK_CUDA_OK(cudaMemsetAsync(indptr, 0, 8, st)); return SRK_OK; }
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  int32_t* deg = reinterpret_cast<int32_t*>(ws);
+  int32_t* cursor = reinterpret_cast<int32_t*>(ws + up((size_t)M * 4));
+  int32_t* tmp = reinterpret_cast<int32_t*>(ws + 2 * up((size_t)M * 4));
+  int64_t* block_sum = reinterpret_cast<int64_t*>(ws + 2 * up((size_t)M * 4) + up((size_t)m * 4));
+  SRK_CUDA_OK(cudaMemsetAsync(deg, 0, 2 * up((size_t)M * 4), st));            // degrees and cursors
+  const unsigned eb = (unsigned)((m + 255) / 256);
+  if (m) edge_degree_kernel<<<eb, 256, 0, st>>>(rows, m, M, deg, status);
+  const int64_t blocks = (M + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS);
+  scan_blocks_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(deg, M, indptr, block_sum);
+  scan_sums_kernel<<<1, 32, 0, st>>>(block_sum, blocks);
+  scan_add_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, st>>>(indptr, M, m, block_sum);
+  if (m) {
+    edge_scatter_kernel<<<eb, 256, 0, st>>>(rows, cols, m, M, K, indptr, cursor, tmp, status);
+    int dev = 0, sms = 0;
+    SRK_CUDA_OK(cudaGetDevice(&dev));
+    SRK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SRK_CUDA_OK(cudaFuncSetAttribute(row_bitmap_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bitmap_bytes));
+    const int64_t per_sm = bitmap_bytes ? (int64_t)(200 * 1024 / (bitmap_bytes + 1024)) : 8;
+    int64_t grid = (int64_t)sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+    if (grid > M) grid = M;
+    row_bitmap_sort_kernel<<<(unsigned)grid, SORT_THREADS, bitmap_bytes, st>>>(indptr, tmp, M, K, indices, status);
+  }
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }

@@ -731,7 +731,7 @@ class ShardedCsr16Half(ShardedCsrHalf):
             self.Xq = torch.zeros((self.n_out, self.ldxt), dtype=torch.int16, device=self.device)
         if self._quantized_version != self.version and self.rows:
             _lib.check(_lib.load().srk_quantize_rows_u16(_ptr(self.S), self.ld, self.rows, self.n_out, self.row0,
-                                                         _ptr(self.Xq), self.ldxt, _ptr(self.unit), _stream()),
+                                                         _ptr(self.Xq), self.ldxt, _ptr(self.unit), 0, _stream()),
                        "srk_quantize_rows_u16")
         self._quantized_version = self.version
         return self.Xq, self.unit
@@ -745,7 +745,7 @@ class ShardedCsr16Half(ShardedCsrHalf):
 
     def update(self, src: "ShardedCsr16Half") -> None:
         kappa = self.coef * self.rho_max ** 2
-        if choose_slices(None, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
+        if getattr(self, "force_f64", False) or choose_slices(None, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
             self.slices_used.append(0)                              # 0 = float64 update
             self._err_next = kappa * src.err
             super().update(src)

@@ -7,7 +7,19 @@ import torch
 
 from . import engine as _eng
 from .engine import FitInfo, run_loop  # noqa: F401  (re-exported for SimRank/SimRank.py)
-from .graph import HostOperator, build_bipartite, build_directed  # noqa: F401
+from . import graph as _graph
+from .graph import HostOperator
+
+
+def build_directed(data, weighted, from_node_column, to_node_column, weight_column):
+    """graph.build_directed with the CSR arrays built on the GPU (engine.device_csr)."""
+    return _graph.build_directed(data, weighted, from_node_column, to_node_column, weight_column, csr=_eng.device_csr)
+
+
+def build_bipartite(data, weighted, node_group1_column, node_group2_column, weight_column):
+    """graph.build_bipartite with the CSR arrays built on the GPU (engine.device_csr)."""
+    return _graph.build_bipartite(data, weighted, node_group1_column, node_group2_column, weight_column,
+                                  csr=_eng.device_csr)
 
 
 def _device_op(op: HostOperator, device=None) -> _eng.DeviceOperator:

@@ -77,6 +77,40 @@ def require_cuda(device=None) -> torch.device:
     return torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
 
 
+# --------------------------------------------------------------------------- graph build
+DEVICE_CSR_MIN_EDGES = 32768          # below this the host sort beats a device round trip
+_DEVICE_CSR_MAX_COLUMNS = 819200      # srk_edges_to_csr: K-bit row bitmap in shared memory
+
+
+def device_csr(rows, cols, M, K, device=None):
+    """Edge positions -> CSR on the GPU (srk_edges_to_csr: histogram, scan, scatter, per-row bitmap
+    sort with duplicate detection): the device replacement of the pivot + row scatter of
+    SimRank.py:50-52.  -> (indptr, indices, (device indptr, device indices)) or None when the graph is
+    too small to be worth the round trip (the host sort takes it).  Raises the pivot's ValueError on
+    a duplicate (row, column) pair."""
+    from .graph import _DUPLICATE_MSG
+    m = int(np.asarray(rows).size)
+    if m < DEVICE_CSR_MIN_EDGES or K > _DEVICE_CSR_MAX_COLUMNS or max(M, m) >= (1 << 31) or not torch.cuda.is_available():
+        return None
+    dev = require_cuda(device)
+    lib = _lib.load()
+    r = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int32)).to(dev)
+    c = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).to(dev)
+    indptr = torch.empty(M + 1, dtype=torch.int64, device=dev)
+    indices = torch.empty(m, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = int(lib.srk_edges_to_csr_workspace(m, M))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.srk_edges_to_csr(_ptr(r), _ptr(c), m, M, K, _ptr(indptr), _ptr(indices), _ptr(status), _ptr(ws),
+                                    nbytes, _stream()), "srk_edges_to_csr")
+    st = int(status.item())
+    if st & 2:
+        raise IndexError("edge endpoint outside the node range")
+    if st & 1:
+        raise ValueError(_DUPLICATE_MSG)
+    return indptr.cpu().numpy(), indices.cpu().numpy(), (indptr, indices)
+
+
 # --------------------------------------------------------------------------- operators
 class DeviceOperator:
     """``G = diag(g) * A`` resident on the GPU: CSR always, dense uint8 A on demand."""
@@ -85,8 +119,12 @@ class DeviceOperator:
         self.host = host
         self.M, self.K = host.M, host.K
         self.device = device
-        self.indptr = torch.from_numpy(host.indptr).to(device)
-        self.indices = torch.from_numpy(host.indices).to(device)
+        dev_csr = getattr(host, "dev_csr", None)                  # built on the device already (device_csr)
+        if dev_csr is not None and dev_csr[0].device == torch.device(device):
+            self.indptr, self.indices = dev_csr
+        else:
+            self.indptr = torch.from_numpy(host.indptr).to(device)
+            self.indices = torch.from_numpy(host.indices).to(device)
         self.g_host = np.ascontiguousarray(host.g)
         self.g = torch.from_numpy(self.g_host).to(device)
         self.dead = torch.from_numpy(host.dead).to(device)
@@ -205,9 +243,10 @@ def contraction(op: HostOperator, coef: float, blend: float = 1.0) -> float:
 
 def choose_mode(op: HostOperator, requested: str | None = None, coef: float = 0.8, lbd: float = 0.0,
                 has_prior: bool = False) -> str:
-    """'csr' (exact f64 gather path) or 'i8' (tcgen05 fixed-point path).  An explicit 'i8' that the
-    fixed-point path cannot hold raises; 'auto' sends such problems -- and updates that do not
-    contract (kappa >= 1: the a-priori error bound of choose_slices does not exist) -- to 'csr'."""
+    """'csr' (exact f64 gather), 'csr16' (uint16 fixed-point gather) or 'i8' (tcgen05 fixed-point dense
+    chain).  An explicit fixed-point mode that cannot hold the problem raises; 'auto' sends such
+    problems -- and updates that do not contract (kappa >= 1: the a-priori error bound of
+    choose_slices does not exist) -- to 'csr', and picks between the fixed-point paths by density."""
     mode = (requested or os.environ.get("SIMRANK_B200_MODE", "auto")).lower()
     if mode == "csr":
         return mode
@@ -226,8 +265,18 @@ def choose_mode(op: HostOperator, requested: str | None = None, coef: float = 0.
     blend = (1.0 - lbd) if has_prior else 1.0
     ok = bool(_lib.load().srk_i8_supported()) and obstacle is None and contraction(op, coef, blend) < 0.999
     dense_bytes = op.M * _round_up(op.K, 128)
+    if not (ok and min(op.M, op.K) >= 1024 and dense_bytes <= (16 << 30)):
+        return "csr"
+    # Measured crossover at BASELINE cfg4 (n = 32768, 0.19 % dense; profiles/r2_bench_n1.json): the dense
+    # tensor-core chain costs 63 ms whatever the density, the fixed-point gather 26 ms, growing with
+    # nnz * n -- they meet at a density of about 0.45 %.  The float64 gather is 2.3x slower than the
+    # fixed-point one and only beats the dense chain below 0.1 %.
     density = op.nnz / max(1, op.M * op.K)
-    return "i8" if ok and min(op.M, op.K) >= 1024 and dense_bytes <= (16 << 30) and density >= 1.0 / 1024 else "csr"
+    if density >= 1.0 / 256:
+        return "i8"
+    if not has_prior and (op.deg.size == 0 or int(op.deg.max()) < 65536):
+        return "csr16"
+    return "i8" if density >= 1.0 / 1024 else "csr"
 
 
 # --------------------------------------------------------------------------- one similarity matrix
@@ -458,7 +507,7 @@ class _Half:
             lib = _lib.load()
             _lib.check(self._timed("quantize_rows_u16", lambda: lib.srk_quantize_rows_u16(
                 _ptr(self.S), self.ld, self.n_out, self.n_out, 0, _ptr(self.Xq), self.ldxt, _ptr(self.unit),
-                _stream())), "srk_quantize_rows_u16")
+                1, _stream())), "srk_quantize_rows_u16")      # S is bit-exactly symmetric in this mode
             self._quantized_version = self.version
         return self.Xq, self.unit
 
@@ -470,7 +519,7 @@ class _Half:
         # keep the guaranteed deviation inside ERR_BUDGET (large similarities, C close to 1) THIS update
         # runs in float64: both kinds of update read and write the same float64 S.
         kappa = self.coef * self.rho_max ** 2
-        if choose_slices(self.ns, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
+        if getattr(self, "force_f64", False) or choose_slices(self.ns, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
             self.slices_used.append(0)                                     # 0 = float64 update
             self._err_next = kappa * src.err
             return self._update_f64(src)                                   # bumps self.version
@@ -514,6 +563,14 @@ class _Half:
 
     def result(self) -> torch.Tensor:
         return self.S[:, : self.n_out]
+
+    # the names the row-sharded halves use (dist.py), so that callers can treat both alike
+    local_result = result
+    row0 = 0
+
+    @property
+    def rows(self) -> int:
+        return self.n_out
 
 
 @dataclass

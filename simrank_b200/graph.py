@@ -33,6 +33,7 @@ class HostOperator:
     indices: np.ndarray         # int32 [nnz]
     g: np.ndarray               # float64 [M]
     deg: np.ndarray = field(default=None)   # int64 [M] structural row degree
+    dev_csr: object = field(default=None, repr=False, compare=False)   # (indptr, indices) device tensors, if built there
 
     def __post_init__(self):
         if self.deg is None:
@@ -67,6 +68,7 @@ def _inverse_or_zero(x: np.ndarray) -> np.ndarray:
 
 
 def _csr(rows: np.ndarray, cols: np.ndarray, M: int, K: int):
+    """Host CSR build (small graphs, and machines without the device builder): one sort of packed keys."""
     if rows.size:
         # one sort of packed (row, column) keys; both halves come back with shifts.  32-bit keys when
         # they fit (n < 65536 on both sides): the sort is the dominant cost and 1.4x faster on uint32
@@ -89,8 +91,19 @@ def _per_node(series: pd.Series, labels: pd.Index) -> np.ndarray:
     return series.reindex(labels).to_numpy(dtype=np.float64)
 
 
+def _build_csr(rows, cols, M, K, csr):
+    """(indptr, indices, device arrays or None) through ``csr`` (a device builder such as
+    engine.device_csr: the GPU replacement of pivot + row scatter) or the host sort."""
+    if csr is not None:
+        out = csr(rows, cols, M, K)
+        if out is not None:
+            return out
+    indptr, indices = _csr(rows, cols, M, K)
+    return indptr, indices, None
+
+
 def build_directed(data: pd.DataFrame, weighted: bool, from_node_column: str, to_node_column: str,
-                   weight_column: str):
+                   weight_column: str, csr=None):
     """-> (node_set, node_list, HostOperator) for SimRank / SimRankPP / AprioriSimRank.
 
     ``G[to, from] = 1 / inNeighbors(to)`` (SimRank.py:42-52)."""
@@ -110,12 +123,14 @@ def build_directed(data: pd.DataFrame, weighted: bool, from_node_column: str, to
         inn = np.bincount(rows, minlength=n).astype(np.float64)
         inn[inn == 0] = np.nan
     g = _inverse_or_zero(inn)
-    indptr, indices = _csr(rows, cols, n, n)
-    return node_set, nodes, HostOperator(n, n, indptr, indices, g)
+    indptr, indices, dev = _build_csr(rows, cols, n, n, csr)
+    op = HostOperator(n, n, indptr, indices, g)
+    op.dev_csr = dev
+    return node_set, nodes, op
 
 
 def build_bipartite(data: pd.DataFrame, weighted: bool, node_group1_column: str,
-                    node_group2_column: str, weight_column: str):
+                    node_group2_column: str, weight_column: str, csr=None):
     """-> (set1, set2, sorted1, sorted2, G12, G21) for the bipartite classes.
 
     ``G12[a, b] = 1/deg1(a)``, ``G21[b, a] = 1/deg2(b)`` in sorted-label order
@@ -135,10 +150,11 @@ def build_bipartite(data: pd.DataFrame, weighted: bool, node_group1_column: str,
     i1 = l1.get_indexer(data[c1])
     i2 = l2.get_indexer(data[c2])
     n1, n2 = len(l1), len(l2)
-    p12, x12 = _csr(i1, i2, n1, n2)
-    p21, x21 = _csr(i2, i1, n2, n1)
-    return (set1, set2, list(l1), list(l2),
-            HostOperator(n1, n2, p12, x12, g1), HostOperator(n2, n1, p21, x21, g2))
+    p12, x12, d12 = _build_csr(i1, i2, n1, n2, csr)
+    p21, x21, d21 = _build_csr(i2, i1, n2, n1, csr)
+    op12, op21 = HostOperator(n1, n2, p12, x12, g1), HostOperator(n2, n1, p21, x21, g2)
+    op12.dev_csr, op21.dev_csr = d12, d21
+    return set1, set2, list(l1), list(l2), op12, op21
 
 
 def operator_from_edges(rows, cols, M, K, g=None) -> HostOperator:

@@ -46,7 +46,7 @@ def test_quantize_rows_u16(dev, R, K, diag):
     xt = torch.full((K, ldxt), -1, dtype=torch.int16, device=dev)
     unit = torch.zeros(R, dtype=torch.float64, device=dev)
     _lib.check(_lib.load().srk_quantize_rows_u16(engine._ptr(Vd), K, R, K, diag, engine._ptr(xt), ldxt,
-                                                 engine._ptr(unit), engine._stream()))
+                                                 engine._ptr(unit), 0, engine._stream()))
     torch.cuda.synchronize()
     W = np.where(np.isnan(V) | (V < 0), 0.0, V)
     if diag >= 0:
@@ -60,6 +60,25 @@ def test_quantize_rows_u16(dev, R, K, diag):
     got = xt.cpu().numpy().view(np.uint16)
     np.testing.assert_array_equal(got[:, :R], q.T.astype(np.uint16))
     assert not got[:, R:].any()
+
+
+@pytest.mark.parametrize("n", [5, 64, 333])
+def test_quantize_symmetric_matrix_without_transposition(dev, n):
+    rng = np.random.default_rng(n)
+    V = rng.random((n, n)) * rng.random((n, 1))
+    V = np.triu(V) + np.triu(V, 1).T
+    ldxt = engine._round_up(n, 64)
+    Vd = torch.from_numpy(V).to(dev)
+    outs = []
+    for sym in (0, 1):
+        xt = torch.full((n, ldxt), -1, dtype=torch.int16, device=dev)
+        unit = torch.zeros(n, dtype=torch.float64, device=dev)
+        _lib.check(_lib.load().srk_quantize_rows_u16(engine._ptr(Vd), n, n, n, 0, engine._ptr(xt), ldxt,
+                                                     engine._ptr(unit), sym, engine._stream()))
+        torch.cuda.synchronize()
+        outs.append((xt.cpu().numpy(), unit.cpu().numpy()))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
 
 
 @pytest.mark.parametrize("M,K,L,density", [(37, 53, 29, 0.3), (300, 257, 260, 0.05), (129, 130, 515, 0.5),

@@ -198,3 +198,74 @@ def test_evidence_counts_tensor_core_uint8(dev, M, K):
     torch.cuda.synchronize()
     want = np.minimum(A.astype(np.int64) @ A.astype(np.int64).T, 255).astype(np.uint8)
     np.testing.assert_array_equal(cnt[:, :M].cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------- edge list -> CSR on the device
+def _edges_to_csr(dev, rows, cols, M, K):
+    lib = _lib.load()
+    m = len(rows)
+    r = torch.from_numpy(np.asarray(rows, dtype=np.int32)).to(dev)
+    c = torch.from_numpy(np.asarray(cols, dtype=np.int32)).to(dev)
+    indptr = torch.full((M + 1,), -1, dtype=torch.int64, device=dev)
+    indices = torch.full((max(m, 1),), -1, dtype=torch.int32, device=dev)
+    status = torch.full((1,), 99, dtype=torch.int32, device=dev)
+    nbytes = int(lib.srk_edges_to_csr_workspace(m, M))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.srk_edges_to_csr(engine._ptr(r), engine._ptr(c), m, M, K, engine._ptr(indptr), engine._ptr(indices),
+                                    engine._ptr(status), engine._ptr(ws), nbytes, engine._stream()))
+    torch.cuda.synchronize()
+    return indptr.cpu().numpy(), indices.cpu().numpy()[:m], int(status.item())
+
+
+@pytest.mark.parametrize("M,K,m", [(1, 1, 1), (50, 70, 400), (5000, 3000, 60000), (300, 200000, 50000),
+                                   (20000, 64, 100000)])
+def test_edges_to_csr_matches_host_build(dev, M, K, m):
+    rng = np.random.default_rng(M + K)
+    keys = rng.choice(M * K, size=min(m, M * K), replace=False)         # unique pairs, arbitrary order
+    rows, cols = keys // K, keys % K
+    if M > 10:
+        rows[rows == 3] = 4                                                # an empty row ...
+        keep = np.unique(rows * K + cols, return_index=True)[1]            # ... without creating duplicates
+        rows, cols = rows[keep], cols[keep]
+        perm = rng.permutation(rows.size)
+        rows, cols = rows[perm], cols[perm]
+    indptr, indices, status = _edges_to_csr(dev, rows, cols, M, K)
+    want_ptr, want_idx = graph._csr(rows.astype(np.int64), cols.astype(np.int64), M, K)
+    assert status == 0
+    np.testing.assert_array_equal(indptr, want_ptr)
+    np.testing.assert_array_equal(indices, want_idx)
+
+
+def test_edges_to_csr_flags_duplicates_and_bad_indices(dev):
+    rows, cols = np.array([0, 1, 1, 2, 1]), np.array([1, 2, 0, 2, 2])    # (1, 2) twice
+    assert _edges_to_csr(dev, rows, cols, 3, 3)[2] & 1
+    assert _edges_to_csr(dev, np.array([0, 5]), np.array([1, 1]), 3, 3)[2] & 2
+    assert _edges_to_csr(dev, np.array([0, 1]), np.array([1, -1]), 3, 3)[2] & 2
+    indptr, _, status = _edges_to_csr(dev, np.array([], dtype=np.int64), np.array([], dtype=np.int64), 4, 4)
+    assert status == 0 and indptr.tolist() == [0, 0, 0, 0, 0]
+
+
+def test_device_csr_feeds_the_drop_in_classes(dev):
+    """engine.device_csr is what drivers.build_* use above DEVICE_CSR_MIN_EDGES: same operator as the
+    host build, the pivot's ValueError on duplicate pairs, device arrays reused by DeviceOperator."""
+    import pandas as pd
+
+    from simrank_b200 import drivers, synth
+    df = synth.directed_frame(3000, 60000, 0.8, 5)
+    _, nodes_h, op_h = graph.build_directed(df, False, "from", "to", "weight")
+    _, nodes_d, op_d = drivers.build_directed(df, False, "from", "to", "weight")
+    assert nodes_h == nodes_d and op_d.dev_csr is not None and op_h.dev_csr is None
+    np.testing.assert_array_equal(op_d.indptr, op_h.indptr)
+    np.testing.assert_array_equal(op_d.indices, op_h.indices)
+    dop = engine.DeviceOperator(op_d, dev)
+    assert dop.indptr.data_ptr() == op_d.dev_csr[0].data_ptr()
+    dup = pd.concat([df, df.iloc[:1]], ignore_index=True)
+    with pytest.raises(ValueError, match="duplicate entries"):
+        drivers.build_directed(dup, False, "from", "to", "weight")
+    bi = synth.bipartite_frame(700, 300, 40000, 1.0, 23)
+    out_h = graph.build_bipartite(bi, True, "user", "item", "weight")
+    out_d = drivers.build_bipartite(bi, True, "user", "item", "weight")
+    for a, b in zip(out_h[4:], out_d[4:]):
+        np.testing.assert_array_equal(a.indptr, b.indptr)
+        np.testing.assert_array_equal(a.indices, b.indices)
+        np.testing.assert_array_equal(a.g, b.g)
