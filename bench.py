@@ -506,8 +506,9 @@ def run_cfg5(args):
         for _ in range(args.steps):
             last = solver.step()
         e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - wall0) / args.steps      # every step ends with its scalar read-back
         sync_all()
-    wall = (time.perf_counter() - wall0) / args.steps
     launches = _srk_lib.LAUNCHES - launches_before
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:

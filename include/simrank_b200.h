@@ -141,8 +141,8 @@ typedef struct srk_csr_args {
 int srk_csr_half(const srk_csr_args* args, void* stream);
 
 /* Source operand of the fixed-point gather: unit[r] = max_k V[r, k] / 65535 (element (r, r +
- * zero_diag_offset) excluded and stored as 0; negatives and NaN as 0), XT[k, r] = rint(V[r, k] /
- * unit[r]) -- the TRANSPOSED matrix [K x ldxt] with one scale per column r.  For the symmetric S of
+ * zero_diag_offset) excluded and stored as 0; negatives and NaN as 0), XT[k, r] = rint(V[r, k] *
+ * (1 / unit[r])) -- the TRANSPOSED matrix [K x ldxt] with one scale per column r.  For the symmetric S of
  * SimRank this is S_off itself with column scales; for a row shard (R local rows) it is the column
  * block the first half gathers from.  Columns R..ldxt-1 are zero-filled.  symmetric != 0: the caller
  * guarantees V == V^T bit for bit (R == K; what the symmetric second half leaves behind), and

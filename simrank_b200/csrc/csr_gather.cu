@@ -537,7 +537,7 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 
 // ------------------------------------------------------------------------------------------
 // Fixed-point source operand of the u16 gather.  unit[r] = max_k V[r, k] / 65535 over the row (the
-// element (r, r + zero_diag_offset) excluded: S = I + S_off), then XT[k, r] = rint(V[r, k] / unit[r]):
+// element (r, r + zero_diag_offset) excluded: S = I + S_off), then XT[k, r] = rint(V[r, k] * (1 / unit[r])):
 // the TRANSPOSED matrix with one scale per column -- for a symmetric S this is S_off itself scaled by
 // its column maxima, which is what lets the gather sum whole columns as integers.
 constexpr int QT = 64;
@@ -567,15 +567,20 @@ __global__ void __launch_bounds__(256)
 quantize_transpose_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
                               const double* __restrict__ unit, uint16_t* __restrict__ XT, int64_t ldxt) {
   __shared__ uint16_t t[QT][QT + 2];
+  __shared__ double inv[QT];
   const int64_t r0 = (int64_t)blockIdx.y * QT, k0 = (int64_t)blockIdx.x * QT;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
+  if (threadIdx.x < QT) {
+    const double u = r0 + threadIdx.x < R ? unit[r0 + threadIdx.x] : 0.0;
+    inv[threadIdx.x] = u > 0.0 ? 1.0 / u : 0.0;                // one division per row of the tile, not per element
+  }
+  __syncthreads();
   for (int rr = ty; rr < QT; rr += 4) {
     const int64_t r = r0 + rr, k = k0 + tx;
     unsigned q = 0u;
     if (r < R && k < K) {
-      const double u = unit[r];
       const double v = (zero_diag_offset >= 0 && k == r + zero_diag_offset) ? 0.0 : V[r * ldv + k];
-      double x = u > 0.0 ? rint(v / u) : 0.0;
+      double x = rint(v * inv[rr]);
       if (!(x > 0.0)) x = 0.0;
       if (x > 65535.0) x = 65535.0;
       q = (unsigned)x;
@@ -610,33 +615,40 @@ static EncodeTiledFn encode_fn() {
 __global__ void __launch_bounds__(256)
 quantize_sym_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t n, int64_t zero_diag_offset,
                         const double* __restrict__ unit, uint16_t* __restrict__ XT, int64_t ldxt) {
-  // a warp covers 256 consecutive columns of one row: lane l takes the column pairs 2 l + 64 j, j < 4
-  // (512 B per load instruction, 128 B per store instruction, four independent loads in flight)
+  // A warp covers 8 rows x 64 consecutive columns: lane l takes the column pair 2 l of every row (512 B
+  // per load instruction, 128 B per store instruction, eight independent loads in flight) and divides
+  // by the units of its two columns ONCE: values are scaled with the reciprocal (a float64 division per
+  // element made the pass compute-bound).
   const int lane = threadIdx.x & 31;
-  const int64_t warps_per_row = (ldxt + 255) / 256;
+  const int64_t chunks = (ldxt + 63) / 64, row_blocks = (n + 7) / 8;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= n * warps_per_row) return;
-  const int64_t k = w / warps_per_row, cbase = (w % warps_per_row) * 256;
+  if (w >= row_blocks * chunks) return;
+  const int64_t k0 = (w / chunks) * 8, r = (w % chunks) * 64 + 2 * lane;
+  if (r >= ldxt) return;
   const bool vec = ((reinterpret_cast<uintptr_t>(V) | (uintptr_t)(ldv * 8)) & 15) == 0;
-  double2 v[4];
+  double inv[2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int64_t r = cbase + 64 * j + 2 * lane;
-    if (vec && r + 1 < n) v[j] = __ldcs(reinterpret_cast<const double2*>(V + k * ldv + r));
+  for (int x = 0; x < 2; ++x) {
+    const double u = r + x < n ? unit[r + x] : 0.0;
+    inv[x] = u > 0.0 ? 1.0 / u : 0.0;
+  }
+  double2 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int64_t k = k0 + j;
+    if (k >= n) v[j] = make_double2(0.0, 0.0);
+    else if (vec && r + 1 < n) v[j] = __ldcs(reinterpret_cast<const double2*>(V + k * ldv + r));
     else v[j] = make_double2(r < n ? V[k * ldv + r] : 0.0, r + 1 < n ? V[k * ldv + r + 1] : 0.0);
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int64_t r = cbase + 64 * j + 2 * lane;
-    if (r >= ldxt) continue;
+  for (int j = 0; j < 8; ++j) {
+    const int64_t k = k0 + j;
+    if (k >= n) continue;
     uint32_t out = 0u;
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-      const int64_t rr = r + x;
-      if (rr >= n) continue;
-      const double u = unit[rr];
-      const double val = (zero_diag_offset >= 0 && k == rr + zero_diag_offset) ? 0.0 : (x ? v[j].y : v[j].x);
-      double y = u > 0.0 ? rint(val / u) : 0.0;
+      const double val = (zero_diag_offset >= 0 && k == r + x + zero_diag_offset) ? 0.0 : (x ? v[j].y : v[j].x);
+      double y = rint(val * inv[x]);
       if (!(y > 0.0)) y = 0.0;
       if (y > 65535.0) y = 65535.0;
       out |= (uint32_t)y << (16 * x);
@@ -772,7 +784,7 @@ extern "C" int srk_quantize_rows_u16(const double* V, int64_t ldv, int64_t R, in
   cudaStream_t st = (cudaStream_t)stream;
   gat::row_unit_kernel<<<(unsigned)R, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, unit);
   if (symmetric) {
-    const int64_t threads = K * ((ldxt + 255) / 256) * 32;
+    const int64_t threads = ((K + 7) / 8) * ((ldxt + 63) / 64) * 32;
     SRK_REQUIRE((threads + 255) / 256 < (1ll << 31), "matrix too large for one launch");
     gat::quantize_sym_u16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(V, ldv, K, zero_diag_offset, unit, XT, ldxt);
     SRK_CUDA_OK(cudaGetLastError());

@@ -481,6 +481,11 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tw.advance(cluster_id);
       int stage = 0; uint32_t phase = 0;
       const uint64_t pol = (p.flags & 1) ? policy_evict_normal() : policy_evict_last();
+      // The A8 row panels of a band (group_j x 256 rows) are re-read by every wave of the band, the
+      // V panels only by the pairs of one wave (which are at the same k: lockstep).  SRK_X2_FLAGS 4 / 8
+      // (A/B profiling) take the V loads out of the evict_last class (normal / evict_first), so that the
+      // band of A8 can stay resident in L2 across the waves.
+      const uint64_t polv = (p.flags & 8) ? policy_evict_first() : ((p.flags & 4) ? policy_evict_normal() : pol);
       unsigned int peek = 0u;                              // lockstep: counter of unit peek_unit, read ahead
       int peek_unit = -1;
       for (int t = 0; t < my_tiles; ++t) {
@@ -529,9 +534,9 @@ i8x2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const int plane = nrow / RT, rr = nrow % RT;
             if (p.kblock > 0) {
               const int k = kb * BK;
-              tma_load_4d(sb + b * C::BR * BK, &map_v, &full_bar[stage], pol, k % p.kblock, r0 + rr, k / p.kblock, plane);
+              tma_load_4d(sb + b * C::BR * BK, &map_v, &full_bar[stage], polv, k % p.kblock, r0 + rr, k / p.kblock, plane);
             } else {
-              tma_load_3d(sb + b * C::BR * BK, &map_v, &full_bar[stage], pol, kb * BK, r0 + rr, plane);
+              tma_load_3d(sb + b * C::BR * BK, &map_v, &full_bar[stage], polv, kb * BK, r0 + rr, plane);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -1042,6 +1047,7 @@ static int launch(const srk_x2_args& a, cudaStream_t st) {
   p.tiles_j = (int)((a.M + 255) / 256);
   p.tiles_r = (int)((a.R + C::RT - 1) / C::RT);
   p.group_j = 8;
+  if (const char* e = getenv("SRK_X2_GROUP")) { const int gj = atoi(e); if (gj >= 1 && gj <= 64) p.group_j = gj; }   // A/B profiling
   p.total_tiles = count_tiles(p.tiles_j, p.tiles_r, C::RT, p.layout == SRK_X2_SYMMETRIC);
   p.kblock = (int)a.in_kblock;
   { const char* e = getenv("SRK_X2_FLAGS"); p.flags = e ? atoi(e) : 0; }

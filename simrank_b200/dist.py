@@ -114,6 +114,8 @@ def _all_reduce_max(t, group):
 def _all_to_all(recv, send, group):
     if isinstance(group, LocalRank):
         return group.all_to_all(recv, send)
+    if recv.dtype == torch.int16:                      # NCCL has no 16-bit integer type: move the bytes
+        recv, send = recv.view(torch.uint8), send.view(torch.uint8)
     dist.all_to_all_single(recv, send, group=group)
 
 

@@ -213,6 +213,42 @@ def bipartite_solver(op12: HostOperator, op21: HostOperator, C1, C2, evidence1=N
                                 evidence1_from_pattern=pat1, evidence2_from_pattern=pat2)
 
 
+class _PinnedPool:
+    """Page-locked host buffers for result transfers, reused across fits.  Page-locking a fresh
+    gigabyte costs as much as copying it, so a buffer whose last user is gone (the DataFrame built on
+    it has been dropped: a weak reference to the ndarray the frame was built on tells) is
+    handed out again; a buffer that is still referenced is never reused.  Bounded by
+    SIMRANK_B200_PINNED_POOL_BYTES (default 4 GiB): larger results get a fresh allocation that is not
+    kept."""
+
+    def __init__(self):
+        self.entries = []                                      # [base tensor, weakref to the ndarray handed out]
+
+    def take(self, shape, dtype):
+        import os
+        import weakref
+        n = int(np.prod(shape))
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if nbytes < (1 << 20):
+            t = torch.empty(shape, dtype=dtype)                # small: pageable is fine
+            return t, t.numpy()
+        for e in self.entries:
+            if e[0].numel() == n and e[0].dtype == dtype and (e[1] is None or e[1]() is None):
+                view = e[0].view(shape)
+                arr = view.numpy()
+                e[1] = weakref.ref(arr)
+                return view, arr
+        base = torch.empty(n, dtype=dtype, pin_memory=True)
+        view = base.view(shape)
+        arr = view.numpy()
+        if nbytes <= int(os.environ.get("SIMRANK_B200_PINNED_POOL_BYTES", 4 << 30)):
+            self.entries = self.entries[-3:] + [[base, weakref.ref(arr)]]
+        return view, arr
+
+
+_PINNED = _PinnedPool()
+
+
 class Result:
     """Device-resident result of a fit: similarity matrices + their labels.  ``rows[w]`` is the
     (first, last+1) range of rows of matrix ``w`` held here: everything on a single GPU or with
@@ -230,9 +266,9 @@ class Result:
     def frame(self, which: int = 0) -> pd.DataFrame:
         """The labelled DataFrame the reference returns (SimRank.py:141, 303)."""
         S = self.mats[which]
-        host = torch.empty(S.shape, dtype=S.dtype, pin_memory=S.numel() >= (1 << 20))
+        host, arr = _PINNED.take(tuple(S.shape), S.dtype)
         host.copy_(S)
-        return pd.DataFrame(host.numpy(), index=self._row_labels(which), columns=self.labels[which], copy=False)
+        return pd.DataFrame(arr, index=self._row_labels(which), columns=self.labels[which], copy=False)
 
     def top_k(self, k: int, which: int = 0):
         S = self.mats[which]

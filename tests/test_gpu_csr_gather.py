@@ -56,7 +56,7 @@ def test_quantize_rows_u16(dev, R, K, diag):
     u = W.max(axis=1) / 65535.0
     np.testing.assert_array_equal(unit.cpu().numpy(), u)
     with np.errstate(divide="ignore", invalid="ignore"):
-        q = np.where(u[:, None] > 0, np.rint(W / u[:, None]), 0.0)
+        q = np.clip(np.where(u[:, None] > 0, np.rint(W * (1.0 / u)[:, None]), 0.0), 0, 65535)   # scaled by the reciprocal
     got = xt.cpu().numpy().view(np.uint16)
     np.testing.assert_array_equal(got[:, :R], q.T.astype(np.uint16))
     assert not got[:, R:].any()
