@@ -105,10 +105,10 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
  * an exact integer (row degrees < 65536), scaled once per output element -- 4x fewer gathered bytes
  * than float64 with the rounding of the tensor-core path's 2 planes (DESIGN.md "K3").  The unit
  * diagonal of S stays outside the fixed-point matrices (S = I + S_off, as in srk_x2_half):
- *   mode SRK_CSR_FIRST  OUT[c, i] = rint(D[i, c] * unit(c) / (out_bound(i) / 65535)) as uint16, clipped;
+ *   mode SRK_CSR_FIRST  OUT[c, i] = rint(D[i, c] * unit(c) / (out_bound(i) / qmax)) as uint16, clipped;
  *                       D[i, c] = sum_{m in N(i)} X[m, c].  With X = srk_quantize_rows_u16(S_in) this
  *                       is U = A S_off transposed (`G.dot(S)` of SimRank.py:139 without g), column i
- *                       in units of out_bound(i) / 65535, out_bound(i) >= deg(i) * max(S_off).
+ *                       in units of out_bound(i) / qmax, out_bound(i) >= deg(i) * max(S_off).
  *   mode SRK_CSR_FINAL  x = g[i] * g_col[r] * (D[i, r] * unit(r) + counts[r, i])   (counts = A A^T when
  *                       add_counts, the unit-diagonal term), then the srk_epilogue chain with the
  *                       evidence factor taken from `counts` when use_evidence, stored as float64 at
@@ -116,6 +116,10 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
  *   symmetric != 0      (FINAL; square problem, whole row range, no prior, diag_offset 0, OUT row-major
  *                       n x n): only pairs r >= i are computed and every value is stored at (i, r) AND
  *                       (r, i); counts / s_old / evidence are read at (i, r) (they are symmetric).
+ * qmax: the sums are exact while deg(i) * qmax < 2^32.  Graphs with a row degree above 65536 (the
+ * popular items of a ratings graph) are held with qmax = floor((2^32 - 1) / max degree) < 65535 in
+ * every matrix that row gathers from -- the same arithmetic with a coarser step; the units the
+ * caller passes (in_unit, and bound / qmax of srk_quantize_rows_u16) follow qmax.
  * elem = SRK_ELEM_F64 is srk_csr_half_f64 (in_unit, out_bound, g_col, counts ignored), plus the
  * symmetric second half.
  * The TMA gather needs 16-byte aligned rows of X (X % 16 == 0, ldx * sizeof(elem) % 16 == 0); other
@@ -133,6 +137,7 @@ typedef struct srk_csr_args {
   void* OUT; int64_t ldo;
   srk_rowbound in_unit;                                   /* U16: unit of column c of X */
   srk_rowbound out_bound;                                 /* U16 FIRST: bound of output column i */
+  double qmax;                                            /* U16: largest fixed-point value, 0 = 65535 (see below) */
   const double* g_col;                                    /* U16 FINAL: row factor of output row r */
   const void* counts; int64_t ld_counts;                  /* uint16 / uint32 A A^T, indexed like OUT */
   int counts_bits, add_counts, use_evidence;
@@ -140,7 +145,7 @@ typedef struct srk_csr_args {
 } srk_csr_args;
 int srk_csr_half(const srk_csr_args* args, void* stream);
 
-/* Source operand of the fixed-point gather: unit[r] = max_k V[r, k] / 65535 (element (r, r +
+/* Source operand of the fixed-point gather: unit[r] = max_k V[r, k] / qmax (element (r, r +
  * zero_diag_offset) excluded and stored as 0; negatives and NaN as 0), XT[k, r] = rint(V[r, k] *
  * (1 / unit[r])) -- the TRANSPOSED matrix [K x ldxt] with one scale per column r.  For the symmetric S of
  * SimRank this is S_off itself with column scales; for a row shard (R local rows) it is the column
@@ -148,7 +153,7 @@ int srk_csr_half(const srk_csr_args* args, void* stream);
  * guarantees V == V^T bit for bit (R == K; what the symmetric second half leaves behind), and
  * XT[k, r] is read as V[k, r]: the same result in one streaming pass without the transposition.  */
 int srk_quantize_rows_u16(const double* V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
-                          uint16_t* XT, int64_t ldxt, double* unit, int symmetric, void* stream);
+                          uint16_t* XT, int64_t ldxt, double* unit, double qmax, int symmetric, void* stream);
 
 /* Common-in-neighbour counts cnt[i,j] = |N(i) & N(j)| clipped to 255, for rows
  * [row_begin,row_end) x all j < M: `np.dot((G>0).astype(int), (G>0).T.astype(int))`

@@ -52,7 +52,7 @@ class CsrArgs(C.Structure):
                 ("M", C.c_int64), ("row_begin", C.c_int64), ("row_end", C.c_int64),
                 ("X", C.c_void_p), ("ldx", C.c_int64), ("L", C.c_int64), ("K", C.c_int64),
                 ("OUT", C.c_void_p), ("ldo", C.c_int64),
-                ("in_unit", RowBound), ("out_bound", RowBound),
+                ("in_unit", RowBound), ("out_bound", RowBound), ("qmax", C.c_double),
                 ("g_col", C.c_void_p),
                 ("counts", C.c_void_p), ("ld_counts", C.c_int64),
                 ("counts_bits", C.c_int), ("add_counts", C.c_int), ("use_evidence", C.c_int),
@@ -88,7 +88,7 @@ SYMBOLS = {
     "srk_device_cc": (_INT, []),
     "srk_csr_half_f64": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, C.POINTER(Epilogue), _P]),
     "srk_csr_half": (_INT, [C.POINTER(CsrArgs), _P]),
-    "srk_quantize_rows_u16": (_INT, [_P, _I64, _I64, _I64, _I64, _P, _I64, _P, _INT, _P]),
+    "srk_quantize_rows_u16": (_INT, [_P, _I64, _I64, _I64, _I64, _P, _I64, _P, _DBL, _INT, _P]),
     "srk_edges_to_csr_workspace": (C.c_size_t, [_I64, _I64]),
     "srk_edges_to_csr": (_INT, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _P, C.c_size_t, _P]),
     "srk_csr_evidence_counts": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _I64, _P]),

@@ -47,7 +47,7 @@ namespace gat {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int TI = 32;                      // graph rows per CTA
+constexpr int kTI = 32;                     // graph rows per CTA (the transposed second half takes 16, see Smem)
 constexpr int kRowsPerOp = 4;               // rows of X per TMA instruction (tile::gather4)
 
 constexpr int MODE_FIRST = 0, MODE_FINAL = 1, MODE_FINAL_SYM = 2;
@@ -107,7 +107,8 @@ struct Params {
   const void* X; int64_t ldx, L;
   void* OUT; int64_t ldo;
   srk_rowbound in_unit;        // u16: value of one unit of column c of X
-  srk_rowbound out_bound;      // u16 FIRST: bound of output column i (one unit = bound / 65535)
+  srk_rowbound out_bound;      // u16 FIRST: bound of output column i (one unit = bound / qmax)
+  double qmax;                 // u16: largest fixed-point value (65535, less when a row degree exceeds 65536)
   const double* g_col;         // u16 FINAL: row factor of output row r (= column of X)
   const void* counts; int64_t ld_counts; int counts32, add_counts, use_evidence;
   EpilogueDev epi; double* maxdiff; double* maxoff;
@@ -209,6 +210,10 @@ struct TileElem<uint16_t, MODE_FINAL> { typedef uint32_t type; };
 template <typename E, int TC, int MODE>
 struct Smem {
   typedef typename TileElem<E, MODE>::type TileT;
+  // The transposed second half keeps 4 or 8 bytes per element of its tile in shared memory: with 16
+  // rows per CTA the tile of a full-width panel (1 KB segments) still leaves room for two CTAs per SM,
+  // and a row of the result is still a whole 128-byte line.
+  static constexpr int TI = MODE == MODE_FINAL ? 16 : kTI;
   static constexpr int kSeg = TC * (int)sizeof(E);                   // bytes of one row segment (<= 1024)
   static constexpr int kSlot = kRowsPerOp * kSeg;
   // TMA instructions in flight per warp: as many as shared memory allows with two CTAs per SM
@@ -219,6 +224,7 @@ struct Smem {
   static constexpr int kFac = (MODE == MODE_FINAL_SYM && sizeof(E) == 2) ? TC * 16 : 0;
   // transposed-store tile [TC][kPitch]: odd pitch in 32-bit words where the element size allows
   static constexpr int kPitch = sizeof(TileT) == 2 ? TI + 2 : TI + 1;
+  static constexpr int kRowsPerPass = 32 / TI;                        // tile rows a warp stores per pass of the transposed store
   static constexpr int kTile = MODE == MODE_FINAL_SYM ? 0 : TC * kPitch * (int)sizeof(TileT);
   static constexpr int kBytes = kRing + kBars + kFac + kTile + 128;
   static_assert(kSeg % 512 == 0 && kSeg <= 1024, "row segments are 512 B or 1 KB (TMA box <= 256 elements of 4 B)");
@@ -232,10 +238,11 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   typedef Acc<E, TC> A;
   constexpr bool kU16 = sizeof(E) == 2;
   constexpr int kDepth = SM::kDepth;
+  constexpr int TI = SM::TI;
   extern __shared__ uint8_t smem_raw[];
   __shared__ double red[2][kWarps];
   __shared__ int next_row;                    // rows of the tile are claimed by the warps as they go
-  __shared__ uint8_t fifo[kWarps][TI];        // rows a warp has claimed, in order (issue side -> consume side)
+  __shared__ uint8_t fifo[kWarps][kTI];       // rows a warp has claimed, in order (issue side -> consume side)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kRing);
   double2* fac = reinterpret_cast<double2*>(smem + SM::kRing + SM::kBars);
@@ -382,14 +389,14 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
       if (MODE == MODE_FIRST) {
         if (kU16) {
           const double bo = row_bound(p.out_bound, row);
-          const double inv = bo > 0.0 ? 65535.0 / bo : 0.0;
+          const double inv = bo > 0.0 ? p.qmax / bo : 0.0;
 #pragma unroll
           for (int j = 0; j < A::kCols; ++j) {
             const int cl = col_of<E, TC>(j, lane);
             const int64_t c = c0 + cl;
             double q = c < p.L ? rint(acc.val(j) * row_bound(p.in_unit, c) * inv) : 0.0;
             if (!(q > 0.0)) q = 0.0;
-            if (q > 65535.0) q = 65535.0;
+            if (q > p.qmax) q = p.qmax;
             tile[cl * SM::kPitch + il] = (TileT)(unsigned)q;
           }
         } else {
@@ -486,23 +493,25 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 
   if (MODE != MODE_FINAL_SYM) {
     __syncthreads();
-    const int64_t i = i0 + lane;
-    for (int cl = warp; cl < TC; cl += kWarps) {
+    // transposed store: a warp pass covers kRowsPerPass tile rows (columns c of X), TI lanes each
+    const int il = lane % TI, sub = lane / TI;
+    const int64_t i = i0 + il;
+    for (int cl = warp * SM::kRowsPerPass + sub; cl < TC; cl += kWarps * SM::kRowsPerPass) {
       const int64_t r = c0 + cl;
       if (r >= p.L || i >= p.row_end) continue;
       if (MODE == MODE_FIRST) {
-        if (kU16) reinterpret_cast<uint16_t*>(p.OUT)[r * p.ldo + i] = (uint16_t)tile[cl * SM::kPitch + lane];
-        else __stcs(reinterpret_cast<double*>(p.OUT) + r * p.ldo + i, (double)tile[cl * SM::kPitch + lane]);
+        if (kU16) reinterpret_cast<uint16_t*>(p.OUT)[r * p.ldo + i] = (uint16_t)tile[cl * SM::kPitch + il];
+        else __stcs(reinterpret_cast<double*>(p.OUT) + r * p.ldo + i, (double)tile[cl * SM::kPitch + il]);
         continue;
       }
       uint32_t cnt = 0u;
       if (p.counts) cnt = load_count(p.counts, r * p.ld_counts + i, p.counts32);
       double v;
       if (kU16)
-        v = p.g[i] * p.g_col[r] * ((double)tile[cl * SM::kPitch + lane] * row_bound(p.in_unit, r) +
+        v = p.g[i] * p.g_col[r] * ((double)tile[cl * SM::kPitch + il] * row_bound(p.in_unit, r) +
                                   (p.add_counts ? (double)cnt : 0.0));
       else
-        v = (double)tile[cl * SM::kPitch + lane];
+        v = (double)tile[cl * SM::kPitch + il];
       v *= p.epi.coef;
       // the epilogue streams (evidence, prior, S_old, the result) are touched once: evict-first
       // loads/stores keep them from pushing the gathered panel of X out of L2
@@ -536,14 +545,14 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Fixed-point source operand of the u16 gather.  unit[r] = max_k V[r, k] / 65535 over the row (the
+// Fixed-point source operand of the u16 gather.  unit[r] = max_k V[r, k] / qmax over the row (the
 // element (r, r + zero_diag_offset) excluded: S = I + S_off), then XT[k, r] = rint(V[r, k] * (1 / unit[r])):
 // the TRANSPOSED matrix with one scale per column -- for a symmetric S this is S_off itself scaled by
 // its column maxima, which is what lets the gather sum whole columns as integers.
 constexpr int QT = 64;
 __global__ void __launch_bounds__(256)
 row_unit_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
-                double* __restrict__ unit) {
+                double qmax, double* __restrict__ unit) {
   __shared__ double red[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r = blockIdx.x;
@@ -560,12 +569,12 @@ row_unit_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int64_t K,
   if (warp == 0) {
     m = lane < 8 ? red[lane] : 0.0;
     m = warp_max(m);
-    if (lane == 0) unit[r] = m / 65535.0;
+    if (lane == 0) unit[r] = m / qmax;
   }
 }
 __global__ void __launch_bounds__(256)
 quantize_transpose_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
-                              const double* __restrict__ unit, uint16_t* __restrict__ XT, int64_t ldxt) {
+                              double qmax, const double* __restrict__ unit, uint16_t* __restrict__ XT, int64_t ldxt) {
   __shared__ uint16_t t[QT][QT + 2];
   __shared__ double inv[QT];
   const int64_t r0 = (int64_t)blockIdx.y * QT, k0 = (int64_t)blockIdx.x * QT;
@@ -582,7 +591,7 @@ quantize_transpose_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t
       const double v = (zero_diag_offset >= 0 && k == r + zero_diag_offset) ? 0.0 : V[r * ldv + k];
       double x = rint(v * inv[rr]);
       if (!(x > 0.0)) x = 0.0;
-      if (x > 65535.0) x = 65535.0;
+      if (x > qmax) x = qmax;
       q = (unsigned)x;
     }
     t[tx][rr] = (uint16_t)q;
@@ -613,7 +622,7 @@ static EncodeTiledFn encode_fn() {
 // Symmetric V (R == K, bit-exactly symmetric as the symmetric second half leaves it): XT[k, r] =
 // rint(V[r, k] / unit[r]) = rint(V[k, r] / unit[r]) -- a streaming pass, no transposition.
 __global__ void __launch_bounds__(256)
-quantize_sym_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t n, int64_t zero_diag_offset,
+quantize_sym_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t n, int64_t zero_diag_offset, double qmax,
                         const double* __restrict__ unit, uint16_t* __restrict__ XT, int64_t ldxt) {
   // A warp covers 8 rows x 64 consecutive columns: lane l takes the column pair 2 l of every row (512 B
   // per load instruction, 128 B per store instruction, eight independent loads in flight) and divides
@@ -650,7 +659,7 @@ quantize_sym_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t n, in
       const double val = (zero_diag_offset >= 0 && k == r + x + zero_diag_offset) ? 0.0 : (x ? v[j].y : v[j].x);
       double y = rint(val * inv[x]);
       if (!(y > 0.0)) y = 0.0;
-      if (y > 65535.0) y = 65535.0;
+      if (y > qmax) y = qmax;
       out |= (uint32_t)y << (16 * x);
     }
     *reinterpret_cast<uint32_t*>(XT + k * ldxt + r) = out;
@@ -715,6 +724,8 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   p.row_begin = a->row_begin; p.row_end = a->row_end;
   p.X = a->X; p.ldx = a->ldx; p.L = a->L; p.OUT = a->OUT; p.ldo = a->ldo;
   p.in_unit = a->in_unit; p.out_bound = a->out_bound; p.g_col = a->g_col;
+  p.qmax = a->qmax == 0.0 ? 65535.0 : a->qmax;
+  SRK_REQUIRE(p.qmax >= 1.0 && p.qmax <= 65535.0, "qmax must be in 1..65535");
   p.counts = a->counts; p.ld_counts = a->ld_counts; p.counts32 = a->counts_bits == 32;
   p.add_counts = a->add_counts; p.use_evidence = a->use_evidence;
   if (a->mode == SRK_CSR_FINAL) { p.epi = to_dev(a->epi); p.maxdiff = a->epi.maxdiff; p.maxoff = a->epi.maxoff; }
@@ -728,18 +739,19 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   // Panel width = columns of X per CTA = what all CTAs of a grid column gather from; the panel (rows
   // of X x segment bytes, held once per L2 die) has to survive in L2 next to the streams of the
   // epilogue.  1 KB segments (uint16: 512 columns, float64: 128) reach the L2 roof, 512 B ones stop at
-  // two thirds of it (profiles/r2_micro_tma_gather_rate.txt); the transposed second half keeps a
-  // 4-byte tile per element in shared memory and takes the narrower panel.
+  // two thirds of it (profiles/r2_micro_tma_gather_rate.txt); the transposed second half keeps a 4- or
+  // 8-byte tile per element in shared memory and takes 16 graph rows per CTA instead of 32.
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = a->row_end - a->row_begin;
   const int mode = a->mode == SRK_CSR_FIRST ? gat::MODE_FIRST : (sym ? gat::MODE_FINAL_SYM : gat::MODE_FINAL);
-  const int tc = a->elem == SRK_ELEM_U16 ? (mode == gat::MODE_FINAL ? 256 : 512) : (mode == gat::MODE_FINAL ? 64 : 128);
-  const int64_t gx = (rows + gat::TI - 1) / gat::TI, gy = (a->L + tc - 1) / tc;
+  const int tc = a->elem == SRK_ELEM_U16 ? 512 : 128;
+  const int ti = mode == gat::MODE_FINAL ? 16 : gat::kTI;
+  const int64_t gx = (rows + ti - 1) / ti, gy = (a->L + tc - 1) / tc;
   SRK_REQUIRE(gy <= 65535, "too many column panels");
   dim3 grid((unsigned)gx, (unsigned)gy);
   p.tiles_x = gx;
   if (sym) {
-    const int64_t per = tc / gat::TI, full = gx / per;               // see the kernel: triangular numbering
+    const int64_t per = tc / ti, full = gx / per;                    // see the kernel: triangular numbering
     int64_t total = per * full * (full + 1) / 2;
     if (gy > full) total += (gy - full) * gx;
     SRK_REQUIRE(total < (1ll << 31), "too many tiles");
@@ -748,13 +760,13 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   if (a->elem == SRK_ELEM_U16) {
     switch (mode) {
       case gat::MODE_FIRST: return gat::launch_one<uint16_t, 512, gat::MODE_FIRST>(p, x_rows, grid, st);
-      case gat::MODE_FINAL: return gat::launch_one<uint16_t, 256, gat::MODE_FINAL>(p, x_rows, grid, st);
+      case gat::MODE_FINAL: return gat::launch_one<uint16_t, 512, gat::MODE_FINAL>(p, x_rows, grid, st);
       default: return gat::launch_one<uint16_t, 512, gat::MODE_FINAL_SYM>(p, x_rows, grid, st);
     }
   }
   switch (mode) {
     case gat::MODE_FIRST: return gat::launch_one<double, 128, gat::MODE_FIRST>(p, x_rows, grid, st);
-    case gat::MODE_FINAL: return gat::launch_one<double, 64, gat::MODE_FINAL>(p, x_rows, grid, st);
+    case gat::MODE_FINAL: return gat::launch_one<double, 128, gat::MODE_FINAL>(p, x_rows, grid, st);
     default: return gat::launch_one<double, 128, gat::MODE_FINAL_SYM>(p, x_rows, grid, st);
   }
 }
@@ -775,24 +787,27 @@ extern "C" int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, c
 }
 
 extern "C" int srk_quantize_rows_u16(const double* V, int64_t ldv, int64_t R, int64_t K, int64_t zero_diag_offset,
-                                     uint16_t* XT, int64_t ldxt, double* unit, int symmetric, void* stream) {
+                                     uint16_t* XT, int64_t ldxt, double* unit, double qmax, int symmetric,
+                                     void* stream) {
   SRK_REQUIRE(V && XT && unit, "null pointer");
+  if (qmax == 0.0) qmax = 65535.0;
+  SRK_REQUIRE(qmax >= 1.0 && qmax <= 65535.0 && qmax == floor(qmax), "qmax must be an integer in 1..65535");
   SRK_REQUIRE(ldv >= K && ldxt >= R && ldxt % 8 == 0 && ((uintptr_t)XT % 16) == 0,
               "XT must be 16-byte aligned with ldxt a multiple of 8 and >= R");
   SRK_REQUIRE(!symmetric || R == K, "a symmetric matrix is square");
   if (R == 0 || K == 0) return SRK_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  gat::row_unit_kernel<<<(unsigned)R, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, unit);
+  gat::row_unit_kernel<<<(unsigned)R, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, qmax, unit);
   if (symmetric) {
     const int64_t threads = ((K + 7) / 8) * ((ldxt + 63) / 64) * 32;
     SRK_REQUIRE((threads + 255) / 256 < (1ll << 31), "matrix too large for one launch");
-    gat::quantize_sym_u16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(V, ldv, K, zero_diag_offset, unit, XT, ldxt);
+    gat::quantize_sym_u16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(V, ldv, K, zero_diag_offset, qmax, unit, XT, ldxt);
     SRK_CUDA_OK(cudaGetLastError());
     return SRK_OK;
   }
   dim3 grid((unsigned)((K + gat::QT - 1) / gat::QT), (unsigned)((ldxt + gat::QT - 1) / gat::QT));
   SRK_REQUIRE(grid.y <= 65535, "too many row tiles");
-  gat::quantize_transpose_u16_kernel<<<grid, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, unit, XT, ldxt);
+  gat::quantize_transpose_u16_kernel<<<grid, 256, 0, st>>>(V, ldv, R, K, zero_diag_offset, qmax, unit, XT, ldxt);
   SRK_CUDA_OK(cudaGetLastError());
   return SRK_OK;
 }

@@ -37,7 +37,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import _ptr, _round_up, _stream, attach_sync_ws, choose_slices, count_bits, slice_delta
+from .engine import _ptr, _round_up, _stream, attach_sync_ws, choose_slices, count_bits, gather_qmax, slice_delta
 from .graph import HostOperator
 
 _NO_DIAGONAL = -(1 << 40)
@@ -713,6 +713,7 @@ class ShardedCsr16Half(ShardedCsrHalf):
         g = np.ascontiguousarray(op.g, dtype=np.float64)
         self.rho_max = float((g * op.deg).max()) if g.size else 0.0
         self.deg_dev = torch.from_numpy(op.deg.astype(np.float64)).to(device)
+        self.qmax = gather_qmax(op.deg)                            # of the gathers THIS half runs
         self.lda = _round_up(max(self.n_in, 1), 128)
         self.a8 = self._dense_pattern()
         self.counts = self._pattern_counts()
@@ -720,22 +721,23 @@ class ShardedCsr16Half(ShardedCsrHalf):
         self.err = self._err_next = 0.0
         self.ldxt = _round_up(self.per, 64)
         self.Xq, self.unit = None, torch.zeros(self.per, dtype=torch.float64, device=device)
-        self.version, self._quantized_version = 0, -1
+        self.version, self._quantized_version = 0, (-1, 0.0)
         self._send16 = self._recv16 = None
 
     _dense_pattern = ShardedHalf._dense_pattern
     _pattern_counts = ShardedHalf._pattern_counts
     _launch = ShardedHalf._launch
 
-    def _quantized(self):
-        """uint16 transposed local row block of the CURRENT S (cached per version)."""
+    def _quantized(self, qmax: float = 65535.0):
+        """uint16 transposed local row block of the CURRENT S (cached per version and range; ``qmax`` is
+        the consumer's, engine.gather_qmax)."""
         if self.Xq is None:
             self.Xq = torch.zeros((self.n_out, self.ldxt), dtype=torch.int16, device=self.device)
-        if self._quantized_version != self.version and self.rows:
+        if self._quantized_version != (self.version, qmax) and self.rows:
             _lib.check(_lib.load().srk_quantize_rows_u16(_ptr(self.S), self.ld, self.rows, self.n_out, self.row0,
-                                                         _ptr(self.Xq), self.ldxt, _ptr(self.unit), 0, _stream()),
+                                                         _ptr(self.Xq), self.ldxt, _ptr(self.unit), qmax, 0, _stream()),
                        "srk_quantize_rows_u16")
-        self._quantized_version = self.version
+        self._quantized_version = (self.version, qmax)
         return self.Xq, self.unit
 
     def _args(self, elem, mode):
@@ -747,14 +749,16 @@ class ShardedCsr16Half(ShardedCsrHalf):
 
     def update(self, src: "ShardedCsr16Half") -> None:
         kappa = self.coef * self.rho_max ** 2
-        if getattr(self, "force_f64", False) or choose_slices(None, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
+        qmax = self.qmax
+        if getattr(self, "force_f64", False) or choose_slices(None, self.coef, 1.0, self.rho_max,
+                                                              src.maxoff * 65536.0 / (qmax + 1.0)) > 2:
             self.slices_used.append(0)                              # 0 = float64 update
             self._err_next = kappa * src.err
             super().update(src)
             self.version += 1
             return
         self.slices_used.append(2)
-        self._err_next = kappa * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff)
+        self._err_next = kappa * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff) * 65536.0 / (qmax + 1.0)
         self.scal.zero_()
         lib = _lib.load()
         P, per_in, per_out = self.world, src.per, self.per
@@ -767,7 +771,7 @@ class ShardedCsr16Half(ShardedCsrHalf):
         def first():
             if src.rows == 0:
                 return
-            xq, unit = src._quantized()
+            xq, unit = src._quantized(qmax)
             for p in range(P):
                 lo, hi = self.plan.start(p), self.plan.stop(p)
                 if hi <= lo:
@@ -778,6 +782,7 @@ class ShardedCsr16Half(ShardedCsrHalf):
                 a.OUT, a.ldo = self._send16[p].data_ptr() - 2 * lo, per_out      # column i lands at i - lo
                 a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
                 a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), bound_mul, 0.0)
+                a.qmax = qmax
                 _lib.check(lib.srk_csr_half(C.byref(a), _stream()), "srk_csr_half(u16, first)")
         self._timed("csr16_half_first", first)
         self._timed("exchange", lambda: _all_to_all(self._recv16, self._send16, self.group))
@@ -789,7 +794,8 @@ class ShardedCsr16Half(ShardedCsrHalf):
             b.row_begin, b.row_end = 0, self.n_out
             b.X, b.ldx, b.L, b.K = self._recv16.data_ptr(), per_out, self.rows, P * per_in
             b.OUT, b.ldo = self.S.data_ptr(), self.ld
-            b.in_unit = _lib.RowBound.of(self.deg_dev.data_ptr() + 8 * self.row0, bound_mul / 65535.0, 0.0)
+            b.in_unit = _lib.RowBound.of(self.deg_dev.data_ptr() + 8 * self.row0, bound_mul / qmax, 0.0)
+            b.qmax = qmax
             b.g_col = self.g.data_ptr() + 8 * self.row0
             esz = self.counts.element_size()
             b.counts, b.ld_counts, b.counts_bits, b.add_counts = self.counts.data_ptr(), self.counts.stride(0), 8 * esz, 1

@@ -254,8 +254,8 @@ def choose_mode(op: HostOperator, requested: str | None = None, coef: float = 0.
     if mode == "csr16" and not obstacle:
         if has_prior:
             obstacle = "does not take a prior (the symmetric second half mirrors every value)"
-        elif op.deg.size and int(op.deg.max()) >= 65536:
-            obstacle = "needs row degrees below 65536 (exact 32-bit sums of uint16 values)"
+        elif op.deg.size and int(op.deg.max()) >= (1 << 24):
+            obstacle = "needs row degrees below 2^24 (exact 32-bit sums of fixed-point values)"
     if mode in ("i8", "csr16"):
         if obstacle:
             raise ValueError(f"mode={mode!r} {obstacle}; use mode='csr' (float64)")
@@ -274,7 +274,7 @@ def choose_mode(op: HostOperator, requested: str | None = None, coef: float = 0.
     density = op.nnz / max(1, op.M * op.K)
     if density >= 1.0 / 256:
         return "i8"
-    if not has_prior and (op.deg.size == 0 or int(op.deg.max()) < 65536):
+    if not has_prior and (op.deg.size == 0 or int(op.deg.max()) < (1 << 24)):
         return "csr16"
     return "i8" if density >= 1.0 / 1024 else "csr"
 
@@ -283,6 +283,14 @@ def choose_mode(op: HostOperator, requested: str | None = None, coef: float = 0.
 def slice_delta(ns: int, coef: float, blend: float, rho_max: float, s_off_max: float) -> float:
     """Largest deviation ONE update adds (see choose_slices)."""
     return 1.5 * blend * coef * rho_max * rho_max * s_off_max / 256.0 ** ns
+
+
+def gather_qmax(deg: np.ndarray) -> float:
+    """Largest fixed-point value of the uint16 gather of an operator: the 32-bit sums over a row's
+    neighbours are exact while deg * qmax < 2^32, so 65535 unless a row has more than 65536
+    neighbours (then fewer levels: the same arithmetic with a coarser step)."""
+    dmax = int(deg.max()) if deg.size else 0
+    return float(min(65535, ((1 << 32) - 1) // max(dmax, 1)))
 
 
 def choose_slices(requested, coef: float, blend: float, rho_max: float, s_off_max: float) -> int:
@@ -348,9 +356,10 @@ class _Half:
             self.ldt = _round_up(max(self.n_out, 1), 64)
             self.Tq = torch.empty((self.n_in, self.ldt), dtype=torch.int16, device=dev)
             self.deg_dev = torch.from_numpy(host.deg.astype(np.float64)).to(dev)
+            self.qmax = gather_qmax(host.deg)                              # of the gathers THIS half runs
             self.evidence_from_pattern = bool(evidence_from_pattern)
             self.counts = op.pattern_counts()
-            self.version, self._quantized_version = 0, -1
+            self.version, self._quantized_version = 0, (-1, 0.0)
             return
         self.rho = op.g_host * host.deg                                    # row sums of G
         self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
@@ -498,17 +507,18 @@ class _Half:
                    "srk_csr_half(f64, second)")
         self.version = getattr(self, "version", 0) + 1
 
-    def _quantized(self):
-        """uint16 source operand of the CURRENT S for the fixed-point gather (cached per version of S):
-        Xq[k, r] = rint(S_off[r, k] / unit[r]), unit[r] = row maximum / 65535."""
+    def _quantized(self, qmax: float = 65535.0):
+        """uint16 source operand of the CURRENT S for the fixed-point gather (cached per version of S and
+        range): Xq[k, r] = rint(S_off[r, k] / unit[r]), unit[r] = row maximum / qmax; ``qmax`` is the
+        consumer's (gather_qmax of the operator whose rows sum these values)."""
         if self.Xq is None:
             self.Xq = torch.empty((self.n_out, self.ldxt), dtype=torch.int16, device=self.S.device)
-        if self._quantized_version != self.version:
+        if self._quantized_version != (self.version, qmax):
             lib = _lib.load()
             _lib.check(self._timed("quantize_rows_u16", lambda: lib.srk_quantize_rows_u16(
                 _ptr(self.S), self.ld, self.n_out, self.n_out, 0, _ptr(self.Xq), self.ldxt, _ptr(self.unit),
-                1, _stream())), "srk_quantize_rows_u16")      # S is bit-exactly symmetric in this mode
-            self._quantized_version = self.version
+                qmax, 1, _stream())), "srk_quantize_rows_u16")      # S is bit-exactly symmetric in this mode
+            self._quantized_version = (self.version, qmax)
         return self.Xq, self.unit
 
     def _update_csr16(self, src: "_Half") -> None:
@@ -519,13 +529,16 @@ class _Half:
         # keep the guaranteed deviation inside ERR_BUDGET (large similarities, C close to 1) THIS update
         # runs in float64: both kinds of update read and write the same float64 S.
         kappa = self.coef * self.rho_max ** 2
-        if getattr(self, "force_f64", False) or choose_slices(self.ns, self.coef, 1.0, self.rho_max, src.maxoff) > 2:
+        # (a coarser range -- qmax < 65535 -- scales the 16-bit bound accordingly)
+        if getattr(self, "force_f64", False) or choose_slices(self.ns, self.coef, 1.0, self.rho_max,
+                                                              src.maxoff * 65536.0 / (self.qmax + 1.0)) > 2:
             self.slices_used.append(0)                                     # 0 = float64 update
             self._err_next = kappa * src.err
             return self._update_f64(src)                                   # bumps self.version
         self.slices_used.append(2)
-        self._err_next = kappa * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff)
-        xq, unit = src._quantized()
+        qmax = self.qmax
+        self._err_next = kappa * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff) * 65536.0 / (qmax + 1.0)
+        xq, unit = src._quantized(qmax)
         guard = 1.0 + 2.0 ** -14
         a = _lib.CsrArgs()
         a.elem, a.mode = _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST
@@ -535,6 +548,7 @@ class _Half:
         a.OUT, a.ldo = self.Tq.data_ptr(), self.ldt
         a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
         a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard, 0.0)
+        a.qmax = qmax
         _lib.check(self._timed("csr16_half_first", lambda: lib.srk_csr_half(C.byref(a), _stream())),
                    "srk_csr_half(u16, first)")
         b = _lib.CsrArgs()
@@ -543,7 +557,8 @@ class _Half:
         b.M, b.row_begin, b.row_end = op.M, 0, op.M
         b.X, b.ldx, b.L, b.K = self.Tq.data_ptr(), self.ldt, self.n_out, self.n_in
         b.OUT, b.ldo = self.S.data_ptr(), self.ld
-        b.in_unit = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard / 65535.0, 0.0)
+        b.in_unit = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard / qmax, 0.0)
+        b.qmax = qmax
         b.g_col = op.g.data_ptr()
         b.counts, b.ld_counts = self.counts.data_ptr(), self.counts.stride(0)
         b.counts_bits, b.add_counts = 8 * self.counts.element_size(), 1

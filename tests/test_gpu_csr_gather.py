@@ -46,7 +46,7 @@ def test_quantize_rows_u16(dev, R, K, diag):
     xt = torch.full((K, ldxt), -1, dtype=torch.int16, device=dev)
     unit = torch.zeros(R, dtype=torch.float64, device=dev)
     _lib.check(_lib.load().srk_quantize_rows_u16(engine._ptr(Vd), K, R, K, diag, engine._ptr(xt), ldxt,
-                                                 engine._ptr(unit), 0, engine._stream()))
+                                                 engine._ptr(unit), 65535.0, 0, engine._stream()))
     torch.cuda.synchronize()
     W = np.where(np.isnan(V) | (V < 0), 0.0, V)
     if diag >= 0:
@@ -74,7 +74,7 @@ def test_quantize_symmetric_matrix_without_transposition(dev, n):
         xt = torch.full((n, ldxt), -1, dtype=torch.int16, device=dev)
         unit = torch.zeros(n, dtype=torch.float64, device=dev)
         _lib.check(_lib.load().srk_quantize_rows_u16(engine._ptr(Vd), n, n, n, 0, engine._ptr(xt), ldxt,
-                                                     engine._ptr(unit), sym, engine._stream()))
+                                                     engine._ptr(unit), 65535.0, sym, engine._stream()))
         torch.cuda.synchronize()
         outs.append((xt.cpu().numpy(), unit.cpu().numpy()))
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
@@ -266,3 +266,39 @@ def test_csr_half_rejects_bad_arguments(dev):
     a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
     a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), 24, 20, X.data_ptr(), 24
     assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"g_col" in lib.srk_last_error()
+
+
+def test_csr16_row_degree_above_65536_uses_a_coarser_range(dev):
+    """A row with more than 65536 neighbours (a popular item of a ratings graph): the 32-bit sums stay
+    exact because every matrix it gathers from is held with qmax = floor((2^32 - 1) / degree) levels."""
+    rng = np.random.default_rng(9)
+    M, K, L, big = 40, 70001, 96, 70000
+    rows = np.concatenate([np.full(big, 7), rng.integers(0, M, 500)])
+    cols = np.concatenate([np.arange(big), rng.integers(0, K, 500)])
+    keep = np.unique(rows * K + cols, return_index=True)[1]
+    op = graph.operator_from_edges(rows[keep], cols[keep], M, K)
+    qmax = engine.gather_qmax(op.deg)
+    assert op.deg.max() >= big and qmax == float(((1 << 32) - 1) // int(op.deg.max())) < 65535
+    dop = engine.DeviceOperator(op, dev)
+    Xq = rng.integers(0, int(qmax) + 1, (K, L), dtype=np.int64)
+    Xq[:, 3] = int(qmax)                                   # the worst case: every neighbour at the top of the range
+    X = _u16(Xq).to(dev)
+    unit = rng.random(L) * 1e-7
+    ob = (op.deg * 1e-7 * qmax + 1e-12).astype(np.float64)  # bound >= deg * max value: nothing clips
+    ud, od = torch.from_numpy(unit).to(dev), torch.from_numpy(ob).to(dev)
+    ldo = engine._round_up(M, 8)
+    out = torch.full((L, ldo), -1, dtype=torch.int16, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST)
+    a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), L, L, K, out.data_ptr(), ldo
+    a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+    a.out_bound = _lib.RowBound.of(od.data_ptr(), 1.0, 0.0)
+    a.qmax = qmax
+    _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+    torch.cuda.synchronize()
+    A = np.zeros((M, K), dtype=np.int64)
+    A[rows[keep], cols[keep]] = 1
+    D = A @ Xq
+    assert D.max() > (1 << 31)                             # the sums really use the whole 32 bits
+    want = np.clip(np.rint(D.astype(np.float64) * unit[None, :] * (qmax / ob)[:, None]), 0, qmax).T
+    got = out.cpu().numpy().view(np.uint16)[:, :M].astype(np.int64)
+    np.testing.assert_array_equal(got, want.astype(np.int64))
