@@ -81,6 +81,8 @@ def stall_page(rep, top=12):
 def traffic_entries(kernels):
     """{bench kernel name: bytes per launch} for the kernels bench.py's roofline can name."""
     names = {"i8x2_kernel<2, 0>": ("x2_half_mid", 2), "i8x2_kernel<2, 1>": ("x2_half_final", 2),
+             "csr_gather_kernel<unsigned short, 512, 0>": ("csr16_half_first", 16),
+             "csr_gather_kernel<unsigned short, 512, 2>": ("csr16_half_final", 16),
              "i8x2_kernel<3, 0>": ("x2_half_mid", 3), "i8x2_kernel<3, 1>": ("x2_half_final", 3)}
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
     out = {}

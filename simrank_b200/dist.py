@@ -272,14 +272,25 @@ class LocalPeerExchange:
         self.group.barrier()
 
 
+_PEER_PROBE = {}                 # (device, group) -> symmetric memory works on every rank (probed once per process)
+
+
 def make_exchange(device, group=None):
     """Peer-memory exchange when every rank can map symmetric memory, else the staged fallback.  The
     decision is agreed across the ranks (MIN all-reduce of a probe allocation + rendezvous), so that a
-    box without P2P / NVLink takes the staged path on all ranks instead of failing on some."""
+    box without P2P / NVLink takes the staged path on all ranks instead of failing on some; the probe
+    (a rendezvous: ~0.5 s) runs once per process and group."""
     want = os.environ.get("SIMRANK_B200_EXCHANGE", "auto").lower()
     if isinstance(group, LocalRank):
         return StagedExchange(group) if want == "staged" else LocalPeerExchange(group)
     if want == "staged" or torch.device(device).type != "cuda":
+        return StagedExchange(group)
+    key = (str(device), id(group) if group is not None else None)
+    if key in _PEER_PROBE:
+        if _PEER_PROBE[key]:
+            return PeerExchange(group)
+        if want == "peer":
+            raise RuntimeError("SIMRANK_B200_EXCHANGE=peer, but symmetric memory is not available on every rank")
         return StagedExchange(group)
     ex, ok = None, 1
     try:
@@ -296,7 +307,8 @@ def make_exchange(device, group=None):
             ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    if int(flag.item()):
+    _PEER_PROBE[key] = bool(int(flag.item()))
+    if _PEER_PROBE[key]:
         ex._handles.clear()                                            # barrier() uses the first REAL allocation
         return ex
     if want == "peer":
