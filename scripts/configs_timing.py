@@ -18,6 +18,9 @@ from simrank_b200 import synth  # noqa: E402
 from SimRank import SimRank as M  # noqa: E402
 
 
+MODES = ("csr", "csr16", "i8", "auto")
+
+
 def timed(fn):
     torch.cuda.synchronize()
     t = time.perf_counter()
@@ -35,8 +38,8 @@ def main():
         K = cfg["iterations"]
         df = synth.config_frame(name)
         row = {"class": cfg["cls"], "iterations": K}
-        for mode in ("csr", "i8"):
-            obj = cls(mode=mode)
+        for mode in MODES:
+            obj = cls(mode=None if mode == "auto" else mode)
             kw = dict(weighted=weighted, iterations=K, eps=0.0, verbose=False)
             obj.fit(df, **kw)                                     # warm-up
             res, dt = timed(lambda: obj.fit(df, **kw))
@@ -52,7 +55,7 @@ def main():
             _, So, _, _ = orc.fit_directed(df, kind=okind, weighted=weighted, iterations=K, eps=0.0)
             want = (So,)
         row["oracle_cpu_seconds"] = round(time.perf_counter() - t, 3)
-        for mode in ("csr", "i8"):
+        for mode in MODES:
             got = row[mode].pop("result")
             got = got if isinstance(got, tuple) else (got,)
             row[mode]["max_abs_vs_oracle"] = max(float(np.abs(g.to_numpy() - w).max()) for g, w in zip(got, want))

@@ -14,7 +14,7 @@ echo "rc=$?"; tail -12 gpurun_out/r2_dist_tests_n$n.log
 fi
 echo "== bench N=$n (cfg4)"; timeout -k 10 600 $tr --master-port 29541 bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/r2_scale_n$n.json 2> gpurun_out/r2_scale_n$n.err
 echo "rc=$?"; grep '^{' gpurun_out/r2_scale_n$n.json | cut -c1-2500; grep -v "OMP_NUM\|\*\*\*" gpurun_out/r2_scale_n$n.err | tail -5 | cut -c1-300
-for mode in csr16 i8; do
+for mode in ${CFG5_MODES:-csr16 i8}; do
 echo "== cfg5 scale=$scale mode=$mode N=$n"; timeout -k 10 900 $tr --master-port 29542 bench.py --config cfg5 --scale $scale --mode $mode --gpus $n --steps 3 --warmup 3 > gpurun_out/r2_cfg5_${mode}_n$n.json 2> gpurun_out/r2_cfg5_${mode}_n$n.err
 echo "rc=$?"; grep '^{' gpurun_out/r2_cfg5_${mode}_n$n.json | cut -c1-3500; grep -v "OMP_NUM\|\*\*\*" gpurun_out/r2_cfg5_${mode}_n$n.err | tail -8 | cut -c1-400
 done

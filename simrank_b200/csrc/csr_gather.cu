@@ -275,6 +275,16 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   if (p.tma && lane < kDepth) mbar_init(&wbar[lane], 1);
   if (p.tma) fence_barrier_init();
   if (threadIdx.x == 0) next_row = 0;
+  if (MODE == MODE_FINAL && i0 < p.row_end) {
+    // the transposed epilogue reads TI consecutive elements of S_old (and counts) for each of the TC
+    // output rows of this tile once the gather is done: pull those lines into L2 now
+    for (int c = threadIdx.x; c < TC; c += kThreads) {
+      const int64_t r = c0 + c;
+      if (r >= p.L) break;
+      if (p.epi.s_old) prefetch_l2(p.epi.s_old + r * p.epi.ld_s_old + i0);
+      if (p.counts) prefetch_l2(reinterpret_cast<const uint8_t*>(p.counts) + (r * p.ld_counts + i0) * (p.counts32 ? 4 : 2));
+    }
+  }
   if (MODE == MODE_FINAL_SYM && kU16) {
     for (int c = threadIdx.x; c < TC; c += kThreads) {
       const int64_t cc = c0 + c;
@@ -496,34 +506,61 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     // transposed store: a warp pass covers kRowsPerPass tile rows (columns c of X), TI lanes each
     const int il = lane % TI, sub = lane / TI;
     const int64_t i = i0 + il;
-    for (int cl = warp * SM::kRowsPerPass + sub; cl < TC; cl += kWarps * SM::kRowsPerPass) {
-      const int64_t r = c0 + cl;
-      if (r >= p.L || i >= p.row_end) continue;
-      if (MODE == MODE_FIRST) {
+    constexpr int kStep = kWarps * SM::kRowsPerPass;
+    if (MODE == MODE_FIRST) {
+      for (int cl = warp * SM::kRowsPerPass + sub; cl < TC; cl += kStep) {
+        const int64_t r = c0 + cl;
+        if (r >= p.L || i >= p.row_end) continue;
         if (kU16) reinterpret_cast<uint16_t*>(p.OUT)[r * p.ldo + i] = (uint16_t)tile[cl * SM::kPitch + il];
         else __stcs(reinterpret_cast<double*>(p.OUT) + r * p.ldo + i, (double)tile[cl * SM::kPitch + il]);
-        continue;
       }
-      uint32_t cnt = 0u;
-      if (p.counts) cnt = load_count(p.counts, r * p.ld_counts + i, p.counts32);
-      double v;
-      if (kU16)
-        v = p.g[i] * p.g_col[r] * ((double)tile[cl * SM::kPitch + il] * row_bound(p.in_unit, r) +
-                                  (p.add_counts ? (double)cnt : 0.0));
-      else
-        v = (double)tile[cl * SM::kPitch + il];
-      v *= p.epi.coef;
-      // the epilogue streams (evidence, prior, S_old, the result) are touched once: evict-first
-      // loads/stores keep them from pushing the gathered panel of X out of L2
-      if (p.use_evidence) v *= evidence_factor(cnt);
-      else if (p.epi.evidence) v *= evidence_factor(__ldcs(p.epi.evidence + r * p.epi.ld_evidence + i));
-      if (p.epi.prior) v = (1.0 - p.epi.lambda) * v + p.epi.lambda * __ldcs(p.epi.prior + r * p.epi.ld_prior + i);
-      if (r + p.epi.diag_offset == i) v = 1.0; else if (v > omax) omax = v;
-      if (p.epi.s_old) {
-        const double d = fabs(v - __ldcs(p.epi.s_old + r * p.epi.ld_s_old + i));
-        if (d > dmax) dmax = d;                  // NaN compares false: ignored like SimRank.py:74
+    } else {
+      // Four passes at a time with all their loads issued before the first use: one pass is a chain of
+      // dependent global loads (counts, S_old -- prefetched into L2 when the CTA started), and a CTA
+      // has TC / kStep = 32 .. 64 of them.
+      constexpr int kBatch = 4;
+      const double gi = i < p.row_end ? p.g[i] : 0.0;
+      for (int cb = warp * SM::kRowsPerPass + sub; cb < TC; cb += kStep * kBatch) {
+        uint32_t cnt[kBatch];
+        double so[kBatch], ev[kBatch], pr[kBatch], fu[kBatch], gc[kBatch];
+        bool live[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const int cl = cb + b * kStep;
+          const int64_t r = c0 + cl;
+          live[b] = cl < TC && r < p.L && i < p.row_end;
+          cnt[b] = 0u; so[b] = 0.0; ev[b] = 1.0; pr[b] = 0.0; fu[b] = 0.0; gc[b] = 0.0;
+          if (!live[b]) continue;
+          if (p.counts) cnt[b] = load_count(p.counts, r * p.ld_counts + i, p.counts32);
+          if (p.epi.s_old) so[b] = __ldcs(p.epi.s_old + r * p.epi.ld_s_old + i);
+          if (!p.use_evidence && p.epi.evidence) ev[b] = evidence_factor(__ldcs(p.epi.evidence + r * p.epi.ld_evidence + i));
+          if (p.epi.prior) pr[b] = __ldcs(p.epi.prior + r * p.epi.ld_prior + i);
+          if (kU16) { fu[b] = row_bound(p.in_unit, r); gc[b] = p.g_col[r]; }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          if (!live[b]) continue;
+          const int cl = cb + b * kStep;
+          const int64_t r = c0 + cl;
+          double v;
+          if (kU16)
+            v = gi * gc[b] * ((double)tile[cl * SM::kPitch + il] * fu[b] + (p.add_counts ? (double)cnt[b] : 0.0));
+          else
+            v = (double)tile[cl * SM::kPitch + il];
+          v *= p.epi.coef;
+          if (p.use_evidence) v *= evidence_factor(cnt[b]);
+          else v *= ev[b];
+          if (p.epi.prior) v = (1.0 - p.epi.lambda) * v + p.epi.lambda * pr[b];
+          if (r + p.epi.diag_offset == i) v = 1.0; else if (v > omax) omax = v;
+          if (p.epi.s_old) {
+            const double d = fabs(v - so[b]);
+            if (d > dmax) dmax = d;                // NaN compares false: ignored like SimRank.py:74
+          }
+          // the epilogue streams are touched once: evict-first stores keep them from pushing the
+          // gathered panel of X out of L2
+          __stcs(reinterpret_cast<double*>(p.OUT) + r * p.ldo + i, v);
+        }
       }
-      __stcs(reinterpret_cast<double*>(p.OUT) + r * p.ldo + i, v);
     }
   }
   if (MODE != MODE_FIRST) {
@@ -744,6 +781,9 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = a->row_end - a->row_begin;
   const int mode = a->mode == SRK_CSR_FIRST ? gat::MODE_FIRST : (sym ? gat::MODE_FINAL_SYM : gat::MODE_FINAL);
+  // (Narrower panels were tried for operands with so many rows that a 1 KB-wide panel cannot stay in L2
+  // -- 138k rows at BASELINE cfg5: 142 MB -- and did not pay: 512 B segments cost more per byte than the
+  // residency wins back, profiles/r2_csr_shapes.jsonl.)
   const int tc = a->elem == SRK_ELEM_U16 ? 512 : 128;
   const int ti = mode == gat::MODE_FINAL ? 16 : gat::kTI;
   const int64_t gx = (rows + ti - 1) / ti, gy = (a->L + tc - 1) / tc;
