@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 9
+#define SRK_ABI_VERSION 10
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -123,11 +123,29 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
  * elem = SRK_ELEM_F64 is srk_csr_half_f64 (in_unit, out_bound, g_col, counts ignored), plus the
  * symmetric second half.
  * The TMA gather needs 16-byte aligned rows of X (X % 16 == 0, ldx * sizeof(elem) % 16 == 0); other
- * operands are gathered with plain loads (slower, same results).                                 */
+ * operands are gathered with plain loads (slower, same results).
+ *
+ * Split neighbour lists (SRK_ELEM_U16; all five fields optional).  A ratings graph has rows with tens of
+ * thousands of neighbours (the popular items of BASELINE cfg5) next to rows with a handful: one warp
+ * walking such a row is the tail of the whole launch, and the rows of X it gathers from do not stay in L2.
+ * The integer sums do not care how a row's list is cut, so the caller may pre-sum pieces of it:
+ *   mode SRK_CSR_ACCUM  the "rows" are PIECES of neighbour lists: piece t covers indices[row_lo[t] ..
+ *                       row_hi[t]) and its column sums are added (atomically, uint32) to
+ *                       accum[accum_slot[t] * ld_accum + c], c < L.  M = number of pieces, the whole
+ *                       range [row_begin, row_end) of pieces; indptr, g, OUT are not used.  Pieces
+ *                       that are neighbours in t run at the same time: ordering them by the range of X
+ *                       rows they gather from keeps that range in L2.
+ *   FIRST / FINAL       with row_lo / row_hi given, the list of row r is indices[row_lo[r] .. row_hi[r])
+ *                       instead of indptr[r] .. indptr[r + 1]; a row with accum_slot[r] >= 0 starts from
+ *                       the sums accum[accum_slot[r] * ld_accum + c] (its pre-summed pieces; the caller
+ *                       leaves the rest of its list -- normally nothing -- in row_lo / row_hi).
+ * accum is zeroed by the caller; ld_accum is a multiple of 512 and >= L rounded up to 512.  Results are
+ * bit-identical to the unsplit call: the same integers are added in another order.                  */
 #define SRK_ELEM_F64 0
 #define SRK_ELEM_U16 1
 #define SRK_CSR_FIRST 0
 #define SRK_CSR_FINAL 1
+#define SRK_CSR_ACCUM 2
 typedef struct srk_csr_args {
   int elem, mode, symmetric;
   const int64_t* indptr; const int32_t* indices; const double* g;
@@ -142,6 +160,9 @@ typedef struct srk_csr_args {
   const void* counts; int64_t ld_counts;                  /* uint16 / uint32 A A^T, indexed like OUT */
   int counts_bits, add_counts, use_evidence;
   srk_epilogue epi;                                       /* FINAL */
+  const int64_t* row_lo; const int64_t* row_hi;           /* split lists (see above); NULL = indptr */
+  uint32_t* accum; int64_t ld_accum;                      /* U16: pre-summed pieces, [slots][ld_accum] */
+  const int32_t* accum_slot;                              /* per row (FIRST / FINAL) or per piece (ACCUM) */
 } srk_csr_args;
 int srk_csr_half(const srk_csr_args* args, void* stream);
 

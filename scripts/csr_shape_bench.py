@@ -39,6 +39,12 @@ def timed(fn, reps=3):
     return a.elapsed_time(b) / reps
 
 
+def split_info(sp):
+    if sp is None:
+        return None
+    return {"rows": sp.rows, "pieces": sp.pieces, "ranges": sp.ranges, "piece": sp.piece, "min_deg": sp.min_deg}
+
+
 def args_for(dop, elem, mode):
     a = _lib.CsrArgs()
     a.elem, a.mode = elem, mode
@@ -69,9 +75,16 @@ def final_case(dev, op, rows_local, name):
     b.epi.s_old, b.epi.ld_s_old = S.data_ptr(), ld
     b.epi.maxdiff, b.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
     lib = _lib.load()
-    ms = timed(lambda: _lib.check(lib.srk_csr_half(C.byref(b), engine._stream())))
+    split = engine.ListSplit.plan(dop.indptr, dop.indices, n_in, int(op.deg.max()))
+
+    def run():
+        if split is not None:
+            split.accumulate(lib, b.indices, b.X, b.ldx, b.L, b.K, 65535.0)
+            split.attach(b)
+        _lib.check(lib.srk_csr_half(C.byref(b), engine._stream()))
+    ms = timed(run)
     gather = op.nnz * rows_local * 2.0
-    return {"case": name, "ms": ms, "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
+    return {"case": name, "ms": ms, "split": split_info(split), "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
             "panel_MB_per_1KB_segment": n_in * 1024 / 1e6, "shape": [n_out, n_in, rows_local]}
 
 
@@ -87,8 +100,11 @@ def first_case(dev, op, rows_src, world, name):
     deg = torch.from_numpy(op.deg.astype(np.float64)).to(dev)
     send = torch.zeros((world, engine._round_up(rows_src, 16), per_out), dtype=torch.int16, device=dev)
     lib = _lib.load()
+    split = engine.ListSplit.plan(dop.indptr, dop.indices, n_in, int(op.deg.max()))
 
     def run():
+        if split is not None:
+            split.accumulate(lib, dop.indices.data_ptr(), X.data_ptr(), ldxt, rows_src, n_in, 65535.0)
         for p in range(world):
             lo, hi = min(n_out, p * per_out), min(n_out, (p + 1) * per_out)
             if hi <= lo:
@@ -99,10 +115,12 @@ def first_case(dev, op, rows_src, world, name):
             a.OUT, a.ldo = send[p].data_ptr() - 2 * lo, per_out
             a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
             a.out_bound = _lib.RowBound.of(deg.data_ptr(), 1e-4, 0.0)
+            if split is not None:
+                split.attach(a)
             _lib.check(lib.srk_csr_half(C.byref(a), engine._stream()))
     ms = timed(run)
     gather = op.nnz * rows_src * 2.0
-    return {"case": name, "ms": ms, "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
+    return {"case": name, "ms": ms, "split": split_info(split), "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
             "panel_MB_per_1KB_segment": n_in * 1024 / 1e6, "shape": [n_out, n_in, rows_src]}
 
 
@@ -110,32 +128,36 @@ def main():
     dev = engine.require_cuda()
     cases = sys.argv[1:] or ["cfg5_s1_final", "cfg5_s2_first", "cfg4_n8_final", "cfg4_n8_first"]
     ops = {}
-    for c in cases:
-        if c.startswith("cfg5") and "cfg5" not in ops:
-            u, i = random_bipartite(138493, 26744, 20000263, 5)
-            ops["cfg5"] = (graph.operator_from_edges(u, i, 138493, 26744), graph.operator_from_edges(i, u, 26744, 138493))
-        if c.startswith("cfg4") and "cfg4" not in ops:
-            from simrank_b200 import synth
-            frm, to = synth.directed_edges(32768, 32768 * 64, 0.5, 4)
-            ops["cfg4"] = graph.operator_from_edges(to, frm, 32768, 32768)
-        if c == "cfg5_s1_final":
-            out = final_case(dev, ops["cfg5"][0], 17312, c)
-        elif c == "cfg5_s2_final":
-            out = final_case(dev, ops["cfg5"][1], 3344, c)
-        elif c == "cfg5_s2_first":
-            out = first_case(dev, ops["cfg5"][1], 17312, 8, c)
-        elif c == "cfg5_s1_first":
-            out = first_case(dev, ops["cfg5"][0], 3344, 8, c)
-        elif c == "cfg4_n8_final":
-            out = final_case(dev, ops["cfg4"], 4096, c)
-        elif c == "cfg4_n8_first":
-            out = first_case(dev, ops["cfg4"], 4096, 8, c)
-        else:
-            raise SystemExit(f"unknown case {c}")
-        out["flags"] = os.environ.get("SRK_CSR_FLAGS", "")
-        out["panel"] = os.environ.get("SRK_CSR_TC", "")
-        print(json.dumps(out), flush=True)
-        torch.cuda.empty_cache()
+    # SRK_SWEEP="A=1,B=2;A=3": every case runs once per ';'-separated environment setting (one graph build)
+    sweep = [dict(kv.split("=") for kv in part.split(",") if kv) for part in os.environ.get("SRK_SWEEP", "").split(";")]
+    for env in sweep:
+        os.environ.update(env)
+        for c in cases:
+            if c.startswith("cfg5") and "cfg5" not in ops:
+                u, i = random_bipartite(138493, 26744, 20000263, 5)
+                ops["cfg5"] = (graph.operator_from_edges(u, i, 138493, 26744), graph.operator_from_edges(i, u, 26744, 138493))
+            if c.startswith("cfg4") and "cfg4" not in ops:
+                from simrank_b200 import synth
+                frm, to = synth.directed_edges(32768, 32768 * 64, 0.5, 4)
+                ops["cfg4"] = graph.operator_from_edges(to, frm, 32768, 32768)
+            if c == "cfg5_s1_final":
+                out = final_case(dev, ops["cfg5"][0], 17312, c)
+            elif c == "cfg5_s2_final":
+                out = final_case(dev, ops["cfg5"][1], 3344, c)
+            elif c == "cfg5_s2_first":
+                out = first_case(dev, ops["cfg5"][1], 17312, 8, c)
+            elif c == "cfg5_s1_first":
+                out = first_case(dev, ops["cfg5"][0], 3344, 8, c)
+            elif c == "cfg4_n8_final":
+                out = final_case(dev, ops["cfg4"], 4096, c)
+            elif c == "cfg4_n8_first":
+                out = first_case(dev, ops["cfg4"], 4096, 8, c)
+            else:
+                raise SystemExit(f"unknown case {c}")
+            out["flags"] = os.environ.get("SRK_CSR_FLAGS", "")
+            out["env"] = env
+            print(json.dumps(out), flush=True)
+            torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

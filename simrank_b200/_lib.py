@@ -11,7 +11,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
 SRK_X2_DIRECT, SRK_X2_SYMMETRIC, SRK_X2_TRANSPOSED = 0, 1, 2
@@ -43,7 +43,7 @@ class RowBound(C.Structure):
 
 
 SRK_ELEM_F64, SRK_ELEM_U16 = 0, 1
-SRK_CSR_FIRST, SRK_CSR_FINAL = 0, 1
+SRK_CSR_FIRST, SRK_CSR_FINAL, SRK_CSR_ACCUM = 0, 1, 2
 
 
 class CsrArgs(C.Structure):
@@ -56,7 +56,9 @@ class CsrArgs(C.Structure):
                 ("g_col", C.c_void_p),
                 ("counts", C.c_void_p), ("ld_counts", C.c_int64),
                 ("counts_bits", C.c_int), ("add_counts", C.c_int), ("use_evidence", C.c_int),
-                ("epi", Epilogue)]
+                ("epi", Epilogue),
+                ("row_lo", C.c_void_p), ("row_hi", C.c_void_p),
+                ("accum", C.c_void_p), ("ld_accum", C.c_int64), ("accum_slot", C.c_void_p)]
 
 
 class X2Args(C.Structure):

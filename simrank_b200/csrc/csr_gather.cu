@@ -48,9 +48,10 @@ namespace gat {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTI = 32;                     // graph rows per CTA (the transposed second half takes 16, see Smem)
+constexpr int kTIAccum = 8;                 // MODE_ACCUM: pieces of neighbour lists per CTA (equal sizes: one per warp)
 constexpr int kRowsPerOp = 4;               // rows of X per TMA instruction (tile::gather4)
 
-constexpr int MODE_FIRST = 0, MODE_FINAL = 1, MODE_FINAL_SYM = 2;
+constexpr int MODE_FIRST = 0, MODE_FINAL = 1, MODE_FINAL_SYM = 2, MODE_ACCUM = 3;
 
 // ------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -102,7 +103,11 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct Params {
-  const int64_t* indptr; const int32_t* indices; const double* g;
+  // neighbour list of row r: indices[rowbeg[r] .. rowend[r]).  Normally indptr / indptr + 1; with hub rows
+  // split off (srk_csr_args.row_ptr_*), the hubs' lists are empty here and their sums arrive through
+  // `accum`; in MODE_ACCUM the "rows" are the chunks of the hub rows.
+  const int64_t* rowbeg; const int64_t* rowend; const int32_t* indices; const double* g;
+  uint32_t* accum; int64_t ld_accum; const int32_t* accum_slot;   // u16: partial sums of the hub rows, [slots][ld] u32
   int64_t row_begin, row_end;
   const void* X; int64_t ldx, L;
   void* OUT; int64_t ldo;
@@ -154,6 +159,8 @@ struct Acc<double, TC> {
     }
   }
   __device__ __forceinline__ double val(int j) const { return v[j]; }
+  __device__ __forceinline__ uint32_t raw(int) const { return 0u; }
+  __device__ __forceinline__ void load_sums(const uint32_t*, int) {}
 };
 
 // uint16: the low halves of the 32-bit words are not masked out per element: aw accumulates the
@@ -193,6 +200,17 @@ struct Acc<uint16_t, TC> {
   }
   __device__ __forceinline__ uint32_t raw(int j) const { return (j & 1) ? ah[j >> 1] : aw[j >> 1] - (ah[j >> 1] << 16); }
   __device__ __forceinline__ double val(int j) const { return (double)raw(j); }
+  // start from per-column sums computed elsewhere (hub rows): s[c] for the panel's columns, 32-byte aligned
+  __device__ __forceinline__ void load_sums(const uint32_t* s, int lane) {
+#pragma unroll
+    for (int gq = 0; gq < kGroups; ++gq) {
+      const uint4* q = reinterpret_cast<const uint4*>(s + gq * kGroupCols + kVec * lane);
+      const uint4 lo = q[0], hi = q[1];
+      const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) { ah[4 * gq + w] = v[2 * w + 1]; aw[4 * gq + w] = v[2 * w] + (v[2 * w + 1] << 16); }
+    }
+  }
 };
 
 template <typename E, int TC>
@@ -213,11 +231,11 @@ struct Smem {
   // The transposed second half keeps 4 or 8 bytes per element of its tile in shared memory: with 16
   // rows per CTA the tile of a full-width panel (1 KB segments) still leaves room for two CTAs per SM,
   // and a row of the result is still a whole 128-byte line.
-  static constexpr int TI = MODE == MODE_FINAL ? 16 : kTI;
+  static constexpr int TI = MODE == MODE_FINAL ? 16 : (MODE == MODE_ACCUM ? kTIAccum : kTI);
   static constexpr int kSeg = TC * (int)sizeof(E);                   // bytes of one row segment (<= 1024)
   static constexpr int kSlot = kRowsPerOp * kSeg;
   // TMA instructions in flight per warp: as many as shared memory allows with two CTAs per SM
-  static constexpr int kDepth = kSlot >= 4096 ? (MODE == MODE_FINAL_SYM ? 3 : 2) : 4;
+  static constexpr int kDepth = kSlot >= 4096 ? ((MODE == MODE_FINAL_SYM || MODE == MODE_ACCUM) ? 3 : 2) : 4;
   static constexpr int kRing = kWarps * kDepth * kSlot;
   static constexpr int kBars = kWarps * kDepth * 8;
   // FINAL symmetric: per-column factors of the panel, fa = coef g_col unit, fb = coef g_col
@@ -225,7 +243,7 @@ struct Smem {
   // transposed-store tile [TC][kPitch]: odd pitch in 32-bit words where the element size allows
   static constexpr int kPitch = sizeof(TileT) == 2 ? TI + 2 : TI + 1;
   static constexpr int kRowsPerPass = 32 / TI;                        // tile rows a warp stores per pass of the transposed store
-  static constexpr int kTile = MODE == MODE_FINAL_SYM ? 0 : TC * kPitch * (int)sizeof(TileT);
+  static constexpr int kTile = (MODE == MODE_FINAL_SYM || MODE == MODE_ACCUM) ? 0 : TC * kPitch * (int)sizeof(TileT);
   static constexpr int kBytes = kRing + kBars + kFac + kTile + 128;
   static_assert(kSeg % 512 == 0 && kSeg <= 1024, "row segments are 512 B or 1 KB (TMA box <= 256 elements of 4 B)");
 };
@@ -320,8 +338,8 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
         if (r >= rows_here) return;
         if (lane == 0) fifo[warp][wi] = (uint8_t)r;
         ++wi;
-        ip = p.indptr[i0 + r];
-        iend = p.indptr[i0 + r + 1];
+        ip = p.rowbeg[i0 + r];
+        iend = p.rowend[i0 + r];
       }
       const int cnt = (int)min((int64_t)kRowsPerOp, iend - ip);
       pre_my = p.indices[ip + min(lane & 3, cnt - 1)];                // a short group repeats its last row
@@ -353,7 +371,7 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
       if (ri == wi) break;                                            // every claimed row is done, none left to claim
       const int64_t row = i0 + fifo[warp][ri];
       ++ri;
-      const int64_t rbeg = p.indptr[row], rend = p.indptr[row + 1];
+      const int64_t rbeg = p.rowbeg[row], rend = p.rowend[row];
       if (MODE == MODE_FINAL_SYM && p.epi.s_old) {
         // the epilogue of this row reads S_old (and the counts) once the gather is done: pull its
         // lines into L2 now, so that it sees L2 latency instead of DRAM latency
@@ -369,6 +387,10 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
         }
       }
       acc.clear();
+      if (MODE != MODE_ACCUM && kU16 && p.accum_slot) {
+        const int slot = p.accum_slot[row];                       // a hub row: its chunks were summed beforehand
+        if (slot >= 0) acc.load_sums(p.accum + (int64_t)slot * p.ld_accum + c0, lane);
+      }
       if (p.tma) {
         for (int64_t e = rbeg; e < rend; e += kRowsPerOp) {
           const int cnt = (int)min((int64_t)kRowsPerOp, rend - e);
@@ -396,7 +418,15 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 
       // ------------------------------------------------------------------ row `row` is complete
       const int il = (int)(row - i0);
-      if (MODE == MODE_FIRST) {
+      if (MODE == MODE_ACCUM) {
+        // a chunk of a hub row: add its column sums to the row's slot (integer adds: order does not matter)
+        uint32_t* dst = p.accum + (int64_t)p.accum_slot[row] * p.ld_accum + c0;
+#pragma unroll
+        for (int j = 0; j < A::kCols; ++j) {
+          const int cl = col_of<E, TC>(j, lane);
+          if (c0 + cl < p.L) atomicAdd(dst + cl, acc.raw(j));
+        }
+      } else if (MODE == MODE_FIRST) {
         if (kU16) {
           const double bo = row_bound(p.out_bound, row);
           const double inv = bo > 0.0 ? p.qmax / bo : 0.0;
@@ -501,7 +531,7 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     }
   }
 
-  if (MODE != MODE_FINAL_SYM) {
+  if (MODE != MODE_FINAL_SYM && MODE != MODE_ACCUM) {
     __syncthreads();
     // transposed store: a warp pass covers kRowsPerPass tile rows (columns c of X), TI lanes each
     const int il = lane % TI, sub = lane / TI;
@@ -563,7 +593,7 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
       }
     }
   }
-  if (MODE != MODE_FIRST) {
+  if (MODE != MODE_FIRST && MODE != MODE_ACCUM) {
     dmax = warp_max(dmax);
     omax = warp_max(omax);
     if (lane == 0) { red[0][warp] = dmax; red[1][warp] = omax; }
@@ -736,14 +766,25 @@ using namespace srk;
 
 extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   SRK_REQUIRE(a, "null args");
-  SRK_REQUIRE(a->indptr && a->indices && a->g && a->X && a->OUT, "null pointer");
+  const bool accum_mode = a->mode == SRK_CSR_ACCUM;
+  SRK_REQUIRE(a->indices && a->X, "null pointer");
+  SRK_REQUIRE(accum_mode || (a->indptr && a->g && a->OUT), "null pointer");
+  SRK_REQUIRE((a->row_lo == nullptr) == (a->row_hi == nullptr), "row_lo and row_hi come together");
   SRK_REQUIRE(0 <= a->row_begin && a->row_begin <= a->row_end && a->row_end <= a->M, "row range");
   // OUT is addressed as OUT[c * ldo + i] for i in [row_begin, row_end) only: a caller that stores just
   // those columns passes the address of (virtual) column 0, i.e. its buffer minus row_begin elements
-  SRK_REQUIRE(a->L >= 0 && a->ldx >= a->L && a->ldo >= a->row_end - a->row_begin, "leading dimensions");
+  SRK_REQUIRE(a->L >= 0 && a->ldx >= a->L && (accum_mode || a->ldo >= a->row_end - a->row_begin), "leading dimensions");
   SRK_REQUIRE(a->K >= 0 && a->K < (1ll << 31), "K (rows of X) out of range");
   SRK_REQUIRE(a->elem == SRK_ELEM_F64 || a->elem == SRK_ELEM_U16, "elem must be SRK_ELEM_F64 or SRK_ELEM_U16");
-  SRK_REQUIRE(a->mode == SRK_CSR_FIRST || a->mode == SRK_CSR_FINAL, "mode must be SRK_CSR_FIRST or SRK_CSR_FINAL");
+  SRK_REQUIRE(a->mode == SRK_CSR_FIRST || a->mode == SRK_CSR_FINAL || accum_mode,
+              "mode must be SRK_CSR_FIRST, SRK_CSR_FINAL or SRK_CSR_ACCUM");
+  if (accum_mode) SRK_REQUIRE(a->row_lo && a->accum && a->accum_slot, "SRK_CSR_ACCUM needs row_lo, row_hi, accum and accum_slot");
+  if (a->accum || a->accum_slot) {
+    SRK_REQUIRE(a->elem == SRK_ELEM_U16, "pre-summed pieces exist in the fixed-point mode only");
+    SRK_REQUIRE(a->accum && a->accum_slot && a->ld_accum % 512 == 0 && a->ld_accum >= a->L &&
+                    ((uintptr_t)a->accum % 32) == 0,
+                "accum: 32-byte aligned, ld_accum a multiple of 512 and >= L");
+  }
   SRK_REQUIRE(a->counts_bits == 0 || a->counts_bits == 16 || a->counts_bits == 32, "counts_bits must be 16 or 32");
   SRK_REQUIRE(!(a->add_counts || a->use_evidence) || a->counts, "counts missing");
   SRK_REQUIRE(!(a->use_evidence && a->epi.evidence), "evidence given twice (counts and epi.evidence)");
@@ -757,7 +798,10 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
 
   gat::Params p;
   memset(&p, 0, sizeof(p));
-  p.indptr = a->indptr; p.indices = a->indices; p.g = a->g;
+  p.rowbeg = a->row_lo ? a->row_lo : a->indptr;
+  p.rowend = a->row_hi ? a->row_hi : a->indptr + 1;
+  p.indices = a->indices; p.g = a->g;
+  p.accum = a->accum; p.ld_accum = a->ld_accum; p.accum_slot = a->accum_slot;
   p.row_begin = a->row_begin; p.row_end = a->row_end;
   p.X = a->X; p.ldx = a->ldx; p.L = a->L; p.OUT = a->OUT; p.ldo = a->ldo;
   p.in_unit = a->in_unit; p.out_bound = a->out_bound; p.g_col = a->g_col;
@@ -780,12 +824,13 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   // 8-byte tile per element in shared memory and takes 16 graph rows per CTA instead of 32.
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = a->row_end - a->row_begin;
-  const int mode = a->mode == SRK_CSR_FIRST ? gat::MODE_FIRST : (sym ? gat::MODE_FINAL_SYM : gat::MODE_FINAL);
+  const int mode = accum_mode ? gat::MODE_ACCUM
+                              : a->mode == SRK_CSR_FIRST ? gat::MODE_FIRST : (sym ? gat::MODE_FINAL_SYM : gat::MODE_FINAL);
   // (Narrower panels were tried for operands with so many rows that a 1 KB-wide panel cannot stay in L2
   // -- 138k rows at BASELINE cfg5: 142 MB -- and did not pay: 512 B segments cost more per byte than the
   // residency wins back, profiles/r2_csr_shapes.jsonl.)
   const int tc = a->elem == SRK_ELEM_U16 ? 512 : 128;
-  const int ti = mode == gat::MODE_FINAL ? 16 : gat::kTI;
+  const int ti = mode == gat::MODE_FINAL ? 16 : (accum_mode ? gat::kTIAccum : gat::kTI);
   const int64_t gx = (rows + ti - 1) / ti, gy = (a->L + tc - 1) / tc;
   SRK_REQUIRE(gy <= 65535, "too many column panels");
   dim3 grid((unsigned)gx, (unsigned)gy);
@@ -801,6 +846,7 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
     switch (mode) {
       case gat::MODE_FIRST: return gat::launch_one<uint16_t, 512, gat::MODE_FIRST>(p, x_rows, grid, st);
       case gat::MODE_FINAL: return gat::launch_one<uint16_t, 512, gat::MODE_FINAL>(p, x_rows, grid, st);
+      case gat::MODE_ACCUM: return gat::launch_one<uint16_t, 512, gat::MODE_ACCUM>(p, x_rows, grid, st);
       default: return gat::launch_one<uint16_t, 512, gat::MODE_FINAL_SYM>(p, x_rows, grid, st);
     }
   }

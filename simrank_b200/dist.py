@@ -37,7 +37,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import _ptr, _round_up, _stream, attach_sync_ws, choose_slices, count_bits, gather_qmax, slice_delta
+from .engine import (ListSplit, _ptr, _round_up, _stream, attach_sync_ws, choose_slices, count_bits, gather_qmax,
+                     slice_delta)
 from .graph import HostOperator
 
 _NO_DIAGONAL = -(1 << 40)
@@ -735,6 +736,8 @@ class ShardedCsr16Half(ShardedCsrHalf):
         self.Xq, self.unit = None, torch.zeros(self.per, dtype=torch.float64, device=device)
         self.version, self._quantized_version = 0, (-1, 0.0)
         self._send16 = self._recv16 = None
+        # hub rows (the popular items of a ratings graph) are pre-summed in pieces, see engine.ListSplit
+        self.split = ListSplit.plan(self.indptr, self.indices, self.n_in, int(op.deg.max()) if op.deg.size else 0)
 
     _dense_pattern = ShardedHalf._dense_pattern
     _pattern_counts = ShardedHalf._pattern_counts
@@ -784,6 +787,8 @@ class ShardedCsr16Half(ShardedCsrHalf):
             if src.rows == 0:
                 return
             xq, unit = src._quantized(qmax)
+            if self.split is not None:                              # one launch for the hub rows of every block
+                self.split.accumulate(lib, self.indices.data_ptr(), xq.data_ptr(), src.ldxt, src.rows, self.n_in, qmax)
             for p in range(P):
                 lo, hi = self.plan.start(p), self.plan.stop(p)
                 if hi <= lo:
@@ -795,6 +800,8 @@ class ShardedCsr16Half(ShardedCsrHalf):
                 a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
                 a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), bound_mul, 0.0)
                 a.qmax = qmax
+                if self.split is not None:
+                    self.split.attach(a)
                 _lib.check(lib.srk_csr_half(C.byref(a), _stream()), "srk_csr_half(u16, first)")
         self._timed("csr16_half_first", first)
         self._timed("exchange", lambda: _all_to_all(self._recv16, self._send16, self.group))
@@ -819,6 +826,9 @@ class ShardedCsr16Half(ShardedCsrHalf):
             e.s_old, e.ld_s_old = self.S.data_ptr(), self.ld
             e.maxdiff, e.maxoff = self.scal.data_ptr(), self.scal.data_ptr() + 8
             e.diag_offset = self.row0
+            if self.split is not None:
+                self.split.accumulate(lib, self.indices.data_ptr(), b.X, b.ldx, b.L, b.K, qmax)
+                self.split.attach(b)
             _lib.check(lib.srk_csr_half(C.byref(b), _stream()), "srk_csr_half(u16, second)")
         self._timed("csr16_half_final", second)
         self.version += 1

@@ -293,6 +293,96 @@ def gather_qmax(deg: np.ndarray) -> float:
     return float(min(65535, ((1 << 32) - 1) // max(dmax, 1)))
 
 
+class ListSplit:
+    """Neighbour lists of the hub rows, cut into pieces for the fixed-point gather (include/simrank_b200.h,
+    "Split neighbour lists").  A ratings graph has rows with tens of thousands of neighbours next to rows
+    with a handful (BASELINE cfg5: the popular items): one warp walking such a row is the tail of the whole
+    launch.  Rows with at least ``min_deg`` neighbours are cut (a) at the boundaries of ``ranges`` equal
+    ranges of X rows -- pieces that run at the same time then gather from one range, which stays in L2 when
+    the whole panel (rows of X x 1 KB) does not -- and (b) into pieces of at most ``piece`` neighbours.
+    ``srk_csr_half`` SRK_CSR_ACCUM sums the pieces into ``accum[slot]`` (exact integers: the order does not
+    matter, results are bit-identical to the unsplit call) and the FIRST / FINAL launch starts those rows
+    from the sums with an empty list.
+
+    Tunables (environment, read when the plan is made): SRK_SPLIT_MIN (default 256; 0 = never split),
+    SRK_SPLIT_PIECE (512), SRK_SPLIT_RANGE_MB (32: a range of X rows is at most this many MB of 1 KB
+    segments).  Defaults from profiles/r2_csr_split_shapes.jsonl (one rank of BASELINE cfg5 replayed on one
+    GPU): S2's first half 107.8 -> 45.0 ms, its second half 34.0 -> 9.5 ms."""
+
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, K: int, min_deg: int, piece: int, ranges: int):
+        dev = indptr.device
+        M = indptr.numel() - 1
+        deg = indptr[1:] - indptr[:-1]
+        hub = deg >= min_deg
+        self.rows = int(hub.sum().item())
+        self.row_lo = indptr[:-1].clone()
+        self.row_hi = torch.where(hub, self.row_lo, indptr[1:])                      # hubs: nothing left to gather
+        slot = torch.cumsum(hub.to(torch.int32), 0, dtype=torch.int32) - 1
+        self.slot = torch.where(hub, slot, torch.full_like(slot, -1))
+        hub_rows = torch.nonzero(hub).flatten()
+        hub_deg = deg[hub_rows]
+        # positions (in `indices`) of the hub rows' entries, row by row
+        starts = indptr[:-1][hub_rows]
+        first = torch.cumsum(hub_deg, 0) - hub_deg
+        owner = torch.repeat_interleave(torch.arange(hub_rows.numel(), device=dev), hub_deg)
+        pos = starts[owner] + (torch.arange(int(hub_deg.sum().item()), device=dev) - first[owner])
+        span = max(1, -(-max(K, 1) // max(ranges, 1)))
+        key = owner * ranges + torch.div(indices[pos].to(torch.int64), span, rounding_mode="floor")
+        head = torch.ones_like(key, dtype=torch.bool)
+        head[1:] = key[1:] != key[:-1]                                              # first entry of a (row, range) segment
+        seg_at = torch.nonzero(head).flatten()
+        seg_lo = pos[seg_at]
+        seg_len = torch.diff(seg_at, append=torch.tensor([key.numel()], device=dev))
+        seg_key = key[seg_at]
+        n_piece = torch.div(seg_len + piece - 1, piece, rounding_mode="floor")
+        size = torch.div(seg_len + n_piece - 1, n_piece, rounding_mode="floor")     # equal pieces, no short tail
+        pseg = torch.repeat_interleave(torch.arange(seg_at.numel(), device=dev), n_piece)
+        pfirst = torch.cumsum(n_piece, 0) - n_piece
+        k = torch.arange(pseg.numel(), device=dev) - pfirst[pseg]
+        lo = seg_lo[pseg] + k * size[pseg]
+        hi = torch.minimum(lo + size[pseg], (seg_lo + seg_len)[pseg])
+        order = torch.argsort(seg_key[pseg] % ranges, stable=True)                  # range by range
+        self.piece_lo, self.piece_hi = lo[order].contiguous(), hi[order].contiguous()
+        # the k-th hub row owns slot k
+        self.piece_slot = torch.div(seg_key[pseg], ranges, rounding_mode="floor")[order].to(torch.int32).contiguous()
+        self.pieces = int(self.piece_lo.numel())
+        self.ranges, self.piece, self.min_deg = ranges, piece, min_deg
+        self._accum = None
+
+    @classmethod
+    def plan(cls, indptr: torch.Tensor, indices: torch.Tensor, K: int, max_deg: int):
+        """A split for this operator, or None when no row is long enough to need one."""
+        min_deg = int(os.environ.get("SRK_SPLIT_MIN", "256"))
+        if min_deg <= 0 or max_deg < min_deg:
+            return None
+        piece = max(4, int(os.environ.get("SRK_SPLIT_PIECE", "512")))
+        range_mb = float(os.environ.get("SRK_SPLIT_RANGE_MB", "32"))
+        ranges = max(1, int(np.ceil(K * 1024 / (range_mb * 2 ** 20))))
+        return cls(indptr, indices, K, min_deg, piece, ranges)
+
+    def accumulate(self, lib, indices_ptr, x_ptr, ldx: int, L: int, K: int, qmax: float) -> None:
+        """Zero the sums and add every piece's column sums of X[:, :L] (one launch)."""
+        ld = _round_up(max(L, 1), 512)
+        if self._accum is None or self._accum.shape[1] < ld:
+            self._accum = torch.empty((self.rows, ld), dtype=torch.int32, device=self.piece_lo.device)
+        self._accum.zero_()
+        a = _lib.CsrArgs()
+        a.elem, a.mode = _lib.SRK_ELEM_U16, _lib.SRK_CSR_ACCUM
+        a.indices = indices_ptr
+        a.M, a.row_begin, a.row_end = self.pieces, 0, self.pieces
+        a.X, a.ldx, a.L, a.K = x_ptr, ldx, L, K
+        a.qmax = qmax
+        self.attach(a, pieces=True)
+        _lib.check(lib.srk_csr_half(C.byref(a), _stream()), "srk_csr_half(u16, accum)")
+
+    def attach(self, a: "_lib.CsrArgs", pieces: bool = False) -> None:
+        if pieces:
+            a.row_lo, a.row_hi, a.accum_slot = self.piece_lo.data_ptr(), self.piece_hi.data_ptr(), self.piece_slot.data_ptr()
+        else:
+            a.row_lo, a.row_hi, a.accum_slot = self.row_lo.data_ptr(), self.row_hi.data_ptr(), self.slot.data_ptr()
+        a.accum, a.ld_accum = self._accum.data_ptr(), self._accum.shape[1]
+
+
 def choose_slices(requested, coef: float, blend: float, rho_max: float, s_off_max: float) -> int:
     """Planes per matrix for one update of the tensor-core path.
 
@@ -360,6 +450,8 @@ class _Half:
             self.evidence_from_pattern = bool(evidence_from_pattern)
             self.counts = op.pattern_counts()
             self.version, self._quantized_version = 0, (-1, 0.0)
+            # hub rows (tens of thousands of neighbours) are pre-summed in pieces, see ListSplit
+            self.split = ListSplit.plan(op.indptr, op.indices, op.K, int(host.deg.max()) if host.deg.size else 0)
             return
         self.rho = op.g_host * host.deg                                    # row sums of G
         self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
@@ -549,6 +641,9 @@ class _Half:
         a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
         a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard, 0.0)
         a.qmax = qmax
+        if self.split is not None:
+            self._timed("csr16_accum", lambda: self.split.accumulate(lib, a.indices, a.X, a.ldx, a.L, a.K, qmax))
+            self.split.attach(a)
         _lib.check(self._timed("csr16_half_first", lambda: lib.srk_csr_half(C.byref(a), _stream())),
                    "srk_csr_half(u16, first)")
         b = _lib.CsrArgs()
@@ -564,6 +659,9 @@ class _Half:
         b.counts_bits, b.add_counts = 8 * self.counts.element_size(), 1
         b.use_evidence = 1 if self.evidence_from_pattern else 0
         b.epi = self._epilogue()
+        if self.split is not None:
+            self._timed("csr16_accum", lambda: self.split.accumulate(lib, b.indices, b.X, b.ldx, b.L, b.K, qmax))
+            self.split.attach(b)
         _lib.check(self._timed("csr16_half_final", lambda: lib.srk_csr_half(C.byref(b), _stream())),
                    "srk_csr_half(u16, second)")
         self.version += 1

@@ -302,3 +302,129 @@ def test_csr16_row_degree_above_65536_uses_a_coarser_range(dev):
     want = np.clip(np.rint(D.astype(np.float64) * unit[None, :] * (qmax / ob)[:, None]), 0, qmax).T
     got = out.cpu().numpy().view(np.uint16)[:, :M].astype(np.int64)
     np.testing.assert_array_equal(got, want.astype(np.int64))
+
+
+# ------------------------------------------------------------------ split neighbour lists (SRK_CSR_ACCUM)
+def _skewed_graph(rng, M, K, hubs):
+    """A few rows with hundreds of neighbours among rows with a handful (a ratings graph in small)."""
+    mask = rng.random((M, K)) < 0.02
+    for r, d in hubs:
+        mask[r] = False
+        mask[r, rng.choice(K, size=d, replace=False)] = True
+    return graph.operator_from_edges(*np.nonzero(mask), M, K, rng.random(M) * 0.2 + 0.01), mask.astype(np.int64)
+
+
+def _run_split(dop, a, K, min_deg, piece, ranges):
+    sp = engine.ListSplit(dop.indptr, dop.indices, K, min_deg, piece, ranges)
+    sp.accumulate(_lib.load(), a.indices, a.X, a.ldx, a.L, a.K, a.qmax)
+    sp.attach(a)
+    _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+    torch.cuda.synchronize()
+    return sp
+
+
+@pytest.mark.parametrize("piece,ranges", [(8, 1), (64, 3), (1024, 2)])
+def test_split_lists_first_half_is_bit_identical(dev, piece, ranges):
+    rng = np.random.default_rng(piece)
+    M, K, L = 150, 900, 700                                # two column panels, the second one partial
+    op, A = _skewed_graph(rng, M, K, [(0, 900), (17, 333), (149, 512), (60, 100)])
+    dop = engine.DeviceOperator(op, dev)
+    ldx = engine._round_up(L, 8)
+    Xq = rng.integers(0, 65536, (K, ldx), dtype=np.int64)
+    X = _u16(Xq).to(dev)
+    ud = torch.from_numpy(rng.random(L) * 1e-6).to(dev)
+    od = torch.from_numpy(op.deg * 1e-6 * 65535 + 1e-9).to(dev)
+    ldo = engine._round_up(M, 8)
+    outs = []
+    for split in (False, True):
+        out = torch.full((L, ldo), -1, dtype=torch.int16, device=dev)
+        a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST)
+        a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), ldx, L, K, out.data_ptr(), ldo
+        a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+        a.out_bound = _lib.RowBound.of(od.data_ptr(), 1.0, 0.0)
+        if split:
+            sp = _run_split(dop, a, K, 100, piece, ranges)
+            assert sp.rows == 4 and sp.pieces >= 4 * ranges
+        else:
+            _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+            torch.cuda.synchronize()
+        outs.append(out.cpu().numpy().view(np.uint16)[:, :M])
+    np.testing.assert_array_equal(outs[0], outs[1])
+    D = A @ Xq[:, :L]
+    want = np.clip(np.rint(D * ud.cpu().numpy()[None, :] * (65535.0 / od.cpu().numpy())[:, None]), 0, 65535).T
+    np.testing.assert_array_equal(outs[1].astype(np.int64), want.astype(np.int64))
+
+
+@pytest.mark.parametrize("symmetric", [0, 1])
+def test_split_lists_second_half_is_bit_identical(dev, symmetric):
+    rng = np.random.default_rng(40 + symmetric)
+    n = 600
+    op, A = _skewed_graph(rng, n, n, [(3, 600), (200, 333), (599, 257)])
+    dop = engine.DeviceOperator(op, dev)
+    ldt, ld = engine._round_up(n, 64), engine._round_up(n, 16)
+    X = _u16(rng.integers(0, 65536, (n, ldt), dtype=np.int64)).to(dev)
+    cnt = rng.integers(0, 40, (n, n))
+    c16 = torch.from_numpy((np.triu(cnt) + np.triu(cnt, 1).T).astype(np.uint16).view(np.int16)).to(dev)
+    S_old = rng.random((n, n))
+    S_old = np.triu(S_old) + np.triu(S_old, 1).T
+    ud, gd = torch.from_numpy(rng.random(n) * 1e-5).to(dev), torch.from_numpy(rng.random(n) * 0.3).to(dev)
+    res = []
+    for split in (False, True):
+        out = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+        out[:, :n] = torch.from_numpy(S_old)
+        scal = torch.zeros(2, dtype=torch.float64, device=dev)
+        a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
+        a.symmetric = symmetric
+        a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), ldt, n, n, out.data_ptr(), ld
+        a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+        a.g_col = gd.data_ptr()
+        a.counts, a.ld_counts, a.counts_bits, a.add_counts, a.use_evidence = c16.data_ptr(), n, 16, 1, 1
+        a.epi.coef = 0.8
+        a.epi.s_old, a.epi.ld_s_old = out.data_ptr(), ld
+        a.epi.maxdiff, a.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
+        if split:
+            _run_split(dop, a, n, 200, 32, 2)
+        else:
+            _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+            torch.cuda.synchronize()
+        res.append((out[:, :n].cpu().numpy(), scal.tolist()))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1]
+
+
+def test_split_lists_through_the_solver(dev, monkeypatch):
+    """The csr16 solver with hub rows pre-summed gives the matrix of the unsplit solver, bit for bit."""
+    rng = np.random.default_rng(77)
+    n = 1200
+    op, _ = _skewed_graph(rng, n, n, [(5, 1100), (6, 900), (700, 640)])
+    mats = []
+    for min_deg in ("0", "256"):
+        monkeypatch.setenv("SRK_SPLIT_MIN", min_deg)
+        monkeypatch.setenv("SRK_SPLIT_PIECE", "100")
+        monkeypatch.setenv("SRK_SPLIT_RANGE_MB", "0.5")
+        solver = engine.DirectedSolver(engine.DeviceOperator(op, dev), 0.8, mode="csr16")
+        assert (solver.half.split is not None) == (min_deg != "0")
+        for _ in range(4):
+            solver.step()
+        mats.append(solver.S.cpu().numpy().copy())
+    np.testing.assert_array_equal(mats[0], mats[1])
+
+
+def test_accum_mode_rejects_bad_arguments(dev):
+    rng = np.random.default_rng(1)
+    op, _ = _rand_graph(rng, 20, 20, 0.3)
+    dop = engine.DeviceOperator(op, dev)
+    lib = _lib.load()
+    X = torch.zeros((20, 24), dtype=torch.int16, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_ACCUM)
+    a.X, a.ldx, a.L = X.data_ptr(), 24, 20
+    assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"SRK_CSR_ACCUM needs" in lib.srk_last_error()
+    acc = torch.zeros((4, 512), dtype=torch.int32, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_F64, _lib.SRK_CSR_FIRST)
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), 24, 20, X.data_ptr(), 24
+    a.accum, a.ld_accum, a.accum_slot = acc.data_ptr(), 512, acc.data_ptr()
+    assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"fixed-point" in lib.srk_last_error()
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST)
+    a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), 24, 20, X.data_ptr(), 24
+    a.accum, a.ld_accum, a.accum_slot = acc.data_ptr(), 500, acc.data_ptr()
+    assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"ld_accum" in lib.srk_last_error()
