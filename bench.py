@@ -51,6 +51,9 @@ def parse():
                          "graph, row-sharded, CSR SpMM path (BASELINE configs[4]; run under torchrun on 8 GPUs)")
     ap.add_argument("--scale", type=float, default=1.0, help="cfg5 only: shrink every dimension (smoke runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "i8", "csr", "csr16"],
+                    help="mode= of the drop-in class in the end-to-end measurement; 'auto' is what a user's "
+                         "SimRank().fit(df) runs (engine.choose_mode picks the fastest path that keeps 1e-6)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-csr", action="store_true", help="skip the secondary CSR SpMM measurement of the default run")
     ap.add_argument("--no-parity", action="store_true",
@@ -345,6 +348,10 @@ def run_engine(args):
     if not args.no_e2e:
         line["e2e"] = run_e2e(args, edges, n, world, rank)
         torch.cuda.empty_cache()
+        if line["e2e"]["mode_used"] != args.mode:          # the same call pinned to the path `value` is measured on
+            pinned = run_e2e(args, edges, n, world, rank, mode=args.mode)
+            line["e2e"]["with_mode_of_value"] = {k: pinned[k] for k in ("value", "mode_used", "seconds_total", "stages_s")}
+            torch.cuda.empty_cache()
 
     # ---- the reference's CPU path on this host's cores (rank 0, N = 1 only)
     if world == 1 and not args.no_cpu:
@@ -415,9 +422,10 @@ def run_parity(args, solver, halves, op, dev, world, iterations):
     return out
 
 
-def run_e2e(args, edges, n, world, rank):
+def run_e2e(args, edges, n, world, rank, mode=None):
     """``SimRank().fit(DataFrame)`` -> DataFrame with K iterations (eps=0): host graph build, H2D of
-    the CSR graph, K device iterations each reading back max|dS|, D2H of the full S."""
+    the CSR graph, K device iterations each reading back max|dS|, D2H of the full S.  ``mode`` is the
+    constructor's (default: the class default 'auto', the call a user makes)."""
     import pandas as pd
     import torch
     from SimRank import SimRank as M
@@ -426,7 +434,8 @@ def run_e2e(args, edges, n, world, rank):
     K = args.steps
     # under torchrun every rank keeps its own row block of the result (gather="local"): the full
     # matrix reaches the host exactly once, spread over the ranks
-    obj = M.SimRank(mode=args.mode, slices=args.slices, gather="local" if world > 1 else "all")
+    mode = mode or args.e2e_mode
+    obj = M.SimRank(mode=mode, slices=args.slices, gather="local" if world > 1 else "all")
     obj.fit(df, iterations=1, eps=0.0, verbose=False)              # warm-up: allocator, pinned pool, library
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -446,7 +455,7 @@ def run_e2e(args, edges, n, world, rank):
     h2d = (len(frm) * 4 + (n + 1) * 8 + 2 * n * 8) / K
     d2h = (n * n * 8 / world + 16 * K) / K
     return {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "seconds_total": dt, "stages_s": {k: round(v, 4) for k, v in obj.fit_timings_.items()},
+            "mode": mode, "mode_used": obj.fit_info_.mode, "seconds_total": dt, "stages_s": {k: round(v, 4) for k, v in obj.fit_timings_.items()},
             "note": ("whole fit(): pandas graph build + H2D + K iterations + D2H of S into a DataFrame"
                      + ("; every rank returns its own row block (gather='local')" if world > 1 else ""))}
 

@@ -83,8 +83,9 @@ def final_case(dev, op, rows_local, name):
             split.attach(b)
         _lib.check(lib.srk_csr_half(C.byref(b), engine._stream()))
     ms = timed(run)
+    ms_accum = timed(lambda: split.accumulate(lib, b.indices, b.X, b.ldx, b.L, b.K, 65535.0)) if split is not None else 0.0
     gather = op.nnz * rows_local * 2.0
-    return {"case": name, "ms": ms, "split": split_info(split), "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
+    return {"case": name, "ms": ms, "ms_accum": ms_accum, "split": split_info(split), "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
             "panel_MB_per_1KB_segment": n_in * 1024 / 1e6, "shape": [n_out, n_in, rows_local]}
 
 
@@ -119,8 +120,10 @@ def first_case(dev, op, rows_src, world, name):
                 split.attach(a)
             _lib.check(lib.srk_csr_half(C.byref(a), engine._stream()))
     ms = timed(run)
+    ms_accum = timed(lambda: split.accumulate(lib, dop.indices.data_ptr(), X.data_ptr(), ldxt, rows_src, n_in, 65535.0)) \
+        if split is not None else 0.0
     gather = op.nnz * rows_src * 2.0
-    return {"case": name, "ms": ms, "split": split_info(split), "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
+    return {"case": name, "ms": ms, "ms_accum": ms_accum, "split": split_info(split), "gather_GB": gather / 1e9, "gather_TBs": gather / ms / 1e9,
             "panel_MB_per_1KB_segment": n_in * 1024 / 1e6, "shape": [n_out, n_in, rows_src]}
 
 
@@ -134,7 +137,12 @@ def main():
         os.environ.update(env)
         for c in cases:
             if c.startswith("cfg5") and "cfg5" not in ops:
-                u, i = random_bipartite(138493, 26744, 20000263, 5)
+                if os.environ.get("SRK_REAL_CFG5", "0") == "1":        # the bench's own synthetic graph (36 s to build)
+                    from simrank_b200 import synth
+                    c5 = synth.CONFIGS["cfg5"]
+                    u, i = synth.bipartite_edges(c5["n1"], c5["n2"], c5["m"], c5["alpha"], c5["seed"], 20)
+                else:
+                    u, i = random_bipartite(138493, 26744, 20000263, 5)
                 ops["cfg5"] = (graph.operator_from_edges(u, i, 138493, 26744), graph.operator_from_edges(i, u, 26744, 138493))
             if c.startswith("cfg4") and "cfg4" not in ops:
                 from simrank_b200 import synth

@@ -545,7 +545,8 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
         else __stcs(reinterpret_cast<double*>(p.OUT) + r * p.ldo + i, (double)tile[cl * SM::kPitch + il]);
       }
     } else {
-      // Four passes at a time with all their loads issued before the first use: one pass is a chain of
+      // Four passes at a time with all their loads issued before the first use (eight was tried: 80 -> 109 ms on
+      // the cfg5 S1 shape, profiles/r2_csr_shapes_batch8.jsonl): one pass is a chain of
       // dependent global loads (counts, S_old -- prefetched into L2 when the CTA started), and a CTA
       // has TC / kStep = 32 .. 64 of them.
       constexpr int kBatch = 4;

@@ -304,10 +304,12 @@ class ListSplit:
     matter, results are bit-identical to the unsplit call) and the FIRST / FINAL launch starts those rows
     from the sums with an empty list.
 
-    Tunables (environment, read when the plan is made): SRK_SPLIT_MIN (default 256; 0 = never split),
-    SRK_SPLIT_PIECE (512), SRK_SPLIT_RANGE_MB (32: a range of X rows is at most this many MB of 1 KB
-    segments).  Defaults from profiles/r2_csr_split_shapes.jsonl (one rank of BASELINE cfg5 replayed on one
-    GPU): S2's first half 107.8 -> 45.0 ms, its second half 34.0 -> 9.5 ms."""
+    Tunables (environment, read when the plan is made): SRK_SPLIT_MIN (0 = never split), SRK_SPLIT_PIECE,
+    SRK_SPLIT_RANGE_MB (32: a range of X rows is at most this many MB of 1 KB segments).  Defaults from
+    profiles/r2_csr_split_shapes_real.jsonl (one rank's launches of BASELINE cfg5 replayed on one GPU):
+    rows of 1024+ neighbours in pieces of 256 when a panel of X does not fit in L2 (S2's halves: 201 -> 60
+    ms and 41 -> 12 ms), rows of 256+ in pieces of 512 when it does (S1's halves: 91 -> 80 and 13.3 -> 11.8
+    ms; there the gain is balance inside the CTAs, whose rows differ tenfold in length)."""
 
     def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, K: int, min_deg: int, piece: int, ranges: int):
         dev = indptr.device
@@ -352,10 +354,11 @@ class ListSplit:
     @classmethod
     def plan(cls, indptr: torch.Tensor, indices: torch.Tensor, K: int, max_deg: int):
         """A split for this operator, or None when no row is long enough to need one."""
-        min_deg = int(os.environ.get("SRK_SPLIT_MIN", "256"))
+        fits = K * 1024 <= 64 * 2 ** 20                               # a 1 KB-wide panel of X stays in L2
+        min_deg = int(os.environ.get("SRK_SPLIT_MIN", "256" if fits else "1024"))
         if min_deg <= 0 or max_deg < min_deg:
             return None
-        piece = max(4, int(os.environ.get("SRK_SPLIT_PIECE", "512")))
+        piece = max(4, int(os.environ.get("SRK_SPLIT_PIECE", "512" if fits else "256")))
         range_mb = float(os.environ.get("SRK_SPLIT_RANGE_MB", "32"))
         ranges = max(1, int(np.ceil(K * 1024 / (range_mb * 2 ** 20))))
         return cls(indptr, indices, K, min_deg, piece, ranges)

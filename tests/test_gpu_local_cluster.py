@@ -67,6 +67,23 @@ def test_bipartite_pp_logical_shards_match_oracle(world, mode):
     assert (seen1, seen2) == (len(l1), len(l2))                # the blocks tile both matrices
 
 
+def test_bipartite_csr16_shards_with_split_hub_rows_are_bit_identical(monkeypatch):
+    """The popular items of cfg5 have thousands of raters: their neighbour lists are pre-summed in pieces
+    (engine.ListSplit).  Integer sums in another order: the sharded result does not change by a bit."""
+    df = synth.config_frame("cfg5", scale=1 / 32)
+    out = []
+    for min_deg in ("0", "64"):
+        monkeypatch.setenv("SRK_SPLIT_MIN", min_deg)
+        monkeypatch.setenv("SRK_SPLIT_PIECE", "48")
+        monkeypatch.setenv("SRK_SPLIT_RANGE_MB", "1")
+        res = _fit_sharded(3, lambda g: M.BipartitleSimRankPP(mode="csr16", sharded=g, gather="local"),
+                           dict(data=df, weighted=True, iterations=3, eps=0.0, verbose=False))
+        out.append([(S1.to_numpy(), S2.to_numpy()) for (S1, S2), _ in res])
+    for (a1, a2), (b1, b2) in zip(*out):
+        np.testing.assert_array_equal(a1, b1)
+        np.testing.assert_array_equal(a2, b2)
+
+
 def test_local_cluster_propagates_errors():
     cluster = sdist.LocalCluster(2)
 
