@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 10
+#define SRK_ABI_VERSION 11
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -139,13 +139,23 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
  *                       instead of indptr[r] .. indptr[r + 1]; a row with accum_slot[r] >= 0 starts from
  *                       the sums accum[accum_slot[r] * ld_accum + c] (its pre-summed pieces; the caller
  *                       leaves the rest of its list -- normally nothing -- in row_lo / row_hi).
- * accum is zeroed by the caller; ld_accum is a multiple of 512 and >= L rounded up to 512.  Results are
- * bit-identical to the unsplit call: the same integers are added in another order.                  */
+ *   accum_slot[t] < 0   (ACCUM) piece t is the WHOLE list of its row: its sums are stored (not added) into slot
+ *                       -accum_slot[t] - 1, which then needs no zeroing.
+ *   mode SRK_CSR_FINISH the second half of SRK_CSR_FINAL alone: every graph row's sums are already in accum
+ *                       (slot = row, left there by SRK_CSR_ACCUM over pieces that cover every list); this
+ *                       call streams them through the transposed store with the fused epilogue.  Splitting
+ *                       the second half this way pays when the rows are short and uneven (a gather CTA of
+ *                       16 rows spends a third of its life in the epilogue with its ring idle; the ACCUM
+ *                       launch has no epilogue and 8 similar pieces per CTA).  indptr / indices / X are not
+ *                       used.
+ * accum is zeroed by the caller where pieces are added; ld_accum is a multiple of 512 and >= L rounded up to
+ * 512.  Results are bit-identical to the unsplit call: the same integers are added in another order.  */
 #define SRK_ELEM_F64 0
 #define SRK_ELEM_U16 1
 #define SRK_CSR_FIRST 0
 #define SRK_CSR_FINAL 1
 #define SRK_CSR_ACCUM 2
+#define SRK_CSR_FINISH 3
 typedef struct srk_csr_args {
   int elem, mode, symmetric;
   const int64_t* indptr; const int32_t* indices; const double* g;

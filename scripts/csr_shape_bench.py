@@ -75,12 +75,16 @@ def final_case(dev, op, rows_local, name):
     b.epi.s_old, b.epi.ld_s_old = S.data_ptr(), ld
     b.epi.maxdiff, b.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
     lib = _lib.load()
-    split = engine.ListSplit.plan(dop.indptr, dop.indices, n_in, int(op.deg.max()))
+    via_accum = os.environ.get("SRK_FINAL_VIA_ACCUM", "1") == "1"
+    split = engine.ListSplit.plan(dop.indptr, dop.indices, n_in, int(op.deg.max()), all_rows=via_accum)
 
     def run():
         if split is not None:
             split.accumulate(lib, b.indices, b.X, b.ldx, b.L, b.K, 65535.0)
-            split.attach(b)
+            if via_accum:
+                b.mode, b.accum, b.ld_accum = _lib.SRK_CSR_FINISH, split._accum.data_ptr(), split._accum.shape[1]
+            else:
+                split.attach(b)
         _lib.check(lib.srk_csr_half(C.byref(b), engine._stream()))
     ms = timed(run)
     ms_accum = timed(lambda: split.accumulate(lib, b.indices, b.X, b.ldx, b.L, b.K, 65535.0)) if split is not None else 0.0

@@ -213,6 +213,15 @@ struct Acc<uint16_t, TC> {
   }
 };
 
+// One element of the fixed-point second half, x = g_i g_r (D unit_r + counts) coef evidence.  Every rounding
+// is spelled out (no FMA contraction): the transposed second half and the FINISH pass (csr_finish_kernel)
+// must agree bit for bit, whatever the compiler does around them.
+__device__ __forceinline__ double final_value_u16(double gi, double gc, double sum, double fu, double cnt_term,
+                                                  double coef, double evf) {
+  const double v = __dmul_rn(__dmul_rn(gi, gc), __dadd_rn(__dmul_rn(sum, fu), cnt_term));
+  return __dmul_rn(__dmul_rn(v, coef), evf);
+}
+
 template <typename E, int TC>
 __device__ __forceinline__ int col_of(int j, int lane) {
   return (j / Acc<E, TC>::kVec) * Acc<E, TC>::kGroupCols + Acc<E, TC>::kVec * lane + j % Acc<E, TC>::kVec;
@@ -249,7 +258,7 @@ struct Smem {
 };
 
 template <typename E, int TC, int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)   // shared memory allows two CTAs per SM in every mode
 csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
   typedef Smem<E, TC, MODE> SM;
   typedef typename SM::TileT TileT;
@@ -419,12 +428,24 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
       // ------------------------------------------------------------------ row `row` is complete
       const int il = (int)(row - i0);
       if (MODE == MODE_ACCUM) {
-        // a chunk of a hub row: add its column sums to the row's slot (integer adds: order does not matter)
-        uint32_t* dst = p.accum + (int64_t)p.accum_slot[row] * p.ld_accum + c0;
+        // a piece of a neighbour list: add its column sums to the row's slot (integer adds: the order does
+        // not matter); a piece that IS the whole list (slot stored as -slot - 1) simply stores them
+        const int sl = p.accum_slot[row];
+        uint32_t* dst = p.accum + (int64_t)(sl >= 0 ? sl : -sl - 1) * p.ld_accum + c0;
+        if (sl >= 0) {
 #pragma unroll
-        for (int j = 0; j < A::kCols; ++j) {
-          const int cl = col_of<E, TC>(j, lane);
-          if (c0 + cl < p.L) atomicAdd(dst + cl, acc.raw(j));
+          for (int j = 0; j < A::kCols; ++j) {
+            const int cl = col_of<E, TC>(j, lane);
+            if (c0 + cl < p.L) atomicAdd(dst + cl, acc.raw(j));
+          }
+        } else {
+#pragma unroll
+          for (int gq = 0; gq < A::kGroups; ++gq) {                   // 32 bytes per lane and group; ld_accum covers the panel
+            const int j0 = gq * A::kVec;
+            uint4* q = reinterpret_cast<uint4*>(dst + gq * A::kGroupCols + A::kVec * lane);
+            q[0] = make_uint4(acc.raw(j0), acc.raw(j0 + 1), acc.raw(j0 + 2), acc.raw(j0 + 3));
+            if (A::kVec > 4) q[1] = make_uint4(acc.raw(j0 + 4), acc.raw(j0 + 5), acc.raw(j0 + 6), acc.raw(j0 + 7));
+          }
         }
       } else if (MODE == MODE_FIRST) {
         if (kU16) {
@@ -574,13 +595,12 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
           const int cl = cb + b * kStep;
           const int64_t r = c0 + cl;
           double v;
+          const double evf = p.use_evidence ? evidence_factor(cnt[b]) : ev[b];
           if (kU16)
-            v = gi * gc[b] * ((double)tile[cl * SM::kPitch + il] * fu[b] + (p.add_counts ? (double)cnt[b] : 0.0));
+            v = final_value_u16(gi, gc[b], (double)tile[cl * SM::kPitch + il], fu[b],
+                                p.add_counts ? (double)cnt[b] : 0.0, p.epi.coef, evf);
           else
-            v = (double)tile[cl * SM::kPitch + il];
-          v *= p.epi.coef;
-          if (p.use_evidence) v *= evidence_factor(cnt[b]);
-          else v *= ev[b];
+            v = (double)tile[cl * SM::kPitch + il] * p.epi.coef * evf;
           if (p.epi.prior) v = (1.0 - p.epi.lambda) * v + p.epi.lambda * pr[b];
           if (r + p.epi.diag_offset == i) v = 1.0; else if (v > omax) omax = v;
           if (p.epi.s_old) {
@@ -608,6 +628,114 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
         if (p.maxdiff && dmax > 0.0) atomic_max_nonneg(p.maxdiff, dmax);
         if (p.maxoff && omax > 0.0) atomic_max_nonneg(p.maxoff, omax);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SRK_CSR_FINISH: the epilogue of the second half as a streaming pass of its own.  accum[i, r] holds the
+// integer sums D[i, r] of every graph row i (SRK_CSR_ACCUM over pieces that cover every list); this kernel
+// lays a tile of them down transposed in shared memory and runs the srk_epilogue chain in the orientation of
+// the result, OUT[r, i].  Tile = 64 graph rows x 128 result rows: both sides move 512-byte runs (accum rows
+// on the way in, S_old / OUT rows on the way out), a warp keeps 8 result rows of S_old and counts in flight,
+// and the small tile (33 KB) leaves room for three CTAs per SM -- this pass is pure HBM traffic (4 + 8 + 2 + 8
+// bytes per element), it needs bytes in flight, nothing else.
+constexpr int kFI = 64, kFR = 128, kFPitch = kFI + 1, kFBatch = 8;
+__global__ void __launch_bounds__(kThreads, 3)
+csr_finish_kernel(const Params p) {
+  __shared__ uint32_t tile[kFR * kFPitch];
+  __shared__ double red[2][kWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i0 = p.row_begin + (int64_t)blockIdx.x * kFI, c0 = (int64_t)blockIdx.y * kFR;
+  const int rows_here = (int)min((int64_t)kFI, p.row_end - i0);
+
+  // ---- in: 8 graph rows per warp, 16 bytes per lane and row, all eight loads issued before the first use
+  {
+    uint4 v[kFI / kWarps];
+#pragma unroll
+    for (int q = 0; q < kFI / kWarps; ++q) {
+      const int il = warp + kWarps * q;
+      v[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (il < rows_here) v[q] = __ldcs(reinterpret_cast<const uint4*>(p.accum + (i0 + il) * p.ld_accum + c0 + 4 * lane));
+    }
+#pragma unroll
+    for (int q = 0; q < kFI / kWarps; ++q) {
+      const int il = warp + kWarps * q;
+      tile[(4 * lane) * kFPitch + il] = v[q].x; tile[(4 * lane + 1) * kFPitch + il] = v[q].y;
+      tile[(4 * lane + 2) * kFPitch + il] = v[q].z; tile[(4 * lane + 3) * kFPitch + il] = v[q].w;
+    }
+  }
+  __syncthreads();
+
+  // ---- out: 16 result rows per warp, lane l owns the graph rows i0 + 2 l, i0 + 2 l + 1
+  double dmax = 0.0, omax = 0.0;
+  const int64_t i = i0 + 2 * lane;
+  const bool in0 = i < p.row_end, in1 = i + 1 < p.row_end;
+  const double g0 = in0 ? p.g[i] : 0.0, g1 = in1 ? p.g[i + 1] : 0.0;
+  const bool vec = in1 && p.vec_aligned && ((p.ldo | p.epi.ld_s_old) & 1) == 0 && (i & 1) == 0;
+  const bool cvec = in1 && !p.counts32 && (p.ld_counts & 1) == 0 && (i & 1) == 0 && (reinterpret_cast<uintptr_t>(p.counts) & 3) == 0;
+  double* out = reinterpret_cast<double*>(p.OUT);
+  for (int rb = warp * (kFR / kWarps); rb < (warp + 1) * (kFR / kWarps); rb += kFBatch) {
+    double2 so[kFBatch];
+    uint32_t c_lo[kFBatch], c_hi[kFBatch];
+#pragma unroll
+    for (int b = 0; b < kFBatch; ++b) {
+      const int64_t r = c0 + rb + b;
+      so[b] = make_double2(0.0, 0.0); c_lo[b] = c_hi[b] = 0u;
+      if (r >= p.L || !in0) continue;
+      if (p.epi.s_old) {
+        const double* q = p.epi.s_old + r * p.epi.ld_s_old + i;
+        if (vec) so[b] = __ldcs(reinterpret_cast<const double2*>(q));
+        else { so[b].x = __ldcs(q); if (in1) so[b].y = __ldcs(q + 1); }
+      }
+      if (p.counts) {
+        if (cvec) {
+          const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.counts) + r * p.ld_counts + i));
+          c_lo[b] = w & 0xffffu; c_hi[b] = w >> 16;
+        } else {
+          c_lo[b] = load_count(p.counts, r * p.ld_counts + i, p.counts32);
+          if (in1) c_hi[b] = load_count(p.counts, r * p.ld_counts + i + 1, p.counts32);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kFBatch; ++b) {
+      const int64_t r = c0 + rb + b;
+      if (r >= p.L || !in0) continue;
+      const double fu = row_bound(p.in_unit, r), gc = p.g_col[r];
+      double v[2];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (x && !in1) { v[1] = 0.0; continue; }
+        const uint32_t cnt = x ? c_hi[b] : c_lo[b];
+        double evf = 1.0;
+        if (p.use_evidence) evf = evidence_factor(cnt);
+        else if (p.epi.evidence) evf = evidence_factor(__ldcs(p.epi.evidence + r * p.epi.ld_evidence + i + x));
+        double val = final_value_u16(x ? g1 : g0, gc, (double)tile[(rb + b) * kFPitch + 2 * lane + x], fu,
+                                     p.add_counts ? (double)cnt : 0.0, p.epi.coef, evf);
+        if (p.epi.prior) val = (1.0 - p.epi.lambda) * val + p.epi.lambda * __ldcs(p.epi.prior + r * p.epi.ld_prior + i + x);
+        if (r + p.epi.diag_offset == i + x) val = 1.0; else if (val > omax) omax = val;
+        if (p.epi.s_old) {
+          const double d = fabs(val - (x ? so[b].y : so[b].x));
+          if (d > dmax) dmax = d;                    // NaN compares false: ignored like SimRank.py:74
+        }
+        v[x] = val;
+      }
+      double* q = out + r * p.ldo + i;
+      if (vec) __stcs(reinterpret_cast<double2*>(q), make_double2(v[0], v[1]));
+      else { __stcs(q, v[0]); if (in1) __stcs(q + 1, v[1]); }
+    }
+  }
+  dmax = warp_max(dmax);
+  omax = warp_max(omax);
+  if (lane == 0) { red[0][warp] = dmax; red[1][warp] = omax; }
+  __syncthreads();
+  if (warp == 0) {
+    dmax = warp_max(lane < kWarps ? red[0][lane] : 0.0);
+    omax = warp_max(lane < kWarps ? red[1][lane] : 0.0);
+    if (lane == 0) {
+      if (p.maxdiff && dmax > 0.0) atomic_max_nonneg(p.maxdiff, dmax);
+      if (p.maxoff && omax > 0.0) atomic_max_nonneg(p.maxoff, omax);
     }
   }
 }
@@ -767,22 +895,24 @@ using namespace srk;
 
 extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   SRK_REQUIRE(a, "null args");
-  const bool accum_mode = a->mode == SRK_CSR_ACCUM;
-  SRK_REQUIRE(a->indices && a->X, "null pointer");
-  SRK_REQUIRE(accum_mode || (a->indptr && a->g && a->OUT), "null pointer");
+  const bool accum_mode = a->mode == SRK_CSR_ACCUM, finish_mode = a->mode == SRK_CSR_FINISH;
+  SRK_REQUIRE(finish_mode || (a->indices && a->X), "null pointer");
+  SRK_REQUIRE(accum_mode || (a->g && a->OUT && (finish_mode || a->indptr)), "null pointer");
   SRK_REQUIRE((a->row_lo == nullptr) == (a->row_hi == nullptr), "row_lo and row_hi come together");
   SRK_REQUIRE(0 <= a->row_begin && a->row_begin <= a->row_end && a->row_end <= a->M, "row range");
   // OUT is addressed as OUT[c * ldo + i] for i in [row_begin, row_end) only: a caller that stores just
   // those columns passes the address of (virtual) column 0, i.e. its buffer minus row_begin elements
-  SRK_REQUIRE(a->L >= 0 && a->ldx >= a->L && (accum_mode || a->ldo >= a->row_end - a->row_begin), "leading dimensions");
+  SRK_REQUIRE(a->L >= 0 && (finish_mode || a->ldx >= a->L) && (accum_mode || a->ldo >= a->row_end - a->row_begin),
+              "leading dimensions");
   SRK_REQUIRE(a->K >= 0 && a->K < (1ll << 31), "K (rows of X) out of range");
   SRK_REQUIRE(a->elem == SRK_ELEM_F64 || a->elem == SRK_ELEM_U16, "elem must be SRK_ELEM_F64 or SRK_ELEM_U16");
-  SRK_REQUIRE(a->mode == SRK_CSR_FIRST || a->mode == SRK_CSR_FINAL || accum_mode,
-              "mode must be SRK_CSR_FIRST, SRK_CSR_FINAL or SRK_CSR_ACCUM");
+  SRK_REQUIRE(a->mode == SRK_CSR_FIRST || a->mode == SRK_CSR_FINAL || accum_mode || finish_mode,
+              "mode must be SRK_CSR_FIRST, SRK_CSR_FINAL, SRK_CSR_ACCUM or SRK_CSR_FINISH");
   if (accum_mode) SRK_REQUIRE(a->row_lo && a->accum && a->accum_slot, "SRK_CSR_ACCUM needs row_lo, row_hi, accum and accum_slot");
+  if (finish_mode) SRK_REQUIRE(a->accum && !a->symmetric, "SRK_CSR_FINISH needs accum (one row of sums per graph row)");
   if (a->accum || a->accum_slot) {
     SRK_REQUIRE(a->elem == SRK_ELEM_U16, "pre-summed pieces exist in the fixed-point mode only");
-    SRK_REQUIRE(a->accum && a->accum_slot && a->ld_accum % 512 == 0 && a->ld_accum >= a->L &&
+    SRK_REQUIRE(a->accum && (a->accum_slot || finish_mode) && a->ld_accum % 512 == 0 && a->ld_accum >= a->L &&
                     ((uintptr_t)a->accum % 32) == 0,
                 "accum: 32-byte aligned, ld_accum a multiple of 512 and >= L");
   }
@@ -794,7 +924,7 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
     SRK_REQUIRE(a->row_begin == 0 && a->row_end == a->M && a->L == a->M && a->epi.prior == nullptr &&
                     a->epi.diag_offset == 0 && a->ldo >= a->L,
                 "the symmetric second half needs the whole square problem and no prior");
-  if (a->elem == SRK_ELEM_U16 && a->mode == SRK_CSR_FINAL) SRK_REQUIRE(a->g_col, "u16 FINAL needs g_col");
+  if (a->elem == SRK_ELEM_U16 && (a->mode == SRK_CSR_FINAL || finish_mode)) SRK_REQUIRE(a->g_col, "u16 FINAL needs g_col");
   if (a->row_end == a->row_begin || a->L == 0) return SRK_OK;
 
   gat::Params p;
@@ -810,7 +940,7 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   SRK_REQUIRE(p.qmax >= 1.0 && p.qmax <= 65535.0, "qmax must be in 1..65535");
   p.counts = a->counts; p.ld_counts = a->ld_counts; p.counts32 = a->counts_bits == 32;
   p.add_counts = a->add_counts; p.use_evidence = a->use_evidence;
-  if (a->mode == SRK_CSR_FINAL) { p.epi = to_dev(a->epi); p.maxdiff = a->epi.maxdiff; p.maxoff = a->epi.maxoff; }
+  if (a->mode == SRK_CSR_FINAL || finish_mode) { p.epi = to_dev(a->epi); p.maxdiff = a->epi.maxdiff; p.maxoff = a->epi.maxoff; }
   const int64_t esz = a->elem == SRK_ELEM_U16 ? 2 : 8;
   // TMA needs 16-byte aligned rows
   p.tma = ((uintptr_t)a->X % 16 == 0) && ((a->ldx * esz) % 16 == 0);
@@ -825,6 +955,13 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   // 8-byte tile per element in shared memory and takes 16 graph rows per CTA instead of 32.
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = a->row_end - a->row_begin;
+  if (finish_mode) {
+    const int64_t fx = (rows + gat::kFI - 1) / gat::kFI, fy = (a->L + gat::kFR - 1) / gat::kFR;
+    SRK_REQUIRE(fy <= 65535, "too many column panels");
+    gat::csr_finish_kernel<<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
+    SRK_CUDA_OK(cudaGetLastError());
+    return SRK_OK;
+  }
   const int mode = accum_mode ? gat::MODE_ACCUM
                               : a->mode == SRK_CSR_FIRST ? gat::MODE_FIRST : (sym ? gat::MODE_FINAL_SYM : gat::MODE_FINAL);
   // (Narrower panels were tried for operands with so many rows that a 1 KB-wide panel cannot stay in L2

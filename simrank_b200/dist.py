@@ -738,6 +738,14 @@ class ShardedCsr16Half(ShardedCsrHalf):
         self._send16 = self._recv16 = None
         # hub rows (the popular items of a ratings graph) are pre-summed in pieces, see engine.ListSplit
         self.split = ListSplit.plan(self.indptr, self.indices, self.n_in, int(op.deg.max()) if op.deg.size else 0)
+        # The second half runs as SRK_CSR_ACCUM over EVERY list + SRK_CSR_FINISH (include/simrank_b200.h): the
+        # gather launch has no epilogue and no transposition tile (15.9 TB/s on BASELINE cfg5's S1 shape, the
+        # L2 roof, against 9.0 for the fused launch whose 16-row CTAs idle through their epilogues), the
+        # epilogue streams afterwards: 76.8 -> 60.0 ms there, 2.95 -> 2.14 ms on one rank of cfg4 over 8 GPUs
+        # (profiles/r2_csr_shapes_finish.jsonl).  SRK_FINAL_VIA_ACCUM=0 keeps the fused launch.
+        self.split_all = None
+        if os.environ.get("SRK_FINAL_VIA_ACCUM", "1") == "1" and op.nnz:
+            self.split_all = ListSplit.plan(self.indptr, self.indices, self.n_in, int(op.deg.max()), all_rows=True)
 
     _dense_pattern = ShardedHalf._dense_pattern
     _pattern_counts = ShardedHalf._pattern_counts
@@ -826,7 +834,11 @@ class ShardedCsr16Half(ShardedCsrHalf):
             e.s_old, e.ld_s_old = self.S.data_ptr(), self.ld
             e.maxdiff, e.maxoff = self.scal.data_ptr(), self.scal.data_ptr() + 8
             e.diag_offset = self.row0
-            if self.split is not None:
+            if self.split_all is not None:
+                self.split_all.accumulate(lib, self.indices.data_ptr(), b.X, b.ldx, b.L, b.K, qmax)
+                b.mode = _lib.SRK_CSR_FINISH
+                b.accum, b.ld_accum = self.split_all._accum.data_ptr(), self.split_all._accum.shape[1]
+            elif self.split is not None:
                 self.split.accumulate(lib, self.indices.data_ptr(), b.X, b.ldx, b.L, b.K, qmax)
                 self.split.attach(b)
             _lib.check(lib.srk_csr_half(C.byref(b), _stream()), "srk_csr_half(u16, second)")

@@ -311,15 +311,22 @@ class ListSplit:
     ms and 41 -> 12 ms), rows of 256+ in pieces of 512 when it does (S1's halves: 91 -> 80 and 13.3 -> 11.8
     ms; there the gain is balance inside the CTAs, whose rows differ tenfold in length)."""
 
-    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, K: int, min_deg: int, piece: int, ranges: int):
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, K: int, min_deg: int, piece: int, ranges: int,
+                 all_rows: bool = False):
         dev = indptr.device
         M = indptr.numel() - 1
         deg = indptr[1:] - indptr[:-1]
-        hub = deg >= min_deg
-        self.rows = int(hub.sum().item())
+        # all_rows: EVERY list goes through the pieces and slot = row (the sums of the whole operator end up in
+        # accum, for SRK_CSR_FINISH); otherwise only the hub rows, numbered in order
+        hub = deg >= (1 if all_rows else min_deg)
+        self.all_rows = bool(all_rows)
+        self.rows = M if all_rows else int(hub.sum().item())
         self.row_lo = indptr[:-1].clone()
         self.row_hi = torch.where(hub, self.row_lo, indptr[1:])                      # hubs: nothing left to gather
-        slot = torch.cumsum(hub.to(torch.int32), 0, dtype=torch.int32) - 1
+        if all_rows:
+            slot = torch.arange(M, dtype=torch.int32, device=dev)
+        else:
+            slot = torch.cumsum(hub.to(torch.int32), 0, dtype=torch.int32) - 1
         self.slot = torch.where(hub, slot, torch.full_like(slot, -1))
         hub_rows = torch.nonzero(hub).flatten()
         hub_deg = deg[hub_rows]
@@ -343,32 +350,46 @@ class ListSplit:
         k = torch.arange(pseg.numel(), device=dev) - pfirst[pseg]
         lo = seg_lo[pseg] + k * size[pseg]
         hi = torch.minimum(lo + size[pseg], (seg_lo + seg_len)[pseg])
-        order = torch.argsort(seg_key[pseg] % ranges, stable=True)                  # range by range
+        powner = torch.div(seg_key[pseg], ranges, rounding_mode="floor")            # hub row (position in hub_rows) of a piece
+        pslot = slot[hub_rows][powner].to(torch.int64)
+        per_row = torch.zeros(M, dtype=torch.int64, device=dev)
+        per_row.index_add_(0, hub_rows[powner], torch.ones_like(powner))
+        alone = per_row[hub_rows[powner]] == 1                                      # the piece is its row's whole list
+        pslot = torch.where(alone, -pslot - 1, pslot)                               # stored, not added
+        # range by range (pieces that run together gather from one range of X); inside a range the long pieces
+        # first, so that the 8 pieces of a CTA are alike and the short ones fill the end of the launch
+        order = torch.argsort((seg_key[pseg] % ranges) * (1 << 32) - (hi - lo), stable=True)
         self.piece_lo, self.piece_hi = lo[order].contiguous(), hi[order].contiguous()
-        # the k-th hub row owns slot k
-        self.piece_slot = torch.div(seg_key[pseg], ranges, rounding_mode="floor")[order].to(torch.int32).contiguous()
+        self.piece_slot = pslot[order].to(torch.int32).contiguous()
         self.pieces = int(self.piece_lo.numel())
+        # slots that are added to (or never written: empty lists) start from zero
+        needs_zero = per_row != 1
+        self.zero_slots = slot[needs_zero & (hub | all_rows)].to(torch.int64) if all_rows else None
         self.ranges, self.piece, self.min_deg = ranges, piece, min_deg
         self._accum = None
 
     @classmethod
-    def plan(cls, indptr: torch.Tensor, indices: torch.Tensor, K: int, max_deg: int):
-        """A split for this operator, or None when no row is long enough to need one."""
+    def plan(cls, indptr: torch.Tensor, indices: torch.Tensor, K: int, max_deg: int, all_rows: bool = False):
+        """A split for this operator, or None when no row is long enough to need one (``all_rows``: always a
+        plan, every list in pieces)."""
         fits = K * 1024 <= 64 * 2 ** 20                               # a 1 KB-wide panel of X stays in L2
         min_deg = int(os.environ.get("SRK_SPLIT_MIN", "256" if fits else "1024"))
-        if min_deg <= 0 or max_deg < min_deg:
+        if not all_rows and (min_deg <= 0 or max_deg < min_deg):
             return None
         piece = max(4, int(os.environ.get("SRK_SPLIT_PIECE", "512" if fits else "256")))
         range_mb = float(os.environ.get("SRK_SPLIT_RANGE_MB", "32"))
         ranges = max(1, int(np.ceil(K * 1024 / (range_mb * 2 ** 20))))
-        return cls(indptr, indices, K, min_deg, piece, ranges)
+        return cls(indptr, indices, K, min_deg, piece, ranges, all_rows)
 
     def accumulate(self, lib, indices_ptr, x_ptr, ldx: int, L: int, K: int, qmax: float) -> None:
         """Zero the sums and add every piece's column sums of X[:, :L] (one launch)."""
         ld = _round_up(max(L, 1), 512)
         if self._accum is None or self._accum.shape[1] < ld:
             self._accum = torch.empty((self.rows, ld), dtype=torch.int32, device=self.piece_lo.device)
-        self._accum.zero_()
+        if self.zero_slots is None:
+            self._accum.zero_()
+        elif self.zero_slots.numel():
+            self._accum.index_fill_(0, self.zero_slots, 0)
         a = _lib.CsrArgs()
         a.elem, a.mode = _lib.SRK_ELEM_U16, _lib.SRK_CSR_ACCUM
         a.indices = indices_ptr

@@ -428,3 +428,44 @@ def test_accum_mode_rejects_bad_arguments(dev):
     a.X, a.ldx, a.L, a.OUT, a.ldo = X.data_ptr(), 24, 20, X.data_ptr(), 24
     a.accum, a.ld_accum, a.accum_slot = acc.data_ptr(), 500, acc.data_ptr()
     assert lib.srk_csr_half(C.byref(a), engine._stream()) == -1 and b"ld_accum" in lib.srk_last_error()
+
+
+@pytest.mark.parametrize("piece,ranges", [(16, 1), (64, 3)])
+def test_second_half_as_accum_plus_finish_is_bit_identical(dev, piece, ranges):
+    """SRK_CSR_ACCUM over EVERY neighbour list (single-piece lists stored, the others added) followed by
+    SRK_CSR_FINISH gives the matrix of one SRK_CSR_FINAL launch, bit for bit (transposed store, a row block
+    of the output with its diag_offset)."""
+    rng = np.random.default_rng(piece)
+    n, r0, L = 700, 32, 600
+    op, A = _skewed_graph(rng, n, n, [(3, 650), (200, 333), (699, 257), (11, 0), (12, 1)])
+    dop = engine.DeviceOperator(op, dev)
+    ldx, ld = engine._round_up(L, 8), engine._round_up(n, 16)
+    X = _u16(rng.integers(0, 65536, (n, ldx), dtype=np.int64)).to(dev)
+    c16 = torch.from_numpy(rng.integers(0, 40, (L, n)).astype(np.uint16).view(np.int16)).to(dev)
+    S_old = rng.random((L, n))
+    ud, gd = torch.from_numpy(rng.random(L) * 1e-5).to(dev), torch.from_numpy(rng.random(L) * 0.3).to(dev)
+    res = []
+    for via_accum in (False, True):
+        out = torch.zeros((L, ld), dtype=torch.float64, device=dev)
+        out[:, :n] = torch.from_numpy(S_old)
+        scal = torch.zeros(2, dtype=torch.float64, device=dev)
+        a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL)
+        a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), ldx, L, n, out.data_ptr(), ld
+        a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+        a.g_col = gd.data_ptr()
+        a.counts, a.ld_counts, a.counts_bits, a.add_counts, a.use_evidence = c16.data_ptr(), n, 16, 1, 1
+        a.epi.coef = 0.8
+        a.epi.s_old, a.epi.ld_s_old = out.data_ptr(), ld
+        a.epi.maxdiff, a.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
+        a.epi.diag_offset = r0
+        if via_accum:
+            sp = engine.ListSplit(dop.indptr, dop.indices, n, 1, piece, ranges, all_rows=True)
+            assert sp.rows == n and (sp.piece_slot < 0).any() and (sp.piece_slot >= 0).any()
+            sp.accumulate(_lib.load(), a.indices, a.X, a.ldx, a.L, a.K, 65535.0)
+            a.mode, a.accum, a.ld_accum = _lib.SRK_CSR_FINISH, sp._accum.data_ptr(), sp._accum.shape[1]
+        _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+        torch.cuda.synchronize()
+        res.append((out[:, :n].cpu().numpy(), scal.tolist()))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1]
+    assert res[0][0][5, r0 + 5] == 1.0

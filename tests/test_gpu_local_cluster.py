@@ -72,16 +72,18 @@ def test_bipartite_csr16_shards_with_split_hub_rows_are_bit_identical(monkeypatc
     (engine.ListSplit).  Integer sums in another order: the sharded result does not change by a bit."""
     df = synth.config_frame("cfg5", scale=1 / 32)
     out = []
-    for min_deg in ("0", "64"):
+    for min_deg, via_accum in (("0", "0"), ("64", "0"), ("64", "1")):
         monkeypatch.setenv("SRK_SPLIT_MIN", min_deg)
+        monkeypatch.setenv("SRK_FINAL_VIA_ACCUM", via_accum)       # second half as ACCUM + FINISH
         monkeypatch.setenv("SRK_SPLIT_PIECE", "48")
         monkeypatch.setenv("SRK_SPLIT_RANGE_MB", "1")
         res = _fit_sharded(3, lambda g: M.BipartitleSimRankPP(mode="csr16", sharded=g, gather="local"),
                            dict(data=df, weighted=True, iterations=3, eps=0.0, verbose=False))
         out.append([(S1.to_numpy(), S2.to_numpy()) for (S1, S2), _ in res])
-    for (a1, a2), (b1, b2) in zip(*out):
-        np.testing.assert_array_equal(a1, b1)
-        np.testing.assert_array_equal(a2, b2)
+    for other in out[1:]:
+        for (a1, a2), (b1, b2) in zip(out[0], other):
+            np.testing.assert_array_equal(a1, b1)
+            np.testing.assert_array_equal(a2, b2)
 
 
 def test_local_cluster_propagates_errors():
