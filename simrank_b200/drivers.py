@@ -218,8 +218,9 @@ class _PinnedPool:
     gigabyte costs as much as copying it, so a buffer whose last user is gone (the DataFrame built on
     it has been dropped: a weak reference to the ndarray the frame was built on tells) is
     handed out again; a buffer that is still referenced is never reused.  Bounded by
-    SIMRANK_B200_PINNED_POOL_BYTES (default 4 GiB): larger results get a fresh allocation that is not
-    kept."""
+    SIMRANK_B200_PINNED_POOL_BYTES (default 16 GiB, so that the 8.6 GB result of BASELINE cfg4 on one GPU
+    is kept: page-locking it afresh cost 0.03 - 0.13 s of a 0.9 s fit); larger results get a fresh
+    allocation that is not kept."""
 
     def __init__(self):
         self.entries = []                                      # [base tensor, weakref to the ndarray handed out]
@@ -241,7 +242,7 @@ class _PinnedPool:
         base = torch.empty(n, dtype=dtype, pin_memory=True)
         view = base.view(shape)
         arr = view.numpy()
-        if nbytes <= int(os.environ.get("SIMRANK_B200_PINNED_POOL_BYTES", 4 << 30)):
+        if nbytes <= int(os.environ.get("SIMRANK_B200_PINNED_POOL_BYTES", 16 << 30)):
             self.entries = self.entries[-3:] + [[base, weakref.ref(arr)]]
         return view, arr
 
