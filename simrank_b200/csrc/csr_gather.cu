@@ -641,7 +641,8 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 // and the small tile (33 KB) leaves room for three CTAs per SM -- this pass is pure HBM traffic (4 + 8 + 2 + 8
 // bytes per element), it needs bytes in flight, nothing else.
 constexpr int kFI = 64, kFR = 128, kFPitch = kFI + 1, kFBatch = 8;
-__global__ void __launch_bounds__(kThreads, 3)
+template <int kCtasPerSM>
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
 csr_finish_kernel(const Params p) {
   __shared__ uint32_t tile[kFR * kFPitch];
   __shared__ double red[2][kWarps];
@@ -677,7 +678,7 @@ csr_finish_kernel(const Params p) {
   double* out = reinterpret_cast<double*>(p.OUT);
   for (int rb = warp * (kFR / kWarps); rb < (warp + 1) * (kFR / kWarps); rb += kFBatch) {
     double2 so[kFBatch];
-    uint32_t c_lo[kFBatch], c_hi[kFBatch];
+    uint32_t c_lo[kFBatch], c_hi[kFBatch];                     // (16-bit counts: both in c_lo, split when used)
 #pragma unroll
     for (int b = 0; b < kFBatch; ++b) {
       const int64_t r = c0 + rb + b;
@@ -690,8 +691,7 @@ csr_finish_kernel(const Params p) {
       }
       if (p.counts) {
         if (cvec) {
-          const uint32_t w = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.counts) + r * p.ld_counts + i));
-          c_lo[b] = w & 0xffffu; c_hi[b] = w >> 16;
+          c_lo[b] = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.counts) + r * p.ld_counts + i));
         } else {
           c_lo[b] = load_count(p.counts, r * p.ld_counts + i, p.counts32);
           if (in1) c_hi[b] = load_count(p.counts, r * p.ld_counts + i + 1, p.counts32);
@@ -707,7 +707,7 @@ csr_finish_kernel(const Params p) {
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         if (x && !in1) { v[1] = 0.0; continue; }
-        const uint32_t cnt = x ? c_hi[b] : c_lo[b];
+        const uint32_t cnt = cvec ? (x ? c_lo[b] >> 16 : c_lo[b] & 0xffffu) : (x ? c_hi[b] : c_lo[b]);
         double evf = 1.0;
         if (p.use_evidence) evf = evidence_factor(cnt);
         else if (p.epi.evidence) evf = evidence_factor(__ldcs(p.epi.evidence + r * p.epi.ld_evidence + i + x));
@@ -958,7 +958,9 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   if (finish_mode) {
     const int64_t fx = (rows + gat::kFI - 1) / gat::kFI, fy = (a->L + gat::kFR - 1) / gat::kFR;
     SRK_REQUIRE(fy <= 65535, "too many column panels");
-    gat::csr_finish_kernel<<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
+    // three CTAs per SM (80 registers) or four (64, with spills): SRK_CSR_FLAGS & 4 selects four, for A/B runs
+    if (p.flags & 4) gat::csr_finish_kernel<4><<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
+    else gat::csr_finish_kernel<3><<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
     SRK_CUDA_OK(cudaGetLastError());
     return SRK_OK;
   }
