@@ -34,7 +34,7 @@ extern "C" {
 #define SRK_ERR_UNSUPPORTED (-3)
 
 /* ABI version of this header; srk_abi_version() must return the same value. */
-#define SRK_ABI_VERSION 11
+#define SRK_ABI_VERSION 12
 
 int srk_abi_version(void);
 const char* srk_last_error(void);
@@ -148,6 +148,12 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
  *                       16 rows spends a third of its life in the epilogue with its ring idle; the ACCUM
  *                       launch has no epilogue and 8 similar pieces per CTA).  indptr / indices / X are not
  *                       used.
+ *                       symmetric != 0: the symmetric second half -- ACCUM was run with symmetric != 0 (a
+ *                       piece of row i skips the column panels entirely left of column i) and FINISH
+ *                       computes the pairs r >= i from accum[i, r], storing each value at (i, r) and, through a
+ *                       shared-memory transposition, at (r, i).
+ *   mode SRK_CSR_FINISH_FIRST  the epilogue of SRK_CSR_FIRST alone: OUT[c, i] = rint(accum[i, c] * unit(c) * qmax /
+ *                       out_bound(i)) as uint16.
  * accum is zeroed by the caller where pieces are added; ld_accum is a multiple of 512 and >= L rounded up to
  * 512.  Results are bit-identical to the unsplit call: the same integers are added in another order.  */
 #define SRK_ELEM_F64 0
@@ -156,6 +162,7 @@ int srk_csr_half_f64(const int64_t* indptr, const int32_t* indices, const double
 #define SRK_CSR_FINAL 1
 #define SRK_CSR_ACCUM 2
 #define SRK_CSR_FINISH 3
+#define SRK_CSR_FINISH_FIRST 4
 typedef struct srk_csr_args {
   int elem, mode, symmetric;
   const int64_t* indptr; const int32_t* indices; const double* g;

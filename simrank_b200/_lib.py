@@ -11,7 +11,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsimrank_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 SRK_X2_MID, SRK_X2_FINAL, SRK_X2_COUNTS = 0, 1, 2
 SRK_X2_DIRECT, SRK_X2_SYMMETRIC, SRK_X2_TRANSPOSED = 0, 1, 2
@@ -43,7 +43,7 @@ class RowBound(C.Structure):
 
 
 SRK_ELEM_F64, SRK_ELEM_U16 = 0, 1
-SRK_CSR_FIRST, SRK_CSR_FINAL, SRK_CSR_ACCUM, SRK_CSR_FINISH = 0, 1, 2, 3
+SRK_CSR_FIRST, SRK_CSR_FINAL, SRK_CSR_ACCUM, SRK_CSR_FINISH, SRK_CSR_FINISH_FIRST = 0, 1, 2, 3, 4
 
 
 class CsrArgs(C.Structure):

@@ -119,6 +119,7 @@ struct Params {
   EpilogueDev epi; double* maxdiff; double* maxoff;
   int tma;                     // rows of X are 16-byte aligned: TMA gather; else plain loads
   int vec_aligned;             // OUT, S_old and counts are 16-byte aligned (vector epilogue of the symmetric half)
+  int upper_only;              // ACCUM for a symmetric second half: a piece of row i skips the panels left of column i
   int flags;                   // SRK_CSR_FLAGS (A/B profiling): 1 = default L2 policy for the gather
   int64_t tiles_x;             // row tiles of the problem (symmetric second half: triangular 1-D grid)
 };
@@ -345,6 +346,10 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
         if (lane == 0) r = atomicAdd(&next_row, 1);
         r = __shfl_sync(0xffffffffu, r, 0);
         if (r >= rows_here) return;
+        if (MODE == MODE_ACCUM && p.upper_only) {                       // nothing of this panel lies at or right of
+          const int sl = p.accum_slot[i0 + r];                          // the diagonal of the piece's row (slot = row)
+          if ((int64_t)(sl >= 0 ? sl : -sl - 1) >= c0 + TC) continue;
+        }
         if (lane == 0) fifo[warp][wi] = (uint8_t)r;
         ++wi;
         ip = p.rowbeg[i0 + r];
@@ -640,6 +645,16 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
 // on the way in, S_old / OUT rows on the way out), a warp keeps 8 result rows of S_old and counts in flight,
 // and the small tile (33 KB) leaves room for three CTAs per SM -- this pass is pure HBM traffic (4 + 8 + 2 + 8
 // bytes per element), it needs bytes in flight, nothing else.
+// csr_finish_first_kernel runs as many short CTAs; the tile a CTA reads was requested from DRAM by the CTA that
+// ran kPrefetchAhead tiles earlier (about one wave: CTAs are dispatched in order), so its own loads see L2
+// latency: 2.81 -> 2.49 ms at cfg4.  (The same trick made the two FINISH kernels, which stream three inputs,
+// 8-14 % slower -- profiles/r2_csr_shapes_prefetch.jsonl -- and is not used there.)
+constexpr int kPrefetchAhead = 148 * 3;
+__device__ __forceinline__ void prefetch_block(const void* base, int64_t pitch_bytes, int rows, int row_bytes) {
+  const int per_row = (row_bytes + 127) / 128;
+  for (int t = threadIdx.x; t < rows * per_row; t += blockDim.x)
+    prefetch_l2(reinterpret_cast<const uint8_t*>(base) + (int64_t)(t / per_row) * pitch_bytes + (t % per_row) * 128);
+}
 constexpr int kFI = 64, kFR = 128, kFPitch = kFI + 1, kFBatch = 8;
 template <int kCtasPerSM>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM)
@@ -724,6 +739,173 @@ csr_finish_kernel(const Params p) {
       double* q = out + r * p.ldo + i;
       if (vec) __stcs(reinterpret_cast<double2*>(q), make_double2(v[0], v[1]));
       else { __stcs(q, v[0]); if (in1) __stcs(q + 1, v[1]); }
+    }
+  }
+  dmax = warp_max(dmax);
+  omax = warp_max(omax);
+  if (lane == 0) { red[0][warp] = dmax; red[1][warp] = omax; }
+  __syncthreads();
+  if (warp == 0) {
+    dmax = warp_max(lane < kWarps ? red[0][lane] : 0.0);
+    omax = warp_max(lane < kWarps ? red[1][lane] : 0.0);
+    if (lane == 0) {
+      if (p.maxdiff && dmax > 0.0) atomic_max_nonneg(p.maxdiff, dmax);
+      if (p.maxoff && omax > 0.0) atomic_max_nonneg(p.maxoff, omax);
+    }
+  }
+}
+
+// SRK_CSR_FINISH after a FIRST-type ACCUM: T = (A X)^T re-quantised, OUT[c, i] = rint(accum[i, c] * unit(c) *
+// qmax / out_bound(i)) as uint16 -- the epilogue of MODE_FIRST as a streaming transposition (64 x 128 tile).
+__global__ void __launch_bounds__(kThreads, 3)
+csr_finish_first_kernel(const Params p) {
+  __shared__ uint16_t tile[kFR * (kFI + 2)];
+  constexpr int kP = kFI + 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i0 = p.row_begin + (int64_t)blockIdx.x * kFI, c0 = (int64_t)blockIdx.y * kFR;
+  const int rows_here = (int)min((int64_t)kFI, p.row_end - i0);
+  {
+    const int64_t nxt = (int64_t)blockIdx.y * gridDim.x + blockIdx.x + kPrefetchAhead;
+    const int64_t ni = p.row_begin + (nxt % gridDim.x) * kFI, nc = (nxt / gridDim.x) * kFR;
+    if (nc < p.L && !(p.flags & 8))
+      prefetch_block(p.accum + ni * p.ld_accum + nc, p.ld_accum * 4, (int)min((int64_t)kFI, p.row_end - ni), kFR * 4);
+  }
+  {
+    uint4 v[kFI / kWarps];
+    double inv[kFI / kWarps];
+#pragma unroll
+    for (int q = 0; q < kFI / kWarps; ++q) {
+      const int il = warp + kWarps * q;
+      v[q] = make_uint4(0u, 0u, 0u, 0u);
+      inv[q] = 0.0;
+      if (il < rows_here) {
+        v[q] = __ldcs(reinterpret_cast<const uint4*>(p.accum + (i0 + il) * p.ld_accum + c0 + 4 * lane));
+        const double bo = row_bound(p.out_bound, i0 + il);
+        inv[q] = bo > 0.0 ? p.qmax / bo : 0.0;
+      }
+    }
+    double u[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) u[x] = c0 + 4 * lane + x < p.L ? row_bound(p.in_unit, c0 + 4 * lane + x) : 0.0;
+#pragma unroll
+    for (int q = 0; q < kFI / kWarps; ++q) {
+      const int il = warp + kWarps * q;
+      const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        double t = rint((double)w[x] * u[x] * inv[q]);               // the expression of MODE_FIRST
+        if (!(t > 0.0)) t = 0.0;
+        if (t > p.qmax) t = p.qmax;
+        tile[(4 * lane + x) * kP + il] = (uint16_t)(unsigned)t;
+      }
+    }
+  }
+  __syncthreads();
+  // out: a warp stores 16 rows of OUT, lane l the columns i0 + 2 l, i0 + 2 l + 1 (4 bytes per lane)
+  const int64_t i = i0 + 2 * lane;
+  uint16_t* out = reinterpret_cast<uint16_t*>(p.OUT);
+  const bool pair = i + 1 < p.row_end && (p.ldo & 1) == 0 && (i & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+  for (int rb = warp * (kFR / kWarps); rb < (warp + 1) * (kFR / kWarps); ++rb) {
+    const int64_t r = c0 + rb;
+    if (r >= p.L || i >= p.row_end) continue;
+    const uint32_t lo = tile[rb * kP + 2 * lane], hi = tile[rb * kP + 2 * lane + 1];
+    if (pair) *reinterpret_cast<uint32_t*>(out + r * p.ldo + i) = lo | (hi << 16);
+    else { out[r * p.ldo + i] = (uint16_t)lo; if (i + 1 < p.row_end) out[r * p.ldo + i + 1] = (uint16_t)hi; }
+  }
+}
+
+// SRK_CSR_FINISH of a SYMMETRIC second half: accum[i, r] holds D[i, r] for every r >= i (ACCUM with
+// upper_only).  Tiles (64 rows i) x (64 columns r) with a column at or right of a row: inputs and the result row
+// are read / written along r, the mirror image goes through a shared-memory transposition, so both copies
+// leave as whole 512-byte runs (the fused symmetric launch scatters the mirror 8 bytes at a time).
+constexpr int kSI = 64;
+__global__ void __launch_bounds__(kThreads, 3)
+csr_finish_sym_kernel(const Params p) {
+  __shared__ double tile[kSI * (kSI + 1)];
+  __shared__ double red[2][kWarps];
+  constexpr int kP = kSI + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // triangular numbering of the block pairs (bi <= br)
+  const int64_t t = blockIdx.x;
+  int64_t br = (int64_t)((sqrt(1.0 + 8.0 * (double)t) - 1.0) * 0.5);
+  while (br * (br + 1) / 2 > t) --br;
+  while ((br + 1) * (br + 2) / 2 <= t) ++br;
+  const int64_t bi = t - br * (br + 1) / 2;
+  const int64_t i0 = bi * kSI, r0 = br * kSI;
+  const int64_t r = r0 + 2 * lane;                                     // this lane's two columns
+  const bool in0 = r < p.L, in1 = r + 1 < p.L;
+  const bool vec = in1 && p.vec_aligned && ((p.ldo | p.epi.ld_s_old) & 1) == 0;
+  const bool cvec = in1 && !p.counts32 && (p.ld_counts & 1) == 0 && (reinterpret_cast<uintptr_t>(p.counts) & 3) == 0;
+  const double fu0 = in0 ? row_bound(p.in_unit, r) : 0.0, fu1 = in1 ? row_bound(p.in_unit, r + 1) : 0.0;
+  const double gc0 = in0 ? p.g_col[r] : 0.0, gc1 = in1 ? p.g_col[r + 1] : 0.0;
+  double* out = reinterpret_cast<double*>(p.OUT);
+  double dmax = 0.0, omax = 0.0;
+  constexpr int kRows = kSI / kWarps;                                  // 8 rows per warp, all loads first
+  uint2 sum[kRows];
+  double2 so[kRows];
+  uint32_t cw[kRows], ch[kRows];
+#pragma unroll
+  for (int q = 0; q < kRows; ++q) {
+    const int64_t i = i0 + warp * kRows + q;
+    sum[q] = make_uint2(0u, 0u); so[q] = make_double2(0.0, 0.0); cw[q] = ch[q] = 0u;
+    if (i >= p.row_end || !in0) continue;
+    sum[q] = __ldcs(reinterpret_cast<const uint2*>(p.accum + i * p.ld_accum + r));
+    if (p.epi.s_old) {
+      const double* s = p.epi.s_old + i * p.epi.ld_s_old + r;
+      if (vec) so[q] = __ldcs(reinterpret_cast<const double2*>(s));
+      else { so[q].x = __ldcs(s); if (in1) so[q].y = __ldcs(s + 1); }
+    }
+    if (p.counts) {
+      if (cvec) cw[q] = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p.counts) + i * p.ld_counts + r));
+      else { cw[q] = load_count(p.counts, i * p.ld_counts + r, p.counts32); if (in1) ch[q] = load_count(p.counts, i * p.ld_counts + r + 1, p.counts32); }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kRows; ++q) {
+    const int il = warp * kRows + q;
+    const int64_t i = i0 + il;
+    double v[2] = {0.0, 0.0};
+    if (i < p.row_end && in0) {
+      const double gi = p.g[i];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int64_t c = r + x;
+        if ((x && !in1) || c < i) continue;                            // left of the diagonal: the mirror of (c, i)
+        const uint32_t cnt = cvec ? (x ? cw[q] >> 16 : cw[q] & 0xffffu) : (x ? ch[q] : cw[q]);
+        double evf = 1.0;
+        if (p.use_evidence) evf = evidence_factor(cnt);
+        else if (p.epi.evidence) evf = evidence_factor(__ldcs(p.epi.evidence + i * p.epi.ld_evidence + c));
+        double val = final_value_u16(gi, x ? gc1 : gc0, (double)(x ? sum[q].y : sum[q].x), x ? fu1 : fu0,
+                                     p.add_counts ? (double)cnt : 0.0, p.epi.coef, evf);
+        if (c == i) val = 1.0; else if (val > omax) omax = val;
+        if (p.epi.s_old) {
+          const double d = fabs(val - (x ? so[q].y : so[q].x));
+          if (d > dmax) dmax = d;                                      // NaN compares false: ignored like SimRank.py:74
+        }
+        v[x] = val;
+      }
+      // the row itself: both columns at or right of the diagonal -> one 16-byte store
+      double* o = out + i * p.ldo + r;
+      if (vec && r >= i) __stcs(reinterpret_cast<double2*>(o), make_double2(v[0], v[1]));
+      else { if (r >= i) __stcs(o, v[0]); if (in1 && r + 1 >= i) __stcs(o + 1, v[1]); }
+    }
+    tile[(2 * lane) * kP + il] = v[0];
+    tile[(2 * lane + 1) * kP + il] = v[1];
+  }
+  __syncthreads();
+  // mirror: element (c, i) for c > i; a warp writes 8 rows c of the result, lane l the columns i0 + 2 l, + 1
+  {
+    const int64_t i = i0 + 2 * lane;
+#pragma unroll
+    for (int q = 0; q < kRows; ++q) {
+      const int cl = warp * kRows + q;
+      const int64_t c = r0 + cl;
+      if (c >= p.L || i >= p.row_end) continue;
+      const double a = tile[cl * kP + 2 * lane], b = tile[cl * kP + 2 * lane + 1];
+      double* o = out + c * p.ldo + i;
+      const bool two = i + 1 < p.row_end;
+      if (two && c > i + 1 && p.vec_aligned && (p.ldo & 1) == 0) __stcs(reinterpret_cast<double2*>(o), make_double2(a, b));
+      else { if (c > i) __stcs(o, a); if (two && c > i + 1) __stcs(o + 1, b); }
     }
   }
   dmax = warp_max(dmax);
@@ -895,7 +1077,8 @@ using namespace srk;
 
 extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   SRK_REQUIRE(a, "null args");
-  const bool accum_mode = a->mode == SRK_CSR_ACCUM, finish_mode = a->mode == SRK_CSR_FINISH;
+  const bool accum_mode = a->mode == SRK_CSR_ACCUM, finish_first = a->mode == SRK_CSR_FINISH_FIRST;
+  const bool finish_mode = a->mode == SRK_CSR_FINISH || finish_first;
   SRK_REQUIRE(finish_mode || (a->indices && a->X), "null pointer");
   SRK_REQUIRE(accum_mode || (a->g && a->OUT && (finish_mode || a->indptr)), "null pointer");
   SRK_REQUIRE((a->row_lo == nullptr) == (a->row_hi == nullptr), "row_lo and row_hi come together");
@@ -907,9 +1090,9 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   SRK_REQUIRE(a->K >= 0 && a->K < (1ll << 31), "K (rows of X) out of range");
   SRK_REQUIRE(a->elem == SRK_ELEM_F64 || a->elem == SRK_ELEM_U16, "elem must be SRK_ELEM_F64 or SRK_ELEM_U16");
   SRK_REQUIRE(a->mode == SRK_CSR_FIRST || a->mode == SRK_CSR_FINAL || accum_mode || finish_mode,
-              "mode must be SRK_CSR_FIRST, SRK_CSR_FINAL, SRK_CSR_ACCUM or SRK_CSR_FINISH");
+              "mode must be SRK_CSR_FIRST, SRK_CSR_FINAL, SRK_CSR_ACCUM, SRK_CSR_FINISH or SRK_CSR_FINISH_FIRST");
   if (accum_mode) SRK_REQUIRE(a->row_lo && a->accum && a->accum_slot, "SRK_CSR_ACCUM needs row_lo, row_hi, accum and accum_slot");
-  if (finish_mode) SRK_REQUIRE(a->accum && !a->symmetric, "SRK_CSR_FINISH needs accum (one row of sums per graph row)");
+  if (finish_mode) SRK_REQUIRE(a->accum, "SRK_CSR_FINISH needs accum (one row of sums per graph row)");
   if (a->accum || a->accum_slot) {
     SRK_REQUIRE(a->elem == SRK_ELEM_U16, "pre-summed pieces exist in the fixed-point mode only");
     SRK_REQUIRE(a->accum && (a->accum_slot || finish_mode) && a->ld_accum % 512 == 0 && a->ld_accum >= a->L &&
@@ -919,12 +1102,12 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   SRK_REQUIRE(a->counts_bits == 0 || a->counts_bits == 16 || a->counts_bits == 32, "counts_bits must be 16 or 32");
   SRK_REQUIRE(!(a->add_counts || a->use_evidence) || a->counts, "counts missing");
   SRK_REQUIRE(!(a->use_evidence && a->epi.evidence), "evidence given twice (counts and epi.evidence)");
-  const bool sym = a->mode == SRK_CSR_FINAL && a->symmetric;
+  const bool sym = (a->mode == SRK_CSR_FINAL || a->mode == SRK_CSR_FINISH) && a->symmetric;
   if (sym)
     SRK_REQUIRE(a->row_begin == 0 && a->row_end == a->M && a->L == a->M && a->epi.prior == nullptr &&
                     a->epi.diag_offset == 0 && a->ldo >= a->L,
                 "the symmetric second half needs the whole square problem and no prior");
-  if (a->elem == SRK_ELEM_U16 && (a->mode == SRK_CSR_FINAL || finish_mode)) SRK_REQUIRE(a->g_col, "u16 FINAL needs g_col");
+  if (a->elem == SRK_ELEM_U16 && (a->mode == SRK_CSR_FINAL || a->mode == SRK_CSR_FINISH)) SRK_REQUIRE(a->g_col, "u16 FINAL needs g_col");
   if (a->row_end == a->row_begin || a->L == 0) return SRK_OK;
 
   gat::Params p;
@@ -940,7 +1123,8 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   SRK_REQUIRE(p.qmax >= 1.0 && p.qmax <= 65535.0, "qmax must be in 1..65535");
   p.counts = a->counts; p.ld_counts = a->ld_counts; p.counts32 = a->counts_bits == 32;
   p.add_counts = a->add_counts; p.use_evidence = a->use_evidence;
-  if (a->mode == SRK_CSR_FINAL || finish_mode) { p.epi = to_dev(a->epi); p.maxdiff = a->epi.maxdiff; p.maxoff = a->epi.maxoff; }
+  p.upper_only = accum_mode && a->symmetric;
+  if (a->mode == SRK_CSR_FINAL || a->mode == SRK_CSR_FINISH) { p.epi = to_dev(a->epi); p.maxdiff = a->epi.maxdiff; p.maxoff = a->epi.maxoff; }
   const int64_t esz = a->elem == SRK_ELEM_U16 ? 2 : 8;
   // TMA needs 16-byte aligned rows
   p.tma = ((uintptr_t)a->X % 16 == 0) && ((a->ldx * esz) % 16 == 0);
@@ -955,9 +1139,21 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   // 8-byte tile per element in shared memory and takes 16 graph rows per CTA instead of 32.
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = a->row_end - a->row_begin;
+  if (finish_mode && sym) {
+    const int64_t nb = (a->M + gat::kSI - 1) / gat::kSI, total = nb * (nb + 1) / 2;
+    SRK_REQUIRE(total < (1ll << 31), "too many tiles");
+    gat::csr_finish_sym_kernel<<<(unsigned)total, gat::kThreads, 0, st>>>(p);
+    SRK_CUDA_OK(cudaGetLastError());
+    return SRK_OK;
+  }
   if (finish_mode) {
     const int64_t fx = (rows + gat::kFI - 1) / gat::kFI, fy = (a->L + gat::kFR - 1) / gat::kFR;
     SRK_REQUIRE(fy <= 65535, "too many column panels");
+    if (finish_first) {
+      gat::csr_finish_first_kernel<<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
+      SRK_CUDA_OK(cudaGetLastError());
+      return SRK_OK;
+    }
     // three CTAs per SM (80 registers) or four (64, with spills): SRK_CSR_FLAGS & 4 selects four, for A/B runs
     if (p.flags & 4) gat::csr_finish_kernel<4><<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
     else gat::csr_finish_kernel<3><<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);

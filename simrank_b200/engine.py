@@ -381,8 +381,10 @@ class ListSplit:
         ranges = max(1, int(np.ceil(K * 1024 / (range_mb * 2 ** 20))))
         return cls(indptr, indices, K, min_deg, piece, ranges, all_rows)
 
-    def accumulate(self, lib, indices_ptr, x_ptr, ldx: int, L: int, K: int, qmax: float) -> None:
-        """Zero the sums and add every piece's column sums of X[:, :L] (one launch)."""
+    def accumulate(self, lib, indices_ptr, x_ptr, ldx: int, L: int, K: int, qmax: float, upper: bool = False) -> None:
+        """Zero the sums and add every piece's column sums of X[:, :L] (one launch).  ``upper`` (all_rows plans
+        of a square operator): a piece of row i skips the column panels entirely left of column i -- the
+        symmetric second half only needs the pairs r >= i."""
         ld = _round_up(max(L, 1), 512)
         if self._accum is None or self._accum.shape[1] < ld:
             self._accum = torch.empty((self.rows, ld), dtype=torch.int32, device=self.piece_lo.device)
@@ -396,6 +398,7 @@ class ListSplit:
         a.M, a.row_begin, a.row_end = self.pieces, 0, self.pieces
         a.X, a.ldx, a.L, a.K = x_ptr, ldx, L, K
         a.qmax = qmax
+        a.symmetric = 1 if upper else 0
         self.attach(a, pieces=True)
         _lib.check(lib.srk_csr_half(C.byref(a), _stream()), "srk_csr_half(u16, accum)")
 
@@ -476,6 +479,12 @@ class _Half:
             self.version, self._quantized_version = 0, (-1, 0.0)
             # hub rows (tens of thousands of neighbours) are pre-summed in pieces, see ListSplit
             self.split = ListSplit.plan(op.indptr, op.indices, op.K, int(host.deg.max()) if host.deg.size else 0)
+            # Both halves as SRK_CSR_ACCUM over EVERY list + a streaming pass (FINISH_FIRST; symmetric FINISH
+            # over the pairs r >= i): the gather launch carries no tile and no epilogue and runs at the L2
+            # roof (DESIGN.md "K3").  SRK_CSR_VIA_ACCUM=0 keeps the fused launches.
+            self.split_all = None
+            if os.environ.get("SRK_CSR_VIA_ACCUM", "1") == "1" and host.nnz:
+                self.split_all = ListSplit.plan(op.indptr, op.indices, op.K, int(host.deg.max()), all_rows=True)
             return
         self.rho = op.g_host * host.deg                                    # row sums of G
         self.rho_max = float(self.rho.max()) if self.rho.size else 0.0
@@ -665,11 +674,20 @@ class _Half:
         a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
         a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), src.maxoff * guard, 0.0)
         a.qmax = qmax
-        if self.split is not None:
-            self._timed("csr16_accum", lambda: self.split.accumulate(lib, a.indices, a.X, a.ldx, a.L, a.K, qmax))
-            self.split.attach(a)
-        _lib.check(self._timed("csr16_half_first", lambda: lib.srk_csr_half(C.byref(a), _stream())),
-                   "srk_csr_half(u16, first)")
+        via = self.split_all
+
+        def first_via_accum():
+            self._timed("csr16_first_accum", lambda: via.accumulate(lib, a.indices, a.X, a.ldx, a.L, a.K, qmax))
+            a.mode, a.accum, a.ld_accum = _lib.SRK_CSR_FINISH_FIRST, via._accum.data_ptr(), via._accum.shape[1]
+            return self._timed("csr16_first_finish", lambda: lib.srk_csr_half(C.byref(a), _stream()))
+        if via is not None:
+            _lib.check(self._timed("csr16_half_first", first_via_accum), "srk_csr_half(u16, first via accum)")
+        else:
+            if self.split is not None:
+                self._timed("csr16_accum", lambda: self.split.accumulate(lib, a.indices, a.X, a.ldx, a.L, a.K, qmax))
+                self.split.attach(a)
+            _lib.check(self._timed("csr16_half_first", lambda: lib.srk_csr_half(C.byref(a), _stream())),
+                       "srk_csr_half(u16, first)")
         b = _lib.CsrArgs()
         b.elem, b.mode, b.symmetric = _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINAL, 1
         b.indptr, b.indices, b.g = a.indptr, a.indices, a.g
@@ -683,6 +701,16 @@ class _Half:
         b.counts_bits, b.add_counts = 8 * self.counts.element_size(), 1
         b.use_evidence = 1 if self.evidence_from_pattern else 0
         b.epi = self._epilogue()
+
+        def second_via_accum():
+            self._timed("csr16_second_accum",
+                        lambda: via.accumulate(lib, b.indices, b.X, b.ldx, b.L, b.K, qmax, upper=True))
+            b.mode, b.accum, b.ld_accum = _lib.SRK_CSR_FINISH, via._accum.data_ptr(), via._accum.shape[1]
+            return self._timed("csr16_second_finish", lambda: lib.srk_csr_half(C.byref(b), _stream()))
+        if via is not None:
+            _lib.check(self._timed("csr16_half_final", second_via_accum), "srk_csr_half(u16, second via accum)")
+            self.version += 1
+            return
         if self.split is not None:
             self._timed("csr16_accum", lambda: self.split.accumulate(lib, b.indices, b.X, b.ldx, b.L, b.K, qmax))
             self.split.attach(b)

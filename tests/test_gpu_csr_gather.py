@@ -398,6 +398,7 @@ def test_split_lists_through_the_solver(dev, monkeypatch):
     n = 1200
     op, _ = _skewed_graph(rng, n, n, [(5, 1100), (6, 900), (700, 640)])
     mats = []
+    monkeypatch.setenv("SRK_CSR_VIA_ACCUM", "0")            # the fused launches, with and without the hub split
     for min_deg in ("0", "256"):
         monkeypatch.setenv("SRK_SPLIT_MIN", min_deg)
         monkeypatch.setenv("SRK_SPLIT_PIECE", "100")
@@ -469,3 +470,96 @@ def test_second_half_as_accum_plus_finish_is_bit_identical(dev, piece, ranges):
     np.testing.assert_array_equal(res[0][0], res[1][0])
     assert res[0][1] == res[1][1]
     assert res[0][0][5, r0 + 5] == 1.0
+
+
+@pytest.mark.parametrize("piece,ranges", [(16, 1), (100, 3)])
+def test_first_half_as_accum_plus_finish_is_bit_identical(dev, piece, ranges):
+    rng = np.random.default_rng(piece + 5)
+    M, K, L = 150, 900, 700
+    op, A = _skewed_graph(rng, M, K, [(0, 900), (17, 333), (149, 512), (60, 0)])
+    dop = engine.DeviceOperator(op, dev)
+    ldx = engine._round_up(L, 8)
+    X = _u16(rng.integers(0, 65536, (K, ldx), dtype=np.int64)).to(dev)
+    ud = torch.from_numpy(rng.random(L) * 1e-6).to(dev)
+    ob = op.deg * 1e-6 * 65535 + 1e-9
+    ob[7] = 0.0                                            # bound 0: the column is stored as zeros
+    od = torch.from_numpy(ob).to(dev)
+    ldo = engine._round_up(M, 8)
+    outs = []
+    for via_accum in (False, True):
+        out = torch.full((L, ldo), -1, dtype=torch.int16, device=dev)
+        a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FIRST)
+        a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), ldx, L, K, out.data_ptr(), ldo
+        a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+        a.out_bound = _lib.RowBound.of(od.data_ptr(), 1.0, 0.0)
+        if via_accum:
+            sp = engine.ListSplit(dop.indptr, dop.indices, K, 1, piece, ranges, all_rows=True)
+            sp.accumulate(_lib.load(), a.indices, a.X, a.ldx, a.L, a.K, 65535.0)
+            a.mode, a.accum, a.ld_accum = _lib.SRK_CSR_FINISH_FIRST, sp._accum.data_ptr(), sp._accum.shape[1]
+        _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy().view(np.uint16)[:, :M].copy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    assert outs[1].any()
+
+
+@pytest.mark.parametrize("n,density", [(70, 0.3), (300, 0.05), (515, 0.1), (1100, 0.02)])
+@pytest.mark.parametrize("evidence", [False, True])
+def test_symmetric_second_half_as_accum_plus_finish(dev, n, density, evidence):
+    """ACCUM with upper_only (a row's pieces skip the panels left of its diagonal) + the symmetric FINISH:
+    the upper triangle of the full product, reflected -- the reference of test_csr16_final_symmetric."""
+    rng = np.random.default_rng(n + 1)
+    op, dop, tp, ldt, cnt, S_old, unit, gcol, x = _final_case(rng, dev, n, density, evidence)
+    ld = engine._round_up(n, 16)
+    X = _u16(tp).to(dev)
+    out = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+    out[:, :n] = torch.from_numpy(S_old)
+    c16 = torch.from_numpy(cnt.astype(np.uint16).view(np.int16)).to(dev)
+    ud, gd = torch.from_numpy(unit).to(dev), torch.from_numpy(gcol).to(dev)
+    scal = torch.zeros(2, dtype=torch.float64, device=dev)
+    a = _args(dop, _lib.SRK_ELEM_U16, _lib.SRK_CSR_FINISH)
+    a.symmetric = 1
+    a.X, a.ldx, a.L, a.K, a.OUT, a.ldo = X.data_ptr(), ldt, n, n, out.data_ptr(), ld
+    a.in_unit = _lib.RowBound.of(ud.data_ptr(), 1.0, 0.0)
+    a.g_col = gd.data_ptr()
+    a.counts, a.ld_counts, a.counts_bits, a.add_counts, a.use_evidence = c16.data_ptr(), n, 16, 1, int(evidence)
+    a.epi.coef = 0.8
+    a.epi.s_old, a.epi.ld_s_old = out.data_ptr(), ld
+    a.epi.maxdiff, a.epi.maxoff = scal.data_ptr(), scal.data_ptr() + 8
+    sp = engine.ListSplit(dop.indptr, dop.indices, n, 1, 24, 2, all_rows=True)
+    sp._accum = torch.full((n, engine._round_up(n, 512)), -1, dtype=torch.int32, device=dev)   # skipped panels stay garbage
+    sp.accumulate(_lib.load(), a.indices, a.X, a.ldx, a.L, a.K, 65535.0, upper=True)
+    a.accum, a.ld_accum = sp._accum.data_ptr(), sp._accum.shape[1]
+    _lib.check(_lib.load().srk_csr_half(C.byref(a), engine._stream()))
+    torch.cuda.synchronize()
+    want = np.triu(x, 1)
+    want = want + want.T
+    np.fill_diagonal(want, 1.0)
+    got = out[:, :n].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-300)
+    assert np.array_equal(got, got.T)
+    md, mo = scal.tolist()
+    assert md == np.abs(got - S_old).max()
+    off = got.copy()
+    np.fill_diagonal(off, 0.0)
+    assert mo == off.max()
+
+
+def test_csr16_solver_via_accum_matches_the_fused_launches(dev, monkeypatch):
+    rng = np.random.default_rng(78)
+    n = 1300
+    op, _ = _skewed_graph(rng, n, n, [(5, 1100), (6, 900), (700, 640), (9, 0)])
+    mats = []
+    for via in ("0", "1"):
+        monkeypatch.setenv("SRK_CSR_VIA_ACCUM", via)
+        solver = engine.DirectedSolver(engine.DeviceOperator(op, dev), 0.8, mode="csr16")
+        assert (solver.half.split_all is not None) == (via == "1")
+        for _ in range(5):
+            d = solver.step()
+        mats.append((solver.S.cpu().numpy().copy(), d))
+    a, b = mats[0][0], mats[1][0]
+    assert np.array_equal(b, b.T) and (np.diag(b) == 1.0).all()
+    # the same integer sums; the float64 element is rounded in another order, which can move a value across a
+    # quantisation step of the next update (one step of 2^-16 of a row maximum, contracted by C)
+    assert np.abs(a - b).max() <= 5e-8
+    assert abs(mats[0][1] - mats[1][1]) <= 5e-8
