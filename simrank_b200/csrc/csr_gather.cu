@@ -124,6 +124,18 @@ struct Params {
   int64_t tiles_x;             // row tiles of the problem (symmetric second half: triangular 1-D grid)
 };
 
+// uint32 -> double and double -> nearest integer without the conversion instructions (I2F.F64 / FRND / F2I issue
+// at a quarter of the rate of DADD, profiles/r1_micro_fp64_rate.txt): 2^52 + w has w in its low mantissa word.
+__device__ __forceinline__ double u32_to_double(uint32_t w) {
+  return __hiloint2double(0x43300000, (int)w) - 4503599627370496.0;
+}
+// rint(x) clipped to [0, qmax] as uint32, for finite or NaN x (NaN -> 0); qmax is an integer below 2^32, so
+// clipping first gives what rint-then-clip gives
+__device__ __forceinline__ uint32_t rint_clip_u32(double x, double qmax) {
+  x = fmin(fmax(x, 0.0), qmax);
+  return (uint32_t)__double2loint(x + 4503599627370496.0);
+}
+
 __device__ __forceinline__ uint32_t load_count(const void* base, int64_t idx, int c32) {
   return c32 ? reinterpret_cast<const uint32_t*>(base)[idx] : (uint32_t)reinterpret_cast<const uint16_t*>(base)[idx];
 }
@@ -200,7 +212,7 @@ struct Acc<uint16_t, TC> {
     }
   }
   __device__ __forceinline__ uint32_t raw(int j) const { return (j & 1) ? ah[j >> 1] : aw[j >> 1] - (ah[j >> 1] << 16); }
-  __device__ __forceinline__ double val(int j) const { return (double)raw(j); }
+  __device__ __forceinline__ double val(int j) const { return u32_to_double(raw(j)); }
   // start from per-column sums computed elsewhere (hub rows): s[c] for the panel's columns, 32-byte aligned
   __device__ __forceinline__ void load_sums(const uint32_t* s, int lane) {
 #pragma unroll
@@ -460,10 +472,8 @@ csr_gather_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
           for (int j = 0; j < A::kCols; ++j) {
             const int cl = col_of<E, TC>(j, lane);
             const int64_t c = c0 + cl;
-            double q = c < p.L ? rint(acc.val(j) * row_bound(p.in_unit, c) * inv) : 0.0;
-            if (!(q > 0.0)) q = 0.0;
-            if (q > p.qmax) q = p.qmax;
-            tile[cl * SM::kPitch + il] = (TileT)(unsigned)q;
+            const uint32_t q = c < p.L ? rint_clip_u32(acc.val(j) * row_bound(p.in_unit, c) * inv, p.qmax) : 0u;
+            tile[cl * SM::kPitch + il] = (TileT)q;
           }
         } else {
           const double gi = p.g[row];
@@ -656,14 +666,45 @@ __device__ __forceinline__ void prefetch_block(const void* base, int64_t pitch_b
     prefetch_l2(reinterpret_cast<const uint8_t*>(base) + (int64_t)(t / per_row) * pitch_bytes + (t % per_row) * 128);
 }
 constexpr int kFI = 64, kFR = 128, kFPitch = kFI + 1, kFBatch = 8;
+// shared memory of csr_finish_kernel: the transposed sums, then (fast path) the S_old and counts tiles, which
+// arrive by cp.async -- 80 KB per CTA requested in the first microsecond, no register held while they fly
+constexpr int kFTileBytes = kFR * kFPitch * 4, kFSoBytes = kFR * kFI * 8, kFCnBytes = kFR * kFI * 2;
+constexpr int kFSmemBytes = kFTileBytes + kFSoBytes + kFCnBytes;
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int kCtasPerSM>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM)
 csr_finish_kernel(const Params p) {
-  __shared__ uint32_t tile[kFR * kFPitch];
+  extern __shared__ __align__(16) uint8_t fin_smem[];
+  uint32_t* tile = reinterpret_cast<uint32_t*>(fin_smem);
+  double* so_s = reinterpret_cast<double*>(fin_smem + kFTileBytes);
+  uint16_t* cn_s = reinterpret_cast<uint16_t*>(fin_smem + kFTileBytes + kFSoBytes);
   __shared__ double red[2][kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i0 = p.row_begin + (int64_t)blockIdx.x * kFI, c0 = (int64_t)blockIdx.y * kFR;
   const int rows_here = (int)min((int64_t)kFI, p.row_end - i0);
+  // Fast path, CTA-uniform: a full tile of the usual operands (16-bit counts, S_old present, everything aligned for
+  // 16-byte accesses, no evidence array / prior).
+  const bool fast = rows_here == kFI && c0 + kFR <= p.L && p.vec_aligned && (p.ldo & 1) == 0 && (p.epi.ld_s_old & 1) == 0 &&
+                    (p.ld_counts & 7) == 0 && (i0 & 7) == 0 && p.epi.s_old && p.counts && !p.counts32 &&
+                    !p.epi.evidence && !p.epi.prior && !(p.flags & 16);
+  if (fast) {
+    // S_old[c0 .. c0+128, i0 .. i0+64) and counts, row by row: 32 / 8 chunks of 16 bytes per row
+    const double* sb = p.epi.s_old + c0 * p.epi.ld_s_old + i0;
+    const uint16_t* cb = reinterpret_cast<const uint16_t*>(p.counts) + c0 * p.ld_counts + i0;
+#pragma unroll
+    for (int k = 0; k < kFSoBytes / 16 / kThreads; ++k) {
+      const int ch = threadIdx.x + kThreads * k, row = ch >> 5, c16 = ch & 31;
+      cp_async16(so_s + row * kFI + 2 * c16, sb + row * p.epi.ld_s_old + 2 * c16);
+    }
+#pragma unroll
+    for (int k = 0; k < kFCnBytes / 16 / kThreads; ++k) {
+      const int ch = threadIdx.x + kThreads * k, row = ch >> 3, c16 = ch & 7;
+      cp_async16(cn_s + row * kFI + 8 * c16, cb + row * p.ld_counts + 8 * c16);
+    }
+  }
 
   // ---- in: 8 graph rows per warp, 16 bytes per lane and row, all eight loads issued before the first use
   {
@@ -681,6 +722,7 @@ csr_finish_kernel(const Params p) {
       tile[(4 * lane + 2) * kFPitch + il] = v[q].z; tile[(4 * lane + 3) * kFPitch + il] = v[q].w;
     }
   }
+  if (fast) cp_async_wait_all();
   __syncthreads();
 
   // ---- out: 16 result rows per warp, lane l owns the graph rows i0 + 2 l, i0 + 2 l + 1
@@ -691,6 +733,36 @@ csr_finish_kernel(const Params p) {
   const bool vec = in1 && p.vec_aligned && ((p.ldo | p.epi.ld_s_old) & 1) == 0 && (i & 1) == 0;
   const bool cvec = in1 && !p.counts32 && (p.ld_counts & 1) == 0 && (i & 1) == 0 && (reinterpret_cast<uintptr_t>(p.counts) & 3) == 0;
   double* out = reinterpret_cast<double*>(p.OUT);
+  // (The general loop below spends more instructions on predicates and 64-bit address arithmetic than on the
+  // element, and keeps only what 80 registers hold in flight: 3.2 TB/s, profiles/r2_ncu_full_cfg5_s1_final.json.)
+  if (fast) {
+    const int rb0 = warp * (kFR / kWarps);
+    double* o_p = out + (c0 + rb0) * p.ldo + i;
+    const double* fu_p = p.in_unit.vec ? p.in_unit.vec + c0 + rb0 : nullptr;
+    const double* gc_p = p.g_col + c0 + rb0;
+    const int64_t diag = i - p.epi.diag_offset - c0 - rb0;             // result row (relative) that holds (r, r) for x = 0
+    const uint32_t* t_p = tile + rb0 * kFPitch + 2 * lane;
+    const double2* so_p = reinterpret_cast<const double2*>(so_s + rb0 * kFI) + lane;
+    const uint32_t* cn_p = reinterpret_cast<const uint32_t*>(cn_s + rb0 * kFI) + lane;
+    const bool addc = p.add_counts != 0, ev = p.use_evidence != 0;
+#pragma unroll 4
+    for (int rb = 0; rb < kFR / kWarps; ++rb) {
+      const double2 so = so_p[rb * (kFI / 2)];
+      const uint32_t cw = cn_p[rb * (kFI / 2)];
+      const double fu = fu_p ? fu_p[rb] * p.in_unit.mul + p.in_unit.add : p.in_unit.add, gc = gc_p[rb];
+      const uint32_t c0w = cw & 0xffffu, c1w = cw >> 16;
+      double v0 = final_value_u16(g0, gc, u32_to_double(t_p[rb * kFPitch]), fu, addc ? u32_to_double(c0w) : 0.0, p.epi.coef,
+                                  ev ? evidence_factor(c0w) : 1.0);
+      double v1 = final_value_u16(g1, gc, u32_to_double(t_p[rb * kFPitch + 1]), fu, addc ? u32_to_double(c1w) : 0.0, p.epi.coef,
+                                  ev ? evidence_factor(c1w) : 1.0);
+      if (diag == rb) v0 = 1.0; else omax = fmax(omax, v0);
+      if (diag + 1 == rb) v1 = 1.0; else omax = fmax(omax, v1);
+      const double d0 = fabs(v0 - so.x), d1 = fabs(v1 - so.y);
+      if (d0 > dmax) dmax = d0;                                        // NaN compares false: ignored like SimRank.py:74
+      if (d1 > dmax) dmax = d1;
+      __stcs(reinterpret_cast<double2*>(o_p + rb * p.ldo), make_double2(v0, v1));
+    }
+  } else
   for (int rb = warp * (kFR / kWarps); rb < (warp + 1) * (kFR / kWarps); rb += kFBatch) {
     double2 so[kFBatch];
     uint32_t c_lo[kFBatch], c_hi[kFBatch];                     // (16-bit counts: both in c_lo, split when used)
@@ -793,10 +865,8 @@ csr_finish_first_kernel(const Params p) {
       const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
-        double t = rint((double)w[x] * u[x] * inv[q]);               // the expression of MODE_FIRST
-        if (!(t > 0.0)) t = 0.0;
-        if (t > p.qmax) t = p.qmax;
-        tile[(4 * lane + x) * kP + il] = (uint16_t)(unsigned)t;
+        // the expression of MODE_FIRST, rint(D unit / (bound / qmax)) clipped, without conversion instructions
+        tile[(4 * lane + x) * kP + il] = (uint16_t)rint_clip_u32(u32_to_double(w[x]) * u[x] * inv[q], p.qmax);
       }
     }
   }
@@ -819,9 +889,16 @@ csr_finish_first_kernel(const Params p) {
 // are read / written along r, the mirror image goes through a shared-memory transposition, so both copies
 // leave as whole 512-byte runs (the fused symmetric launch scatters the mirror 8 bytes at a time).
 constexpr int kSI = 64;
-__global__ void __launch_bounds__(kThreads, 3)
+// shared memory: the transposition tile of the mirror store, then (fast path) the tiles of the sums, S_old and
+// counts, staged by cp.async like in csr_finish_kernel
+constexpr int kSTileBytes = kSI * (kSI + 1) * 8, kSSmemBytes = kSTileBytes + kSI * kSI * (4 + 8 + 2);
+__global__ void __launch_bounds__(kThreads, 2)
 csr_finish_sym_kernel(const Params p) {
-  __shared__ double tile[kSI * (kSI + 1)];
+  extern __shared__ __align__(16) uint8_t fin_smem[];
+  double* tile = reinterpret_cast<double*>(fin_smem);
+  uint32_t* acc_s = reinterpret_cast<uint32_t*>(fin_smem + kSTileBytes);
+  double* so_s = reinterpret_cast<double*>(fin_smem + kSTileBytes + kSI * kSI * 4);
+  uint16_t* cn_s = reinterpret_cast<uint16_t*>(fin_smem + kSTileBytes + kSI * kSI * 12);
   __shared__ double red[2][kWarps];
   constexpr int kP = kSI + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -841,6 +918,54 @@ csr_finish_sym_kernel(const Params p) {
   double* out = reinterpret_cast<double*>(p.OUT);
   double dmax = 0.0, omax = 0.0;
   constexpr int kRows = kSI / kWarps;                                  // 8 rows per warp, all loads first
+  // Fast path, CTA-uniform: a full tile right of the diagonal blocks with the usual operands
+  const bool fast = bi != br && r0 + kSI <= p.L && i0 + kSI <= p.row_end && p.vec_aligned && (p.ldo & 1) == 0 &&
+                    (p.epi.ld_s_old & 1) == 0 && (p.ld_counts & 7) == 0 && p.epi.s_old && p.counts && !p.counts32 &&
+                    !p.epi.evidence && !(p.flags & 16);
+  if (fast) {
+    const uint32_t* ab = p.accum + i0 * p.ld_accum + r0;
+    const double* sb = p.epi.s_old + i0 * p.epi.ld_s_old + r0;
+    const uint16_t* cb = reinterpret_cast<const uint16_t*>(p.counts) + i0 * p.ld_counts + r0;
+#pragma unroll
+    for (int k = 0; k < kSI * kSI * 4 / 16 / kThreads; ++k) {
+      const int ch = threadIdx.x + kThreads * k, row = ch >> 4, c16 = ch & 15;
+      cp_async16(acc_s + row * kSI + 4 * c16, ab + row * p.ld_accum + 4 * c16);
+    }
+#pragma unroll
+    for (int k = 0; k < kSI * kSI * 8 / 16 / kThreads; ++k) {
+      const int ch = threadIdx.x + kThreads * k, row = ch >> 5, c16 = ch & 31;
+      cp_async16(so_s + row * kSI + 2 * c16, sb + row * p.epi.ld_s_old + 2 * c16);
+    }
+#pragma unroll
+    for (int k = 0; k < kSI * kSI * 2 / 16 / kThreads; ++k) {
+      const int ch = threadIdx.x + kThreads * k, row = ch >> 3, c16 = ch & 7;
+      cp_async16(cn_s + row * kSI + 8 * c16, cb + row * p.ld_counts + 8 * c16);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const bool addc = p.add_counts != 0, ev = p.use_evidence != 0;
+#pragma unroll 4
+    for (int q = 0; q < kRows; ++q) {
+      const int il = warp * kRows + q;
+      const int64_t i = i0 + il;
+      const uint2 sum = *reinterpret_cast<const uint2*>(acc_s + il * kSI + 2 * lane);
+      const double2 so = *reinterpret_cast<const double2*>(so_s + il * kSI + 2 * lane);
+      const uint32_t cw = *reinterpret_cast<const uint32_t*>(cn_s + il * kSI + 2 * lane);
+      const uint32_t c0w = cw & 0xffffu, c1w = cw >> 16;
+      const double gi = p.g[i];
+      const double v0 = final_value_u16(gi, gc0, u32_to_double(sum.x), fu0, addc ? u32_to_double(c0w) : 0.0, p.epi.coef,
+                                        ev ? evidence_factor(c0w) : 1.0);
+      const double v1 = final_value_u16(gi, gc1, u32_to_double(sum.y), fu1, addc ? u32_to_double(c1w) : 0.0, p.epi.coef,
+                                        ev ? evidence_factor(c1w) : 1.0);
+      omax = fmax(omax, fmax(v0, v1));
+      const double d0 = fabs(v0 - so.x), d1 = fabs(v1 - so.y);
+      if (d0 > dmax) dmax = d0;                                        // NaN compares false: ignored like SimRank.py:74
+      if (d1 > dmax) dmax = d1;
+      __stcs(reinterpret_cast<double2*>(out + i * p.ldo + r), make_double2(v0, v1));
+      tile[(2 * lane) * kP + il] = v0;
+      tile[(2 * lane + 1) * kP + il] = v1;
+    }
+  } else {
   uint2 sum[kRows];
   double2 so[kRows];
   uint32_t cw[kRows], ch[kRows];
@@ -891,6 +1016,7 @@ csr_finish_sym_kernel(const Params p) {
     }
     tile[(2 * lane) * kP + il] = v[0];
     tile[(2 * lane + 1) * kP + il] = v[1];
+  }
   }
   __syncthreads();
   // mirror: element (c, i) for c > i; a warp writes 8 rows c of the result, lane l the columns i0 + 2 l, + 1
@@ -967,10 +1093,7 @@ quantize_transpose_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t
     unsigned q = 0u;
     if (r < R && k < K) {
       const double v = (zero_diag_offset >= 0 && k == r + zero_diag_offset) ? 0.0 : V[r * ldv + k];
-      double x = rint(v * inv[rr]);
-      if (!(x > 0.0)) x = 0.0;
-      if (x > qmax) x = qmax;
-      q = (unsigned)x;
+      q = rint_clip_u32(v * inv[rr], qmax);
     }
     t[tx][rr] = (uint16_t)q;
   }
@@ -1035,10 +1158,7 @@ quantize_sym_u16_kernel(const double* __restrict__ V, int64_t ldv, int64_t n, in
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
       const double val = (zero_diag_offset >= 0 && k == r + x + zero_diag_offset) ? 0.0 : (x ? v[j].y : v[j].x);
-      double y = rint(val * inv[x]);
-      if (!(y > 0.0)) y = 0.0;
-      if (y > qmax) y = qmax;
-      out |= (uint32_t)y << (16 * x);
+      out |= rint_clip_u32(val * inv[x], qmax) << (16 * x);
     }
     *reinterpret_cast<uint32_t*>(XT + k * ldxt + r) = out;
   }
@@ -1142,7 +1262,8 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
   if (finish_mode && sym) {
     const int64_t nb = (a->M + gat::kSI - 1) / gat::kSI, total = nb * (nb + 1) / 2;
     SRK_REQUIRE(total < (1ll << 31), "too many tiles");
-    gat::csr_finish_sym_kernel<<<(unsigned)total, gat::kThreads, 0, st>>>(p);
+    SRK_CUDA_OK(cudaFuncSetAttribute(gat::csr_finish_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gat::kSSmemBytes));
+    gat::csr_finish_sym_kernel<<<(unsigned)total, gat::kThreads, gat::kSSmemBytes, st>>>(p);
     SRK_CUDA_OK(cudaGetLastError());
     return SRK_OK;
   }
@@ -1154,9 +1275,11 @@ extern "C" int srk_csr_half(const srk_csr_args* a, void* stream) {
       SRK_CUDA_OK(cudaGetLastError());
       return SRK_OK;
     }
-    // three CTAs per SM (80 registers) or four (64, with spills): SRK_CSR_FLAGS & 4 selects four, for A/B runs
-    if (p.flags & 4) gat::csr_finish_kernel<4><<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
-    else gat::csr_finish_kernel<3><<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, 0, st>>>(p);
+    // two CTAs per SM: the S_old / counts tiles of the fast path are staged in shared memory (113 KB per CTA);
+    // three (80 registers) and four CTAs (64, spills) were tried without staging: profiles/r2_csr_shapes_finish_ctas.jsonl
+    auto kern = gat::csr_finish_kernel<2>;
+    SRK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gat::kFSmemBytes));
+    kern<<<dim3((unsigned)fx, (unsigned)fy), gat::kThreads, gat::kFSmemBytes, st>>>(p);
     SRK_CUDA_OK(cudaGetLastError());
     return SRK_OK;
   }
