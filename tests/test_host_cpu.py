@@ -188,3 +188,64 @@ def test_run_loop_semantics():
     pairs = iter([(0.5, 0.00001), (0.00001, 0.5), (0.00001, 0.00001)])
     applied, conv, _ = run_loop(lambda: next(pairs), 100, 1e-4, True)
     assert (applied, conv) == (3, True)                 # both groups must converge (SimRank.py:289)
+
+
+@pytest.mark.parametrize("all_rows", [False, True])
+def test_list_split_plan_partitions_the_neighbour_lists(all_rows):
+    """engine.ListSplit (host logic of SRK_CSR_ACCUM): the pieces tile exactly the lists they replace, stay
+    inside one range of X rows, respect the piece length, come range by range with the long ones first; a
+    piece that is a whole list is marked 'store' (negative slot), everything else 'add'."""
+    import torch
+    from simrank_b200 import engine
+    rng = np.random.default_rng(0)
+    M, K, min_deg, piece, ranges = 60, 1000, 100, 64, 3
+    deg = rng.integers(0, 40, size=M)
+    deg[[3, 10, 49, 0, 5]] = [700, 333, 1000, 100, 0]
+    lists = [np.sort(rng.choice(K, size=d, replace=False)) for d in deg]
+    indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    indices = np.concatenate(lists).astype(np.int32)
+    sp = engine.ListSplit(torch.from_numpy(indptr), torch.from_numpy(indices), K, min_deg, piece, ranges, all_rows)
+    split = (deg >= 1) if all_rows else (deg >= min_deg)
+    hubs = np.nonzero(split)[0]
+    assert sp.rows == (M if all_rows else hubs.size)
+    lo, hi, sl = sp.piece_lo.numpy(), sp.piece_hi.numpy(), sp.piece_slot.numpy()
+    span = -(-K // ranges)
+    cover, pieces_of, prev = np.zeros(indices.size, int), np.zeros(M, int), (-1, 0)
+    for a, b, s in zip(lo, hi, sl):
+        slot = s if s >= 0 else -s - 1
+        row = slot if all_rows else hubs[slot]
+        assert 0 < b - a <= piece and indptr[row] <= a and b <= indptr[row + 1]
+        rg = indices[a:b] // span
+        assert rg.min() == rg.max()
+        assert (rg[0], -(b - a)) >= prev                       # range by range, long pieces first
+        prev = (rg[0], -(b - a))
+        cover[a:b] += 1
+        pieces_of[row] += 1
+        assert (s < 0) == ((a, b) == (indptr[row], indptr[row + 1]))
+    for r in range(M):
+        assert (cover[indptr[r]:indptr[r + 1]] == int(split[r])).all()
+    # what is left for the FIRST / FINAL launch: nothing of the split rows, everything of the others
+    np.testing.assert_array_equal(sp.row_hi.numpy() - sp.row_lo.numpy(), np.where(split, 0, deg))
+    want_slot = np.where(split, np.arange(M) if all_rows else np.cumsum(split) - 1, -1)
+    np.testing.assert_array_equal(sp.slot.numpy(), want_slot)
+    if all_rows:                                               # rows that are added to, or never written, start from zero
+        assert set(sp.zero_slots.tolist()) == set(np.nonzero(pieces_of != 1)[0].tolist())
+    else:
+        assert sp.zero_slots is None
+
+
+def test_list_split_plan_thresholds(monkeypatch):
+    import torch
+    from simrank_b200 import engine
+    indptr = torch.tensor([0, 3, 3, 300], dtype=torch.int64)
+    indices = torch.arange(300, dtype=torch.int32) % 50
+    for k in ("SRK_SPLIT_MIN", "SRK_SPLIT_PIECE", "SRK_SPLIT_RANGE_MB"):
+        monkeypatch.delenv(k, raising=False)
+    assert engine.ListSplit.plan(indptr, indices, 50, 255) is None            # no row long enough
+    sp = engine.ListSplit.plan(indptr, indices, 50, 297)
+    assert (sp.min_deg, sp.piece, sp.ranges, sp.rows) == (256, 512, 1, 1)     # the panel fits in L2
+    sp = engine.ListSplit.plan(indptr, indices, 138493, 2000)                 # it does not: 142 MB of 1 KB segments
+    assert (sp.min_deg, sp.piece, sp.ranges) == (1024, 256, 5) and sp.rows == 0
+    monkeypatch.setenv("SRK_SPLIT_MIN", "0")
+    assert engine.ListSplit.plan(indptr, indices, 50, 297) is None
+    assert engine.ListSplit.plan(indptr, indices, 50, 297, all_rows=True).rows == 3
