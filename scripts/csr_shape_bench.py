@@ -105,7 +105,8 @@ def first_case(dev, op, rows_src, world, name):
     deg = torch.from_numpy(op.deg.astype(np.float64)).to(dev)
     send = torch.zeros((world, engine._round_up(rows_src, 16), per_out), dtype=torch.int16, device=dev)
     lib = _lib.load()
-    split = engine.ListSplit.plan(dop.indptr, dop.indices, n_in, int(op.deg.max()))
+    via_accum = os.environ.get("SRK_FIRST_VIA_ACCUM", "1") == "1" and n_in * 1024 <= 64 * 2 ** 20
+    split = engine.ListSplit.plan(dop.indptr, dop.indices, n_in, int(op.deg.max()), all_rows=via_accum)
 
     def run():
         if split is not None:
@@ -120,7 +121,9 @@ def first_case(dev, op, rows_src, world, name):
             a.OUT, a.ldo = send[p].data_ptr() - 2 * lo, per_out
             a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
             a.out_bound = _lib.RowBound.of(deg.data_ptr(), 1e-4, 0.0)
-            if split is not None:
+            if split is not None and via_accum:
+                a.mode, a.accum, a.ld_accum = _lib.SRK_CSR_FINISH_FIRST, split._accum.data_ptr(), split._accum.shape[1]
+            elif split is not None:
                 split.attach(a)
             _lib.check(lib.srk_csr_half(C.byref(a), engine._stream()))
     ms = timed(run)

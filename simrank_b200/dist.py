@@ -746,6 +746,12 @@ class ShardedCsr16Half(ShardedCsrHalf):
         self.split_all = None
         if os.environ.get("SRK_FINAL_VIA_ACCUM", "1") == "1" and op.nnz:
             self.split_all = ListSplit.plan(self.indptr, self.indices, self.n_in, int(op.deg.max()), all_rows=True)
+        # The first half goes the same way (ACCUM over every list, then SRK_CSR_FINISH_FIRST per destination
+        # block) when a 1 KB-wide panel of its operand stays in L2; when it does not (S2 of cfg5: 142 MB) most
+        # lists span several ranges and every piece would be an atomic add: there the hub split + the fused
+        # launch stay.  SRK_FIRST_VIA_ACCUM=0 keeps the fused launch everywhere.
+        self.first_via_accum = (self.split_all is not None and self.n_in * 1024 <= 64 * 2 ** 20 and
+                                os.environ.get("SRK_FIRST_VIA_ACCUM", "1") == "1")
 
     _dense_pattern = ShardedHalf._dense_pattern
     _pattern_counts = ShardedHalf._pattern_counts
@@ -795,7 +801,10 @@ class ShardedCsr16Half(ShardedCsrHalf):
             if src.rows == 0:
                 return
             xq, unit = src._quantized(qmax)
-            if self.split is not None:                              # one launch for the hub rows of every block
+            via = self.split_all if self.first_via_accum else None
+            if via is not None:                                     # one gather launch for every graph row
+                via.accumulate(lib, self.indices.data_ptr(), xq.data_ptr(), src.ldxt, src.rows, self.n_in, qmax)
+            elif self.split is not None:                            # one launch for the hub rows of every block
                 self.split.accumulate(lib, self.indices.data_ptr(), xq.data_ptr(), src.ldxt, src.rows, self.n_in, qmax)
             for p in range(P):
                 lo, hi = self.plan.start(p), self.plan.stop(p)
@@ -808,7 +817,9 @@ class ShardedCsr16Half(ShardedCsrHalf):
                 a.in_unit = _lib.RowBound.of(unit.data_ptr(), 1.0, 0.0)
                 a.out_bound = _lib.RowBound.of(self.deg_dev.data_ptr(), bound_mul, 0.0)
                 a.qmax = qmax
-                if self.split is not None:
+                if via is not None:
+                    a.mode, a.accum, a.ld_accum = _lib.SRK_CSR_FINISH_FIRST, via._accum.data_ptr(), via._accum.shape[1]
+                elif self.split is not None:
                     self.split.attach(a)
                 _lib.check(lib.srk_csr_half(C.byref(a), _stream()), "srk_csr_half(u16, first)")
         self._timed("csr16_half_first", first)

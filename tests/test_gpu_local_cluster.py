@@ -72,9 +72,10 @@ def test_bipartite_csr16_shards_with_split_hub_rows_are_bit_identical(monkeypatc
     (engine.ListSplit).  Integer sums in another order: the sharded result does not change by a bit."""
     df = synth.config_frame("cfg5", scale=1 / 32)
     out = []
-    for min_deg, via_accum in (("0", "0"), ("64", "0"), ("64", "1")):
+    for min_deg, via_accum, first in (("0", "0", "0"), ("64", "0", "0"), ("64", "1", "0"), ("64", "1", "1")):
         monkeypatch.setenv("SRK_SPLIT_MIN", min_deg)
         monkeypatch.setenv("SRK_FINAL_VIA_ACCUM", via_accum)       # second half as ACCUM + FINISH
+        monkeypatch.setenv("SRK_FIRST_VIA_ACCUM", first)           # first half as ACCUM + FINISH_FIRST
         monkeypatch.setenv("SRK_SPLIT_PIECE", "48")
         monkeypatch.setenv("SRK_SPLIT_RANGE_MB", "1")
         res = _fit_sharded(3, lambda g: M.BipartitleSimRankPP(mode="csr16", sharded=g, gather="local"),
