@@ -639,6 +639,10 @@ class ShardedCsrHalf:
     def _reduce_scalars(self):
         _all_reduce_max(self.scal, self.group)
 
+    def _library(self):
+        """The C ABI (replaced by the numpy emulator in the CPU tests)."""
+        return _lib.load()
+
     _timed = ShardedHalf._timed
 
     # ---- one update ----------------------------------------------------------------------------
@@ -687,7 +691,7 @@ class ShardedCsrHalf:
                 b.counts, b.ld_counts = self.counts.data_ptr(), self.counts.stride(0)
                 b.counts_bits, b.use_evidence = 8 * self.counts.element_size(), 1
                 b.epi = e
-                _lib.check(_lib.load().srk_csr_half(C.byref(b), _stream()), "srk_csr_half(f64, second)")
+                _lib.check(self._library().srk_csr_half(C.byref(b), _stream()), "srk_csr_half(f64, second)")
                 return
             self._launch_csr(0, self.n_out, self._recv.data_ptr(), per_out, self.rows, self.S.data_ptr(), self.ld, e)
         self._timed("csr_half_final", second)
@@ -763,8 +767,8 @@ class ShardedCsr16Half(ShardedCsrHalf):
         if self.Xq is None:
             self.Xq = torch.zeros((self.n_out, self.ldxt), dtype=torch.int16, device=self.device)
         if self._quantized_version != (self.version, qmax) and self.rows:
-            _lib.check(_lib.load().srk_quantize_rows_u16(_ptr(self.S), self.ld, self.rows, self.n_out, self.row0,
-                                                         _ptr(self.Xq), self.ldxt, _ptr(self.unit), qmax, 0, _stream()),
+            _lib.check(self._library().srk_quantize_rows_u16(_ptr(self.S), self.ld, self.rows, self.n_out, self.row0,
+                                                             _ptr(self.Xq), self.ldxt, _ptr(self.unit), qmax, 0, _stream()),
                        "srk_quantize_rows_u16")
         self._quantized_version = (self.version, qmax)
         return self.Xq, self.unit
@@ -789,7 +793,7 @@ class ShardedCsr16Half(ShardedCsrHalf):
         self.slices_used.append(2)
         self._err_next = kappa * src.err + slice_delta(2, self.coef, 1.0, self.rho_max, src.maxoff) * 65536.0 / (qmax + 1.0)
         self.scal.zero_()
-        lib = _lib.load()
+        lib = self._library()
         P, per_in, per_out = self.world, src.per, self.per
         if self._send16 is None or self._send16.shape != (P, per_in, per_out):
             self._send16 = torch.zeros((P, per_in, per_out), dtype=torch.int16, device=self.device)

@@ -50,6 +50,8 @@ def _ptr(t):
 
 
 def _stream():
+    if not torch.cuda.is_available():          # CPU emulation of the host logic (tests/test_dist_gloo.py): no stream
+        return C.c_void_p(0)
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -1,5 +1,6 @@
-"""Host-memory emulator of ``srk_x2_half``, ``srk_slice_rows_max_f64`` and ``srk_csr_half_f64``
-(include/simrank_b200.h) in numpy.  TEST ONLY.
+"""Host-memory emulator of ``srk_x2_half``, ``srk_slice_rows_max_f64``, ``srk_csr_half_f64``, ``srk_csr_half``
+(the calls of the row-sharded fixed-point CSR solver) and ``srk_quantize_rows_u16`` (include/simrank_b200.h)
+in numpy.  TEST ONLY.
 
 It interprets the very structs the product passes to the CUDA library, but on CPU tensors, so the
 multi-rank host logic (shard offsets, block assignment of the symmetric update, staging layouts,
@@ -176,3 +177,127 @@ def srk_csr_half_f64(indptr, indices, g, M, row_begin, row_end, X_ptr, ldx, L, O
                 m = _f64(epi.maxdiff, 1)
                 m[0] = max(m[0], d.max())
     block(OUT_ptr, C.c_double, ldo)[:, :] = val
+
+
+# ------------------------------------------------------------------ fixed-point CSR path (srk_csr_half, U16)
+def srk_quantize_rows_u16(V_ptr, ldv, R, K, zero_diag_offset, XT_ptr, ldxt, unit_ptr, qmax, symmetric):
+    """unit[r] = max_k V[r, k] / qmax, XT[k, r] = rint(V[r, k] * (1 / unit[r])) clipped (header: srk_quantize_rows_u16)."""
+    qmax = 65535.0 if qmax == 0 else float(qmax)
+    V = _view(V_ptr, C.c_double, R, K, ldv).copy()
+    V[np.isnan(V) | (V < 0)] = 0.0
+    if zero_diag_offset >= 0:
+        r = np.arange(R)
+        ok = r + zero_diag_offset < K
+        V[r[ok], r[ok] + zero_diag_offset] = 0.0
+    unit = V.max(axis=1) / qmax if K else np.zeros(R)
+    _f64(unit_ptr, R)[:] = unit
+    with np.errstate(divide="ignore"):
+        inv = np.where(unit > 0, 1.0 / np.where(unit > 0, unit, 1.0), 0.0)
+    q = np.clip(np.rint(V * inv[:, None]), 0, qmax).astype(np.uint16)
+    XT = _view(XT_ptr, C.c_uint16, K, ldxt, ldxt)
+    XT[:, :R] = q.T
+    XT[:, R:] = 0
+
+
+def _lists(a, rows):
+    """Neighbour list of every row in ``rows``: split bounds when given, else indptr."""
+    if a.row_lo:
+        lo = np.ctypeslib.as_array((C.c_int64 * a.M).from_address(a.row_lo))
+        hi = np.ctypeslib.as_array((C.c_int64 * a.M).from_address(a.row_hi))
+    else:
+        ptr = np.ctypeslib.as_array((C.c_int64 * (a.M + 1)).from_address(a.indptr))
+        lo, hi = ptr[:-1], ptr[1:]
+    idx = np.ctypeslib.as_array((C.c_int32 * max(int(hi.max(initial=0)), 1)).from_address(a.indices))
+    return [idx[lo[r]:hi[r]] for r in rows]
+
+
+def srk_csr_half(a: _lib.CsrArgs) -> None:
+    """numpy statement of srk_csr_half for what the row-sharded solvers call: U16 FIRST / FINAL / ACCUM / FINISH /
+    FINISH_FIRST (transposed store; the symmetric variants belong to the single-GPU solver) and F64 FINAL with
+    the evidence taken from ``counts``."""
+    u16 = a.elem == _lib.SRK_ELEM_U16
+    qmax = 65535.0 if a.qmax == 0 else float(a.qmax)
+    L, K = a.L, a.K
+    rows = np.arange(a.row_begin, a.row_end)
+    if rows.size == 0 or L == 0:
+        return
+    assert not a.symmetric or a.mode == _lib.SRK_CSR_ACCUM, "symmetric second halves are not emulated"
+    acc = None
+    if a.accum:
+        slots = 1 + max(rows.max(), a.M)                              # enough rows for any slot in use
+        acc = _view(a.accum, C.c_uint32, slots, a.ld_accum, a.ld_accum)
+    if a.mode in (_lib.SRK_CSR_FIRST, _lib.SRK_CSR_FINAL, _lib.SRK_CSR_ACCUM):
+        X = _view(a.X, C.c_uint16 if u16 else C.c_double, K, L, a.ldx)
+        X = X.astype(np.int64) if u16 else X
+        D = np.stack([X[nb].sum(axis=0) if nb.size else np.zeros(L, dtype=X.dtype) for nb in _lists(a, rows)])
+    if a.mode == _lib.SRK_CSR_ACCUM:
+        slot = np.ctypeslib.as_array((C.c_int32 * a.M).from_address(a.accum_slot))[rows]
+        for t, s in enumerate(slot):
+            if s >= 0:
+                acc[s, :L] += D[t].astype(np.uint32)
+            else:
+                acc[-s - 1, :L] = D[t].astype(np.uint32)
+        return
+    if a.mode in (_lib.SRK_CSR_FINISH, _lib.SRK_CSR_FINISH_FIRST):
+        D = acc[rows, :L].astype(np.int64)
+    elif u16 and a.accum_slot:                                        # FIRST / FINAL start from the pre-summed pieces
+        slot = np.ctypeslib.as_array((C.c_int32 * a.M).from_address(a.accum_slot))[rows]
+        D = D + np.where(slot[:, None] >= 0, acc[np.maximum(slot, 0), :L].astype(np.int64), 0)
+    assert not u16 or D.max(initial=0) < (1 << 32), "32-bit sums overflow: qmax too large for the degree"
+
+    def block(ptr, ctype, ld):                                        # [L rows r/c, columns row_begin..row_end) of a caller matrix
+        return _view(ptr + a.row_begin * C.sizeof(ctype), ctype, L, rows.size, ld)
+
+    unit = _bound(a.in_unit, L) if u16 else None
+    if a.mode in (_lib.SRK_CSR_FIRST, _lib.SRK_CSR_FINISH_FIRST):
+        assert u16
+        ob = _bound(a.out_bound, a.row_end)[rows]
+        with np.errstate(divide="ignore"):
+            inv = np.where(ob > 0, qmax / np.where(ob > 0, ob, 1.0), 0.0)
+        q = np.clip(np.rint((D.astype(np.float64) * unit[None, :]) * inv[:, None]), 0, qmax)
+        block(a.OUT, C.c_uint16, a.ldo)[:, :] = q.T.astype(np.uint16)
+        return
+    # ---- FINAL / FINISH: value at (r, i), r = column of X = output row
+    e = a.epi
+    g = _f64(a.g, a.row_end)[rows]
+    cnt = None
+    if a.counts:
+        cnt = block(a.counts, C.c_uint32 if a.counts_bits == 32 else C.c_uint16, a.ld_counts).astype(np.int64)
+    if u16:
+        gc = _f64(a.g_col, L)
+        inner = D.T.astype(np.float64) * unit[:, None] + (cnt.astype(np.float64) if a.add_counts else 0.0)
+        val = ((g[None, :] * gc[:, None]) * inner) * e.coef
+    else:
+        val = (D.T * g[None, :]) * e.coef
+    if a.use_evidence:
+        val = val * (1 - 0.5 ** np.minimum(cnt, 60).astype(np.float64))
+    elif e.evidence:
+        val = val * (1 - 0.5 ** np.minimum(block(e.evidence, C.c_uint8, e.ld_evidence).astype(np.float64), 60.0))
+    if e.prior:
+        val = (1 - e.lambda_) * val + e.lambda_ * block(e.prior, C.c_double, e.ld_prior)
+    diag = (np.arange(L)[:, None] + e.diag_offset) == rows[None, :]
+    val = np.where(diag, 1.0, val)
+    if e.maxoff:
+        m = _f64(e.maxoff, 1)
+        m[0] = max(m[0], val[~diag].max(initial=0.0))
+    if e.s_old and e.maxdiff:
+        d = np.abs(val - block(e.s_old, C.c_double, e.ld_s_old))
+        d = d[~np.isnan(d)]
+        if d.size:
+            m = _f64(e.maxdiff, 1)
+            m[0] = max(m[0], d.max())
+    block(a.OUT, C.c_double, a.ldo)[:, :] = val
+
+
+class Library:
+    """Stand-in for the ctypes library object with the two entry points the row-sharded fixed-point solver calls."""
+
+    @staticmethod
+    def srk_csr_half(ref, stream):
+        srk_csr_half(ref._obj)
+        return 0
+
+    @staticmethod
+    def srk_quantize_rows_u16(V, ldv, R, K, zd, XT, ldxt, unit, qmax, symmetric, stream):
+        srk_quantize_rows_u16(V.value, ldv, R, K, zd, XT.value, ldxt, unit.value, qmax, symmetric)
+        return 0

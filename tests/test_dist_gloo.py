@@ -61,14 +61,32 @@ class CpuCsrHalf(sdist.ShardedCsrHalf):
         return fn()
 
 
+class CpuCsr16Half(sdist.ShardedCsr16Half):
+    """ShardedCsr16Half (uint16 gather: quantiser, split neighbour lists, ACCUM + FINISH / FINISH_FIRST, the float64
+    fallback update) with host tensors and the emulated library."""
+
+    _init_identity = CpuCsrHalf._init_identity
+    _launch_csr = CpuCsrHalf._launch_csr
+    _dense_pattern = CpuHalf._dense_pattern
+    _launch = CpuHalf._launch
+
+    def _library(self):
+        return abi_emulator.Library
+
+    def _timed(self, name, fn):
+        return fn()
+
+
 class CpuDirected(sdist.ShardedDirectedSolver):
     half_cls = CpuHalf
     csr_half_cls = CpuCsrHalf
+    csr16_half_cls = CpuCsr16Half
 
 
 class CpuBipartite(sdist.ShardedBipartiteSolver):
     half_cls = CpuHalf
     csr_half_cls = CpuCsrHalf
+    csr16_half_cls = CpuCsr16Half
 
 
 def _free_port():
@@ -134,6 +152,46 @@ def _worker(rank, world, port, case, out):
             with pytest.raises(NotImplementedError, match="symmetric prior"):
                 drivers.directed_solver(op, 0.8, prior=np.triu(np.ones((260, 260))), lbd=0.5, device=dev)
             out.put((rank, worst, 0.0, sol.h1.rows))
+        elif case.startswith("directed_csr16"):
+            # the fixed-point CSR path, what 'auto' picks for sparse graphs on N GPUs: hub rows so that the split
+            # neighbour lists are exercised; "_fused" keeps the fused launches instead of ACCUM + streaming pass
+            if case.endswith("_fused"):
+                os.environ.update(SRK_FINAL_VIA_ACCUM="0", SRK_FIRST_VIA_ACCUM="0")
+            os.environ.update(SRK_SPLIT_MIN="40", SRK_SPLIT_PIECE="16")
+            rng = np.random.default_rng(14)
+            mask = rng.random((230, 230)) < 0.03
+            mask[7] = rng.random(230) < 0.6                           # two hub rows
+            mask[101] = rng.random(230) < 0.4
+            mask[55] = False                                          # and an empty one
+            op = graph.operator_from_edges(*np.nonzero(mask), 230, 230)
+            sol = CpuDirected(op, 0.8, mode="csr16", device=dev)
+            assert sol.mode == "csr16" and sol.half.split is not None
+            assert (sol.half.split_all is not None) == (not case.endswith("_fused"))
+            diffs = [sol.step() for _ in range(5)]
+            G = op.to_dense()
+            So, _, _ = orc.simrank(G, 0.8, 5, 0.0)
+            err = float(np.abs(sol.S.numpy() - So).max())
+            assert 2 in sol.half.slices_used                           # the uint16 updates really ran
+            Sa, Sb, ref_diffs = np.zeros((230, 230)), np.eye(230), []
+            for _ in range(5):
+                Sa, Sb = Sb, 0.8 * G @ Sb @ G.T
+                np.fill_diagonal(Sb, 1)
+                ref_diffs.append(float(np.abs(Sb - Sa).max()))
+            out.put((rank, err, float(np.abs(np.array(diffs) - np.array(ref_diffs)).max()), sol.half.rows))
+        elif case == "bipartite_csr16":
+            # BipartiteSimRankPP shape (n1 != n2), evidence taken from the pattern counts, fixed-point CSR path
+            os.environ.update(SRK_SPLIT_MIN="30", SRK_SPLIT_PIECE="16", SRK_SPLIT_RANGE_MB="0.05")
+            u, i = synth.bipartite_edges(130, 77, 1500, 1.0, 5)
+            op12, op21 = graph.operator_from_edges(u, i, 130, 77), graph.operator_from_edges(i, u, 77, 130)
+            sol = CpuBipartite(op12, op21, 0.8, 0.7, mode="csr16", device=dev, evidence1_from_pattern=True,
+                               evidence2_from_pattern=True)
+            assert sol.mode == "csr16" and sol.h2.split is not None and sol.h2.split.ranges > 1
+            for _ in range(3):
+                sol.step()
+            W1, W2 = op12.to_dense(), op21.to_dense()
+            s1o, s2o, _, _ = orc.bipartite_simrank_pp(W1, W2, orc.evidence(W1), orc.evidence(W2), 0.8, 0.7, 3, 0.0)
+            err = float(max(np.abs(sol.S1.numpy() - s1o).max(), np.abs(sol.S2.numpy() - s2o).max()))
+            out.put((rank, err, 0.0, sol.h1.rows))
         elif case == "directed_csr":
             # negative weight sums: rows of G with a negative scale (SimRank.py:45,49) -- float64 CSR path
             frm, to = synth.directed_edges(210, 1800, 0.8, 12)
@@ -205,7 +263,9 @@ def _worker(rank, world, port, case, out):
 
 @pytest.mark.parametrize("world,case", [(2, "directed"), (3, "directed"), (4, "directed"), (2, "bipartite"),
                                         (3, "bipartite"), (4, "bipartite"), (2, "directed_csr"),
-                                        (3, "bipartite_csr"), (4, "bipartite_csr"), (2, "drivers")])
+                                        (3, "bipartite_csr"), (4, "bipartite_csr"), (2, "drivers"),
+                                        (2, "directed_csr16"), (3, "directed_csr16"), (2, "directed_csr16_fused"),
+                                        (3, "bipartite_csr16")])
 def test_sharded_solver_matches_oracle(world, case):
     ctx = mp.get_context("spawn")
     out = ctx.SimpleQueue()
@@ -221,7 +281,7 @@ def test_sharded_solver_matches_oracle(world, case):
     for rank, err, derr, rows in results:
         assert err <= 1e-6, (rank, err)                 # fixed-point planes: north-star bound
         assert derr <= 1e-6
-    n = {"directed": 300, "directed_csr": 210, "drivers": 120}.get(case, 130)
+    n = {"directed": 300, "directed_csr": 210, "drivers": 120, "directed_csr16": 230, "directed_csr16_fused": 230}.get(case, 130)
     assert sum(r[3] for r in results) == n              # the row blocks tile the matrix
 
 
